@@ -1,0 +1,660 @@
+//---------------------------------------------------------------------------//
+// Reference-side adapter: flattens the reference's host-side CoreParams
+// (/root/reference/src/celeritas/global/CoreTrackData.hh:65-106) into the
+// column arrays of a B200 problem image. This is the code a maintainer of the
+// reference would add to hand a constructed problem across the C-ABI; here it
+// also produces the committed image fixtures under data/images/.
+//---------------------------------------------------------------------------//
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "corecel/data/Collection.hh"
+#include "corecel/sys/ActionRegistry.hh"
+#include "orange/OrangeData.hh"
+#include "orange/OrangeParams.hh"
+#include "celeritas/em/model/BetheHeitlerModel.hh"
+#include "celeritas/em/model/EPlusGGModel.hh"
+#include "celeritas/em/model/KleinNishinaModel.hh"
+#include "celeritas/em/model/LivermorePEModel.hh"
+#include "celeritas/em/model/MollerBhabhaModel.hh"
+#include "celeritas/em/model/RelativisticBremModel.hh"
+#include "celeritas/em/model/SeltzerBergerModel.hh"
+#include "celeritas/em/params/FluctuationParams.hh"
+#include "celeritas/em/params/UrbanMscParams.hh"
+#include "celeritas/geo/GeoMaterialParams.hh"
+#include "celeritas/geo/GeoParams.hh"
+#include "celeritas/global/alongstep/AlongStepGeneralLinearAction.hh"
+#include "celeritas/global/alongstep/AlongStepUniformMscAction.hh"
+#include "celeritas/mat/MaterialParams.hh"
+#include "celeritas/phys/CutoffParams.hh"
+#include "celeritas/phys/ParticleParams.hh"
+#include "celeritas/phys/PhysicsParams.hh"
+#include "celeritas/random/RngParams.hh"
+#include "celeritas/track/SimParams.hh"
+#include "celeritas/track/TrackInitParams.hh"
+
+#include "../../celeritas_b200/host/Image.hh"
+#include "Problem.hh"
+
+using namespace celeritas;
+
+namespace celerref
+{
+namespace
+{
+using U32 = std::vector<uint32_t>;
+using F64 = std::vector<double>;
+using F32 = std::vector<float>;
+using U8 = std::vector<uint8_t>;
+constexpr uint32_t invalid = 0xffffffffu;
+
+template<class T, Ownership W, MemSpace M, class I>
+Span<T const> all(Collection<T, W, M, I> const& c)
+{
+    if (c.empty())
+        return {};
+    return c[AllItems<T, M>{}];
+}
+
+template<class Id>
+uint32_t raw(Id id)
+{
+    return id ? id.unchecked_get() : invalid;
+}
+
+//---------------------------------------------------------------------------//
+void export_geometry(HostCRef<OrangeParamsData> const& g, b200::Image& img)
+{
+    img.put("geo.scalars",
+            U32{g.scalars.max_depth,
+                g.scalars.max_faces,
+                g.scalars.max_intersections,
+                g.scalars.max_logic_depth});
+    img.put("geo.tol", F64{g.scalars.tol.rel, g.scalars.tol.abs});
+
+    // Universes
+    {
+        U8 types;
+        U32 indices;
+        for (auto t : all(g.universe_types))
+            types.push_back(static_cast<uint8_t>(t));
+        for (auto i : all(g.universe_indices))
+            indices.push_back(i);
+        img.put("geo.universe_type", types);
+        img.put("geo.universe_index", indices);
+        U32 so, vo;
+        for (auto v : all(g.universe_indexer_data.surfaces))
+            so.push_back(v);
+        for (auto v : all(g.universe_indexer_data.volumes))
+            vo.push_back(v);
+        img.put("geo.universe_surface_offset", so);
+        img.put("geo.universe_volume_offset", vo);
+    }
+
+    // Flat pools (copied verbatim; records index into them)
+    {
+        U32 lsi, lvi, rid, logic;
+        for (auto v : all(g.local_surface_ids))
+            lsi.push_back(raw(v));
+        for (auto v : all(g.local_volume_ids))
+            lvi.push_back(raw(v));
+        for (auto v : all(g.real_ids))
+            rid.push_back(raw(v));
+        for (auto v : all(g.logic_ints))
+            logic.push_back(v);
+        img.put("geo.local_surface_ids", lsi);
+        img.put("geo.local_volume_ids", lvi);
+        img.put("geo.real_ids", rid);
+        img.put("geo.logic_ints", logic);
+        F64 reals(all(g.reals).begin(), all(g.reals).end());
+        img.put("geo.reals", reals);
+        U8 st;
+        for (auto v : all(g.surface_types))
+            st.push_back(static_cast<uint8_t>(v));
+        img.put("geo.surface_types", st);
+    }
+
+    // Volume records
+    {
+        U32 fb, fe, lb, le, mi, fl, da;
+        for (auto const& v : all(g.volume_records))
+        {
+            fb.push_back(v.faces.begin()->unchecked_get());
+            fe.push_back(v.faces.end()->unchecked_get());
+            lb.push_back(v.logic.begin()->unchecked_get());
+            le.push_back(v.logic.end()->unchecked_get());
+            mi.push_back(v.max_intersections);
+            fl.push_back(v.flags);
+            da.push_back(raw(v.daughter_id));
+        }
+        img.put("geo.vol_face_begin", fb);
+        img.put("geo.vol_face_end", fe);
+        img.put("geo.vol_logic_begin", lb);
+        img.put("geo.vol_logic_end", le);
+        img.put("geo.vol_max_isect", mi);
+        img.put("geo.vol_flags", fl);
+        img.put("geo.vol_daughter", da);
+    }
+    // Connectivity records
+    {
+        U32 nb, ne;
+        for (auto const& c : all(g.connectivity_records))
+        {
+            nb.push_back(c.neighbors.begin()->unchecked_get());
+            ne.push_back(c.neighbors.end()->unchecked_get());
+        }
+        img.put("geo.conn_begin", nb);
+        img.put("geo.conn_end", ne);
+    }
+    // Daughters and transforms
+    {
+        U32 du, dt;
+        for (auto const& d : all(g.daughters))
+        {
+            du.push_back(raw(d.universe_id));
+            dt.push_back(raw(d.transform_id));
+        }
+        img.put("geo.daughter_universe", du);
+        img.put("geo.daughter_transform", dt);
+        U8 tt;
+        U32 to;
+        for (auto const& t : all(g.transforms))
+        {
+            tt.push_back(static_cast<uint8_t>(t.type));
+            to.push_back(raw(t.data_offset));
+        }
+        img.put("geo.transform_type", tt);
+        img.put("geo.transform_offset", to);
+    }
+    // BIH storage
+    {
+        F32 bb;
+        for (auto const& b : all(g.bih_tree_data.bboxes))
+        {
+            for (int i = 0; i < 3; ++i)
+                bb.push_back(b.lower()[i]);
+            for (int i = 0; i < 3; ++i)
+                bb.push_back(b.upper()[i]);
+        }
+        img.put("geo.bih_bboxes", bb);
+        U32 lv;
+        for (auto v : all(g.bih_tree_data.local_volume_ids))
+            lv.push_back(raw(v));
+        img.put("geo.bih_local_volume_ids", lv);
+        U32 ip, ia, ilc, irc;
+        F32 ilp, irp;
+        using Edge = celeritas::detail::BIHInnerNode::Edge;
+        for (auto const& n : all(g.bih_tree_data.inner_nodes))
+        {
+            ip.push_back(raw(n.parent));
+            ia.push_back(static_cast<uint32_t>(n.axis));
+            ilp.push_back(n.bounding_planes[Edge::left].position);
+            ilc.push_back(raw(n.bounding_planes[Edge::left].child));
+            irp.push_back(n.bounding_planes[Edge::right].position);
+            irc.push_back(raw(n.bounding_planes[Edge::right].child));
+        }
+        img.put("geo.bih_inner_parent", ip);
+        img.put("geo.bih_inner_axis", ia);
+        img.put("geo.bih_inner_left_pos", ilp);
+        img.put("geo.bih_inner_left_child", ilc);
+        img.put("geo.bih_inner_right_pos", irp);
+        img.put("geo.bih_inner_right_child", irc);
+        U32 lp, lb, le;
+        for (auto const& n : all(g.bih_tree_data.leaf_nodes))
+        {
+            lp.push_back(raw(n.parent));
+            lb.push_back(n.vol_ids.begin()->unchecked_get());
+            le.push_back(n.vol_ids.end()->unchecked_get());
+        }
+        img.put("geo.bih_leaf_parent", lp);
+        img.put("geo.bih_leaf_vol_begin", lb);
+        img.put("geo.bih_leaf_vol_end", le);
+    }
+    // Simple unit records: one row per unit
+    {
+        U32 rows;
+        for (auto const& u : all(g.simple_units))
+        {
+            rows.push_back(u.surfaces.types.begin()->unchecked_get());
+            rows.push_back(u.surfaces.types.end()->unchecked_get());
+            rows.push_back(u.surfaces.data_offsets.begin()->unchecked_get());
+            rows.push_back(u.connectivity.begin()->unchecked_get());
+            // volumes: ItemMap over a contiguous range of VolumeRecordId
+            rows.push_back(u.volumes.size() ? raw(u.volumes[LocalVolumeId{0}])
+                                            : 0);
+            rows.push_back(u.volumes.size());
+            rows.push_back(raw(u.background));
+            rows.push_back(u.simple_safety ? 1 : 0);
+            auto const& t = u.bih_tree;
+            rows.push_back(t.bboxes.size() ? raw(t.bboxes[LocalVolumeId{0}])
+                                           : 0);
+            rows.push_back(t.inner_nodes.begin()->unchecked_get());
+            rows.push_back(t.inner_nodes.size());
+            rows.push_back(t.leaf_nodes.begin()->unchecked_get());
+            rows.push_back(t.leaf_nodes.size());
+            rows.push_back(t.inf_volids.begin()->unchecked_get());
+            rows.push_back(t.inf_volids.size());
+            rows.push_back(0);
+        }
+        img.put("geo.simple_units", rows);  // 16 u32 per unit
+    }
+    // Rect arrays
+    {
+        U32 rows;
+        for (auto const& r : all(g.rect_arrays))
+        {
+            rows.push_back(r.daughters.size()
+                               ? raw(r.daughters[LocalVolumeId{0}])
+                               : 0);
+            rows.push_back(r.daughters.size());
+            for (int ax = 0; ax < 3; ++ax)
+                rows.push_back(r.dims[ax]);
+            for (int ax = 0; ax < 3; ++ax)
+            {
+                rows.push_back(r.grid[ax].begin()->unchecked_get());
+                rows.push_back(r.grid[ax].end()->unchecked_get());
+            }
+            for (int i = 0; i < 4; ++i)
+                rows.push_back(r.surface_indexer_data.offsets[i]);
+            rows.push_back(0);
+        }
+        img.put("geo.rect_arrays", rows);  // 16 u32 per array
+    }
+}
+
+//---------------------------------------------------------------------------//
+void export_materials(HostCRef<MaterialParamsData> const& m, b200::Image& img)
+{
+    U32 el_z;
+    F64 el;  // 6 per element
+    for (auto const& e : all(m.elements))
+    {
+        el_z.push_back(e.atomic_number.unchecked_get());
+        el.push_back(e.atomic_mass.value());
+        el.push_back(e.cbrt_z);
+        el.push_back(e.cbrt_zzp);
+        el.push_back(e.log_z);
+        el.push_back(e.coulomb_correction);
+        el.push_back(e.mass_radiation_coeff);
+    }
+    img.put("mat.element_z", el_z);
+    img.put("mat.element_reals", el);
+    U32 ce;
+    F64 cf;
+    for (auto const& c : all(m.elcomponents))
+    {
+        ce.push_back(raw(c.element));
+        cf.push_back(c.fraction);
+    }
+    img.put("mat.elcomp_element", ce);
+    img.put("mat.elcomp_fraction", cf);
+    U32 mb, me, ms;
+    F64 mr;  // 8 per material
+    for (auto const& r : all(m.materials))
+    {
+        mb.push_back(r.elements.begin()->unchecked_get());
+        me.push_back(r.elements.end()->unchecked_get());
+        ms.push_back(static_cast<uint32_t>(r.matter_state));
+        mr.push_back(r.number_density);
+        mr.push_back(r.temperature);
+        mr.push_back(r.zeff);
+        mr.push_back(r.density);
+        mr.push_back(r.electron_density);
+        mr.push_back(r.rad_length);
+        mr.push_back(r.mean_exc_energy.value());
+        mr.push_back(r.log_mean_exc_energy.value());
+    }
+    img.put("mat.material_elcomp_begin", mb);
+    img.put("mat.material_elcomp_end", me);
+    img.put("mat.material_state", ms);
+    img.put("mat.material_reals", mr);
+    img.put_scalar<uint32_t>("mat.max_element_components",
+                             m.max_element_components);
+}
+
+//---------------------------------------------------------------------------//
+void export_physics(HostCRef<PhysicsParamsData> const& p,
+                    uint32_t num_materials,
+                    b200::Image& img)
+{
+    auto const& sc = p.scalars;
+    uint32_t const np = p.process_groups.size();
+    uint32_t const P = sc.max_particle_processes;
+    img.put("phys.dims", U32{np, P, num_materials, sc.num_models});
+    img.put("phys.scalars_f64",
+            F64{sc.min_range,
+                sc.max_step_over_range,
+                sc.min_eprime_over_e,
+                sc.lowest_electron_energy.value(),
+                sc.linear_loss_limit,
+                sc.fixed_step_limiter,
+                sc.lambda_limit,
+                sc.range_factor,
+                sc.safety_factor,
+                sc.secondary_stack_factor});
+    img.put("phys.scalars_u32",
+            U32{sc.model_to_action,
+                sc.num_models,
+                static_cast<uint32_t>(sc.step_limit_algorithm),
+                raw(sc.fixed_step_action)});
+
+    // Grids
+    {
+        U32 gsz, gpr, gvo;
+        F64 gfr, gde, gba;
+        for (auto const& g : all(p.value_grids))
+        {
+            gsz.push_back(g.log_energy.size);
+            gfr.push_back(g.log_energy.front);
+            gba.push_back(g.log_energy.back);
+            gde.push_back(g.log_energy.delta);
+            gpr.push_back(g.prime_index);
+            gvo.push_back(g.value.begin()->unchecked_get());
+        }
+        img.put("phys.grid_size", gsz);
+        img.put("phys.grid_log_front", gfr);
+        img.put("phys.grid_log_back", gba);
+        img.put("phys.grid_log_delta", gde);
+        img.put("phys.grid_prime", gpr);
+        img.put("phys.grid_value_offset", gvo);
+        F64 reals(all(p.reals).begin(), all(p.reals).end());
+        img.put("phys.reals", reals);
+    }
+
+    auto grid_of_table = [&](ValueTable const& table, uint32_t idx) -> uint32_t {
+        if (!table || idx >= table.grids.size())
+            return invalid;
+        auto ref = table.grids[idx];
+        if (!ref)
+            return invalid;
+        return raw(p.value_grid_ids[ref]);
+    };
+
+    U32 pp_num(np), pp_eloss(np), pp_at_rest(np);
+    U32 pp_process(np * P, invalid);
+    // [vgt][particle][ppid][material]
+    U32 pp_grid(3 * np * P * num_materials, invalid);
+    U8 pp_integral(np * P, 0);
+    F64 pp_emax(np * P * num_materials, 0.0);
+    U32 pp_model_begin(np * P, 0), pp_model_count(np * P, 0);
+    // per-ppid flattened model bounds
+    F64 pm_energy;  // (count+1) bounds per ppid, concatenated
+    U32 pm_energy_begin(np * P, 0);
+    U32 pm_pmid;  // particle-model ids, concatenated per ppid
+
+    for (uint32_t ip = 0; ip < np; ++ip)
+    {
+        ProcessGroup const& pg = p.process_groups[ParticleId{ip}];
+        pp_num[ip] = pg.size();
+        pp_eloss[ip] = raw(pg.eloss_ppid);
+        pp_at_rest[ip] = pg.has_at_rest;
+        for (uint32_t pp = 0; pp < pg.size(); ++pp)
+        {
+            uint32_t row = ip * P + pp;
+            pp_process[row] = raw(p.process_ids[pg.processes[pp]]);
+            for (int vgt = 0; vgt < 3; ++vgt)
+            {
+                ValueTable const& table
+                    = p.value_tables[pg.tables[ValueGridType(vgt)][pp]];
+                for (uint32_t m = 0; m < num_materials; ++m)
+                {
+                    pp_grid[((vgt * np + ip) * P + pp) * num_materials + m]
+                        = grid_of_table(table, m);
+                }
+            }
+            IntegralXsProcess const& ixs = p.integral_xs[pg.integral_xs[pp]];
+            if (ixs)
+            {
+                pp_integral[row] = 1;
+                for (uint32_t m = 0; m < num_materials; ++m)
+                {
+                    pp_emax[row * num_materials + m]
+                        = p.reals[ixs.energy_max_xs[m]];
+                }
+            }
+            ModelGroup const& mg = p.model_groups[pg.models[pp]];
+            pp_model_begin[row] = pm_pmid.size();
+            pp_model_count[row] = mg.model.size();
+            pm_energy_begin[row] = pm_energy.size();
+            for (auto e : p.reals[mg.energy])
+                pm_energy.push_back(e);
+            for (auto pmid : p.pmodel_ids[mg.model])
+                pm_pmid.push_back(raw(pmid));
+        }
+    }
+    img.put("phys.pp_num", pp_num);
+    img.put("phys.pp_eloss_ppid", pp_eloss);
+    img.put("phys.pp_has_at_rest", pp_at_rest);
+    img.put("phys.pp_process", pp_process);
+    img.put("phys.pp_grid", pp_grid);
+    img.put("phys.pp_integral", pp_integral);
+    img.put("phys.pp_energy_max_xs", pp_emax);
+    img.put("phys.pp_model_begin", pp_model_begin);
+    img.put("phys.pp_model_count", pp_model_count);
+    img.put("phys.pm_energy", pm_energy);
+    img.put("phys.pm_energy_begin", pm_energy_begin);
+    img.put("phys.pm_pmid", pm_pmid);
+
+    // Particle-model -> model id, and per-(pmid, material) element xs grids
+    {
+        uint32_t npm = p.model_ids.size();
+        U32 model_id(npm);
+        U32 elsel_begin(npm * num_materials, invalid);
+        U32 elsel_count(npm * num_materials, 0);
+        U32 elsel_grid;
+        for (uint32_t i = 0; i < npm; ++i)
+        {
+            ParticleModelId pmid{i};
+            model_id[i] = raw(p.model_ids[pmid]);
+            ModelXsTable const& mx = p.model_xs[pmid];
+            if (!mx)
+                continue;
+            for (uint32_t m = 0; m < num_materials; ++m)
+            {
+                auto ref = mx.material[m];
+                if (!ref)
+                    continue;
+                ValueTableId tid = p.value_table_ids[ref];
+                if (!tid)
+                    continue;
+                ValueTable const& table = p.value_tables[tid];
+                if (!table)
+                    continue;
+                elsel_begin[i * num_materials + m] = elsel_grid.size();
+                elsel_count[i * num_materials + m] = table.grids.size();
+                for (uint32_t e = 0; e < table.grids.size(); ++e)
+                    elsel_grid.push_back(grid_of_table(table, e));
+            }
+        }
+        img.put("phys.pmid_model", model_id);
+        img.put("phys.elsel_begin", elsel_begin);
+        img.put("phys.elsel_count", elsel_count);
+        img.put("phys.elsel_grid", elsel_grid);
+    }
+
+    // Hardwired models
+    {
+        auto const& h = p.hardwired;
+        img.put("phys.hardwired",
+                U32{raw(h.photoelectric),
+                    raw(h.livermore_pe),
+                    raw(h.positron_annihilation),
+                    raw(h.eplusgg)});
+        img.put_scalar<double>("phys.photoelectric_table_thresh",
+                               h.photoelectric ? h.photoelectric_table_thresh.value()
+                                               : 0.0);
+    }
+}
+
+//---------------------------------------------------------------------------//
+void export_models(Problem const& prob, b200::Image& img)
+{
+    PhysicsParams const& phys = *prob.core->physics();
+    U32 model_kind(phys.num_models(), 0);
+    std::string labels;
+    for (auto mid : range(ModelId{phys.num_models()}))
+    {
+        auto const& model = *phys.model(mid);
+        labels += std::string(model.label()) + "\n";
+        if (auto* kn = dynamic_cast<KleinNishinaModel const*>(&model))
+        {
+            auto const& d = kn->host_ref();
+            img.put("model.kn.ids", U32{raw(d.ids.electron), raw(d.ids.gamma)});
+            img.put_scalar<double>("model.kn.inv_electron_mass",
+                                   d.inv_electron_mass);
+            img.put_scalar<uint32_t>("model.kn.action",
+                                     kn->action_id().unchecked_get());
+        }
+    }
+    img.put_string("model.labels", labels);
+}
+
+}  // namespace
+
+//---------------------------------------------------------------------------//
+void export_image(Problem const& prob, std::string const& path)
+{
+    b200::Image img;
+    CoreParams const& core = *prob.core;
+    auto const& ref = core.host_ref();
+
+    img.put_string("config", prob.config.dump());
+
+    // Core scalars and the action table
+    {
+        auto const& s = ref.scalars;
+        img.put("core.actions",
+                U32{raw(s.boundary_action),
+                    raw(s.propagation_limit_action),
+                    raw(s.tracking_cut_action),
+                    raw(s.along_step_user_action),
+                    raw(s.along_step_neutral_action)});
+        std::string labels;
+        U32 order;
+        auto const& reg = *core.action_reg();
+        for (auto aid : range(ActionId{reg.num_actions()}))
+        {
+            auto const& a = *reg.action(aid);
+            labels += std::string(a.label()) + "\n";
+            auto* step = dynamic_cast<CoreStepActionInterface const*>(&a);
+            order.push_back(step ? static_cast<uint32_t>(step->order())
+                                 : invalid);
+        }
+        img.put_string("core.action_labels", labels);
+        img.put("core.action_order", order);
+    }
+
+    export_geometry(ref.geometry, img);
+    {
+        // volume -> material
+        U32 vm;
+        for (auto m : all(ref.geo_mats.materials))
+            vm.push_back(raw(m));
+        img.put("geomat.volume_material", vm);
+        // volume labels (for detector maps / diagnostics)
+        std::string labels;
+        auto const& geo = *core.geometry();
+        for (auto v : range(VolumeId{geo.volumes().size()}))
+            labels += geo.volumes().at(v).name + "\n";
+        img.put_string("geo.volume_labels", labels);
+    }
+    export_materials(ref.materials, img);
+
+    // Particles
+    {
+        F64 mass, charge, decay;
+        U8 matter;
+        for (auto v : all(ref.particles.mass))
+            mass.push_back(v.value());
+        for (auto v : all(ref.particles.charge))
+            charge.push_back(v.value());
+        for (auto v : all(ref.particles.decay_constant))
+            decay.push_back(v);
+        for (auto v : all(ref.particles.matter))
+            matter.push_back(static_cast<uint8_t>(v));
+        img.put("particle.mass", mass);
+        img.put("particle.charge", charge);
+        img.put("particle.decay_constant", decay);
+        img.put("particle.matter", matter);
+        U32 pdg;
+        std::string names;
+        auto const& pp = *core.particle();
+        for (auto pid : range(ParticleId{pp.size()}))
+        {
+            pdg.push_back(static_cast<uint32_t>(pp.id_to_pdg(pid).get()));
+            names += pp.id_to_label(pid) + "\n";
+        }
+        img.put("particle.pdg", pdg);
+        img.put_string("particle.names", names);
+    }
+    // Cutoffs
+    {
+        auto const& c = ref.cutoffs;
+        F64 energy, range_;
+        for (auto const& pc : all(c.cutoffs))
+        {
+            energy.push_back(pc.energy.value());
+            range_.push_back(pc.range);
+        }
+        img.put("cutoff.energy", energy);
+        img.put("cutoff.range", range_);
+        U32 idx;
+        for (auto v : all(c.id_to_index))
+            idx.push_back(v);
+        img.put("cutoff.id_to_index", idx);
+        img.put("cutoff.scalars",
+                U32{c.num_particles,
+                    c.num_materials,
+                    c.apply_post_interaction ? 1u : 0u,
+                    raw(c.ids.gamma),
+                    raw(c.ids.electron),
+                    raw(c.ids.positron)});
+    }
+    export_physics(ref.physics, ref.materials.materials.size(), img);
+    export_models(prob, img);
+
+    // RNG
+    {
+        U32 rng;
+        rng.push_back(ref.rng.seed[0]);
+        for (auto const& poly : ref.rng.jump)
+            for (auto w : poly)
+                rng.push_back(w);
+        for (auto const& poly : ref.rng.jump_subsequence)
+            for (auto w : poly)
+                rng.push_back(w);
+        img.put("rng.params", rng);  // seed, jump[32][5], jump_subsequence[32][5]
+    }
+    // Sim
+    {
+        U32 loop;
+        F64 thresh;
+        for (auto const& l : all(ref.sim.looping))
+        {
+            loop.push_back(l.max_subthreshold_steps);
+            loop.push_back(l.max_steps);
+            thresh.push_back(l.threshold_energy.value());
+        }
+        img.put("sim.looping_steps", loop);
+        img.put("sim.looping_energy", thresh);
+    }
+    // Track init
+    img.put("init.scalars",
+            U32{ref.init.capacity,
+                ref.init.max_events,
+                static_cast<uint32_t>(ref.init.track_order)});
+
+    // Detector map for SimpleCalo
+    {
+        std::string names;
+        for (auto const& n : prob.calo_volumes)
+            names += n + "\n";
+        img.put_string("calo.volumes", names);
+    }
+
+    img.write(path);
+}
+}  // namespace celerref

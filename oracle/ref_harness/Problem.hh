@@ -1,0 +1,45 @@
+//---------------------------------------------------------------------------//
+// TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+//
+// A "Problem" is the reference's CoreParams built the way celer-sim builds it
+// (/root/reference/app/celer-sim/Runner.cc:281-442), except that the physics
+// ImportData comes from the JSON fixtures under data/physics (decoded from the
+// reference's own .root exports by tools/rootlite.py) instead of ROOT/Geant4,
+// neither of which exists in this image.
+//---------------------------------------------------------------------------//
+#pragma once
+
+#include <memory>
+#include <string>
+#include <vector>
+#include <nlohmann/json.hpp>
+
+#include "celeritas/global/CoreParams.hh"
+#include "celeritas/io/ImportData.hh"
+#include "celeritas/user/SimpleCalo.hh"
+#include "celeritas/user/StepCollector.hh"
+
+namespace celerref
+{
+struct Problem
+{
+    nlohmann::json config;
+    celeritas::ImportData imported;
+    std::shared_ptr<celeritas::CoreParams> core;
+    std::shared_ptr<celeritas::SimpleCalo> calo;
+    std::shared_ptr<celeritas::StepCollector> collector;
+    std::vector<std::string> calo_volumes;
+    bool has_msc{false};
+    bool has_fluct{false};
+    bool has_field{false};
+};
+
+// Fill ImportData from the rootlite JSON schema
+void import_from_json(nlohmann::json const& j, celeritas::ImportData* out);
+
+// Build from a JSON configuration string
+std::unique_ptr<Problem> build_problem(nlohmann::json const& config);
+
+// Write the flattened problem image consumed by the B200 loader
+void export_image(Problem const& p, std::string const& path);
+}  // namespace celerref

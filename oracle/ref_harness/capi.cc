@@ -1,0 +1,363 @@
+//---------------------------------------------------------------------------//
+// TEST INFRASTRUCTURE ONLY. C API over the reference's own host Stepper so
+// that Python tests (ctypes) and bench.py's CPU baseline can drive it.
+// Reference surface used: Stepper<MemSpace::host>
+// (/root/reference/src/celeritas/global/Stepper.hh:82-190).
+//---------------------------------------------------------------------------//
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <string>
+#include <vector>
+#include <omp.h>
+#include <nlohmann/json.hpp>
+
+#include "corecel/io/Logger.hh"
+#include "corecel/sys/ActionRegistry.hh"
+#include "corecel/sys/Environment.hh"
+#include "celeritas/geo/GeoTrackView.hh"
+#include "celeritas/global/CoreState.hh"
+#include "celeritas/global/Stepper.hh"
+#include "celeritas/phys/Primary.hh"
+#include "celeritas/random/RngEngine.hh"
+
+#include "Problem.hh"
+
+using namespace celeritas;
+using json = nlohmann::json;
+
+namespace
+{
+thread_local std::string g_last_error;
+
+struct RefStepper
+{
+    celerref::Problem* problem;
+    std::unique_ptr<Stepper<MemSpace::host>> step;
+};
+
+//! Same POD layout as B200Primary in include/celeritas_b200.h
+struct CPrimary
+{
+    uint32_t particle_id;
+    uint32_t event_id;
+    double energy;
+    double pos[3];
+    double dir[3];
+    double time;
+};
+
+template<class F>
+int guarded(F&& f)
+{
+    try
+    {
+        f();
+        return 0;
+    }
+    catch (std::exception const& e)
+    {
+        g_last_error = e.what();
+        return 1;
+    }
+}
+
+std::vector<Primary> to_primaries(CPrimary const* p, uint32_t n)
+{
+    std::vector<Primary> result(n);
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        result[i].particle_id = ParticleId{p[i].particle_id};
+        result[i].energy = units::MevEnergy{p[i].energy};
+        result[i].position = {p[i].pos[0], p[i].pos[1], p[i].pos[2]};
+        result[i].direction = {p[i].dir[0], p[i].dir[1], p[i].dir[2]};
+        result[i].time = p[i].time;
+        result[i].event_id = EventId{p[i].event_id};
+    }
+    return result;
+}
+}  // namespace
+
+extern "C" {
+//---------------------------------------------------------------------------//
+char const* celerref_last_error()
+{
+    return g_last_error.c_str();
+}
+
+void* celerref_problem_create(char const* config_json)
+{
+    void* result = nullptr;
+    guarded([&] {
+        // Quiet the reference's logger unless asked
+        if (celeritas::getenv("CELER_LOG").empty())
+        {
+            celeritas::world_logger().level(LogLevel::warning);
+            celeritas::self_logger().level(LogLevel::warning);
+        }
+        auto p = celerref::build_problem(json::parse(config_json));
+        result = p.release();
+    });
+    return result;
+}
+
+void celerref_problem_destroy(void* p)
+{
+    delete static_cast<celerref::Problem*>(p);
+}
+
+int celerref_export_image(void* p, char const* path)
+{
+    return guarded(
+        [&] { celerref::export_image(*static_cast<celerref::Problem*>(p), path); });
+}
+
+//! Number of actions, and label of action i
+uint32_t celerref_num_actions(void* p)
+{
+    return static_cast<celerref::Problem*>(p)->core->action_reg()->num_actions();
+}
+
+//---------------------------------------------------------------------------//
+void* celerref_stepper_create(void* problem, uint32_t num_track_slots)
+{
+    void* result = nullptr;
+    guarded([&] {
+        auto* p = static_cast<celerref::Problem*>(problem);
+        StepperInput inp;
+        inp.params = p->core;
+        inp.stream_id = StreamId{0};
+        inp.num_track_slots = num_track_slots;
+        auto s = std::make_unique<RefStepper>();
+        s->problem = p;
+        s->step = std::make_unique<Stepper<MemSpace::host>>(std::move(inp));
+        result = s.release();
+    });
+    return result;
+}
+
+void celerref_stepper_destroy(void* s)
+{
+    delete static_cast<RefStepper*>(s);
+}
+
+//! One step iteration. counts = {generated, queued, active, alive}
+int celerref_step(void* stepper,
+                  CPrimary const* primaries,
+                  uint32_t num_primaries,
+                  uint32_t* counts)
+{
+    return guarded([&] {
+        auto* s = static_cast<RefStepper*>(stepper);
+        StepperResult r;
+        if (num_primaries > 0)
+        {
+            auto prim = to_primaries(primaries, num_primaries);
+            r = (*s->step)(make_span(prim));
+        }
+        else
+        {
+            r = (*s->step)();
+        }
+        counts[0] = r.generated;
+        counts[1] = r.queued;
+        counts[2] = r.active;
+        counts[3] = r.alive;
+    });
+}
+
+int celerref_reseed(void* stepper, uint64_t event_id)
+{
+    return guarded([&] {
+        static_cast<RefStepper*>(stepper)->step->reseed(
+            UniqueEventId{static_cast<UniqueEventId::size_type>(event_id)});
+    });
+}
+
+//! Copy a per-slot state field into `out` (caller sizes it)
+int celerref_state_get(void* stepper, char const* field, void* out)
+{
+    return guarded([&] {
+        auto* s = static_cast<RefStepper*>(stepper);
+        auto const& state = s->step->state_ref();
+        auto const& params = s->problem->core->host_ref();
+        size_type n = state.size();
+        std::string f = field;
+        auto* o32 = static_cast<uint32_t*>(out);
+        auto* o64 = static_cast<double*>(out);
+        auto* o8 = static_cast<uint8_t*>(out);
+        for (size_type i = 0; i < n; ++i)
+        {
+            TrackSlotId ts{i};
+            if (f == "status")
+                o8[i] = static_cast<uint8_t>(state.sim.status[ts]);
+            else if (f == "track_id")
+                o32[i] = state.sim.track_ids[ts].unchecked_get();
+            else if (f == "parent_id")
+                o32[i] = state.sim.parent_ids[ts].unchecked_get();
+            else if (f == "event_id")
+                o32[i] = state.sim.event_ids[ts].unchecked_get();
+            else if (f == "num_steps")
+                o32[i] = state.sim.num_steps[ts];
+            else if (f == "num_looping_steps")
+                o32[i] = state.sim.num_looping_steps.empty()
+                             ? 0
+                             : state.sim.num_looping_steps[ts];
+            else if (f == "time")
+                o64[i] = state.sim.time[ts];
+            else if (f == "step_length")
+                o64[i] = state.sim.step_length[ts];
+            else if (f == "post_step_action")
+                o32[i] = state.sim.post_step_action[ts].unchecked_get();
+            else if (f == "along_step_action")
+                o32[i] = state.sim.along_step_action[ts].unchecked_get();
+            else if (f == "particle_id")
+                o32[i] = state.particles.particle_id[ts].unchecked_get();
+            else if (f == "energy")
+                o64[i] = state.particles.particle_energy[ts];
+            else if (f == "material_id")
+                o32[i] = state.materials.state[ts].material_id.unchecked_get();
+            else if (f == "interaction_mfp")
+                o64[i] = state.physics.state[ts].interaction_mfp;
+            else if (f == "macro_xs")
+                o64[i] = state.physics.state[ts].macro_xs;
+            else if (f == "energy_deposition")
+                o64[i] = state.physics.state[ts].energy_deposition;
+            else if (f == "dedx_range")
+                o64[i] = state.physics.state[ts].dedx_range;
+            else if (f == "rng")
+            {
+                auto const& r = state.rng.state[ts];
+                for (int k = 0; k < 5; ++k)
+                    o32[6 * i + k] = r.xorstate[k];
+                o32[6 * i + 5] = r.weylstate;
+            }
+            else if (f == "pos" || f == "dir" || f == "volume_id"
+                     || f == "surface_id" || f == "geo_level")
+            {
+                bool inactive = state.sim.status[ts] == TrackStatus::inactive;
+                GeoTrackView geo(params.geometry, state.geometry, ts);
+                if (f == "pos")
+                    for (int k = 0; k < 3; ++k)
+                        o64[3 * i + k] = inactive ? 0 : geo.pos()[k];
+                else if (f == "dir")
+                    for (int k = 0; k < 3; ++k)
+                        o64[3 * i + k] = inactive ? 0 : geo.dir()[k];
+                else if (f == "volume_id")
+                    o32[i] = inactive ? 0xffffffffu
+                                      : geo.volume_id().unchecked_get();
+                else if (f == "surface_id")
+                    o32[i] = inactive ? 0xffffffffu
+                                      : geo.surface_id().unchecked_get();
+                else
+                    o32[i] = inactive ? 0xffffffffu
+                                      : geo.level().unchecked_get();
+            }
+            else
+            {
+                CELER_VALIDATE(false, << "unknown state field '" << f << "'");
+            }
+        }
+    });
+}
+
+//! Per-detector energy deposition accumulated by SimpleCalo [MeV]
+int celerref_calo_get(void* problem, double* out)
+{
+    return guarded([&] {
+        auto* p = static_cast<celerref::Problem*>(problem);
+        CELER_VALIDATE(p->calo, << "no simple_calo in this problem");
+        auto v = p->calo->calc_total_energy_deposition();
+        std::copy(v.begin(), v.end(), out);
+    });
+}
+
+int celerref_calo_clear(void* problem)
+{
+    return guarded([&] {
+        auto* p = static_cast<celerref::Problem*>(problem);
+        if (p->calo)
+            p->calo->clear();
+    });
+}
+
+//---------------------------------------------------------------------------//
+/*!
+ * Transport whole events the way celer-sim's Transporter does
+ * (/root/reference/app/celer-sim/Transporter.cc:84-179): one Stepper per
+ * OpenMP thread, events dealt to threads, `num_steps += active` per iteration.
+ *
+ * primaries are grouped by event: event e owns [offsets[e], offsets[e+1]).
+ * result = {num_steps, num_step_iterations, num_tracks(generated+secondaries
+ * is not tracked by the reference; primaries only), max_queued}; returns wall
+ * seconds of the transport loop (setup and one warm-up step excluded).
+ */
+double celerref_run_events(void* problem,
+                           CPrimary const* primaries,
+                           uint32_t const* offsets,
+                           uint32_t num_events,
+                           uint32_t num_track_slots,
+                           int num_threads,
+                           uint64_t* result)
+{
+    double elapsed = -1;
+    guarded([&] {
+        auto* p = static_cast<celerref::Problem*>(problem);
+        if (num_threads <= 0)
+            num_threads = omp_get_max_threads();
+        num_threads = std::min<int>(num_threads, p->core->max_streams());
+        std::vector<std::unique_ptr<Stepper<MemSpace::host>>> steppers(
+            num_threads);
+        for (int t = 0; t < num_threads; ++t)
+        {
+            StepperInput inp;
+            inp.params = p->core;
+            inp.stream_id = StreamId{static_cast<size_type>(t)};
+            inp.num_track_slots = num_track_slots;
+            steppers[t] = std::make_unique<Stepper<MemSpace::host>>(inp);
+            steppers[t]->warm_up();
+        }
+        uint64_t num_steps = 0, num_iters = 0, max_queued = 0, num_prim = 0;
+        std::string err;
+        auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for num_threads(num_threads) schedule(dynamic, 1) \
+    reduction(+ : num_steps, num_iters, num_prim) reduction(max : max_queued)
+        for (uint32_t e = 0; e < num_events; ++e)
+        {
+            try
+            {
+                auto& step = *steppers[omp_get_thread_num()];
+                auto prim = to_primaries(primaries + offsets[e],
+                                         offsets[e + 1] - offsets[e]);
+                step.reseed(UniqueEventId{prim.front().event_id.get()});
+                num_prim += prim.size();
+                auto counts = step(make_span(prim));
+                while (true)
+                {
+                    num_steps += counts.active;
+                    ++num_iters;
+                    max_queued = std::max<uint64_t>(max_queued, counts.queued);
+                    if (!counts)
+                        break;
+                    counts = step();
+                }
+            }
+            catch (std::exception const& ex)
+            {
+#pragma omp critical
+                err = ex.what();
+            }
+        }
+        auto t1 = std::chrono::steady_clock::now();
+        CELER_VALIDATE(err.empty(), << err);
+        elapsed = std::chrono::duration<double>(t1 - t0).count();
+        result[0] = num_steps;
+        result[1] = num_iters;
+        result[2] = num_prim;
+        result[3] = max_queued;
+    });
+    return elapsed;
+}
+}  // extern "C"
