@@ -1,0 +1,12 @@
+"""celeritas_b200: B200-native per-step track loop behind the reference's Stepper surface.
+
+This package is a thin ctypes binding over ``libceleritas_b200.so`` (C-ABI in
+``include/celeritas_b200.h``). There is no Python or CPU implementation of any
+step action: importing works anywhere, but creating params/state requires a GPU
+and fails loudly otherwise.
+"""
+from .lib import (Params, Stepper, Primary, PRIMARY_DTYPE, make_primaries, library_path,
+                  load_library, launch_count, device_count, B200Error)
+
+__all__ = ['Params', 'Stepper', 'Primary', 'PRIMARY_DTYPE', 'make_primaries', 'library_path',
+           'load_library', 'launch_count', 'device_count', 'B200Error']

@@ -1,0 +1,747 @@
+//---------------------------------------------------------------------------//
+// Step-action kernels and their C-ABI launchers.
+//
+// One kernel per step action of the reference's loop
+// (/root/reference/src/celeritas/global/ActionSequence.cc:77-138),
+// each over all track slots with per-slot predicates, all counters resident in
+// device memory so that a step iteration needs no host round trip.
+//---------------------------------------------------------------------------//
+#include <atomic>
+#include <cstdio>
+
+#include "../../include/celeritas_b200.h"
+#include "along_step.cuh"
+#include "interact.cuh"
+#include "orange.cuh"
+#include "physics.cuh"
+#include "rng.cuh"
+#include "views.cuh"
+
+namespace b200
+{
+constexpr int BLOCK = 128;
+
+B2_D u32 thread_slot()
+{
+    return blockIdx.x * blockDim.x + threadIdx.x;
+}
+
+//---------------------------------------------------------------------------//
+// generate: primaries -> track initializers
+// (track/detail/ProcessPrimariesExecutor.hh:56-76)
+//---------------------------------------------------------------------------//
+__global__ void k_extend_from_primaries(StateView s,
+                                        B200Primary const* __restrict__ primaries,
+                                        u32 const* __restrict__ rank_in_event,
+                                        u32 n)
+{
+    u32 tid = thread_slot();
+    if (tid >= n)
+        return;
+    // counters[NUM_INITIALIZERS] has not yet been incremented
+    u32 idx = s.counters[CTR_NUM_INITIALIZERS] + tid;
+    if (idx >= s.init_capacity)
+    {
+        s.counters[CTR_ERROR] = B200_ERR_INITIALIZER_CAPACITY;
+        return;
+    }
+    B200Primary const& pr = primaries[tid];
+    s.ti_track_id[idx] = s.track_counters[pr.event_id] + rank_in_event[tid];
+    s.ti_parent_id[idx] = INVALID;
+    s.ti_event_id[idx] = pr.event_id;
+    s.ti_time[idx] = pr.time;
+    s.ti_particle_id[idx] = pr.particle_id;
+    s.ti_energy[idx] = pr.energy;
+    for (int k = 0; k < 3; ++k)
+    {
+        s.ti_pos[k * s.init_capacity + idx] = pr.pos[k];
+        s.ti_dir[k * s.init_capacity + idx] = pr.dir[k];
+    }
+}
+
+__global__ void k_primaries_finalize(StateView s,
+                                     u32 const* __restrict__ event_ids,
+                                     u32 const* __restrict__ event_counts,
+                                     u32 num_events,
+                                     u32 n)
+{
+    u32 tid = thread_slot();
+    if (tid < num_events)
+        s.track_counters[event_ids[tid]] += event_counts[tid];
+    if (tid == 0)
+    {
+        s.counters[CTR_NUM_INITIALIZERS] += n;
+        s.counters[CTR_NUM_GENERATED] += n;
+    }
+}
+
+//---------------------------------------------------------------------------//
+// start: initialize tracks in vacant slots
+// (track/detail/InitTracksExecutor.hh:71-175)
+//---------------------------------------------------------------------------//
+__global__ void k_initialize_tracks(ParamsView const p, StateView s)
+{
+    u32 tid = thread_slot();
+    u32 const num_init = s.counters[CTR_NUM_INITIALIZERS];
+    u32 const num_vac = s.counters[CTR_NUM_VACANCIES];
+    u32 const num_new = num_init < num_vac ? num_init : num_vac;
+    if (tid >= num_new)
+        return;
+    u32 ti = num_init - tid - 1;
+    u32 slot = s.vacancies[num_vac - tid - 1];
+
+    // sim
+    s.track_id[slot] = s.ti_track_id[ti];
+    s.parent_id[slot] = s.ti_parent_id[ti];
+    s.event_id[slot] = s.ti_event_id[ti];
+    s.time[slot] = s.ti_time[ti];
+    s.num_steps[slot] = 0;
+    s.num_looping_steps[slot] = 0;
+    s.status[slot] = ST_INITIALIZING;
+    s.step_length[slot] = 0;
+    s.post_step_action[slot] = INVALID;
+    s.along_step_action[slot] = INVALID;
+    // particle
+    s.particle_id[slot] = s.ti_particle_id[ti];
+    s.energy[slot] = s.ti_energy[ti];
+    // geometry
+    Real3 pos, dir;
+    for (int k = 0; k < 3; ++k)
+    {
+        pos[k] = s.ti_pos[k * s.init_capacity + ti];
+        dir[k] = s.ti_dir[k * s.init_capacity + ti];
+    }
+    GeoTrack geo(p, s, slot);
+    geo.initialize(pos, dir);
+    bool errored = geo.failed || geo.is_outside();
+    u32 matid = INVALID;
+    if (!errored)
+    {
+        matid = p.geo.volume_material[geo.volume_id()];
+        errored = (matid == INVALID);
+    }
+    if (errored)
+    {
+        // apply_errored (CoreTrackView.hh:340-347)
+        s.status[slot] = ST_ERRORED;
+        s.along_step_action[slot] = INVALID;
+        s.post_step_action[slot] = p.scalars.tracking_cut_action;
+        return;
+    }
+    s.material_id[slot] = matid;
+    // physics = {} : reset
+    s.interaction_mfp[slot] = 0;
+    s.msc_range[slot] = 0;
+    s.msc_range[s.num_slots + slot] = 0;
+    s.msc_range[2 * s.num_slots + slot] = 0;
+}
+
+__global__ void k_initialize_finalize(StateView s)
+{
+    u32 const num_init = s.counters[CTR_NUM_INITIALIZERS];
+    u32 const num_vac = s.counters[CTR_NUM_VACANCIES];
+    u32 const num_new = num_init < num_vac ? num_init : num_vac;
+    s.counters[CTR_NUM_INITIALIZERS] = num_init - num_new;
+    s.counters[CTR_NUM_VACANCIES] = num_vac - num_new;
+    s.counters[CTR_NUM_ACTIVE] = s.num_slots - (num_vac - num_new);
+    s.counters[CTR_NUM_NEW_TRACKS] = num_new;
+}
+
+//---------------------------------------------------------------------------//
+// pre: physics step limits (phys/detail/PreStepExecutor.hh:45-115)
+//---------------------------------------------------------------------------//
+__global__ void k_pre_step(ParamsView const p, StateView s)
+{
+    u32 slot = thread_slot();
+    if (slot >= s.num_slots)
+        return;
+    u8 status = s.status[slot];
+    if (status == ST_INACTIVE)
+    {
+        s.step_length[slot] = real_inf();
+        s.post_step_action[slot] = INVALID;
+        s.along_step_action[slot] = INVALID;
+        return;
+    }
+    s.energy_deposition[slot] = 0;
+    for (int i = 0; i < MAX_SECONDARIES; ++i)
+        s.sec_particle[i * s.num_slots + slot] = INVALID;
+    s.element[slot] = INVALID;
+    if (status == ST_ERRORED)
+        return;
+    s.status[slot] = ST_ALIVE;
+
+    if (!(s.interaction_mfp[slot] > 0))
+    {
+        Rng rng;
+        rng.load(s, slot);
+        s.interaction_mfp[slot] = sample_exponential(rng);
+        rng.store(s, slot);
+    }
+    Particle particle = load_particle(p, s, slot);
+    PhysTrack phys(p, particle.id, s.material_id[slot]);
+    StepLimit limit = calc_physics_step_limit(p, s, slot, particle, phys);
+    s.step_length[slot] = limit.step;
+    s.post_step_action[slot] = limit.action;
+    s.along_step_action[slot] = (particle.charge == 0) ? p.scalars.along_step_neutral_action
+                                                       : p.scalars.along_step_user_action;
+    // pre-step volume for detector scoring (StepGatherExecutor<pre>)
+    if (s.pre_volume)
+    {
+        GeoTrack geo(p, s, slot);
+        s.pre_volume[slot] = geo.volume_id();
+    }
+}
+
+//---------------------------------------------------------------------------//
+// along-step
+//---------------------------------------------------------------------------//
+__global__ void k_along_step(ParamsView const p, StateView s)
+{
+    u32 slot = thread_slot();
+    if (slot >= s.num_slots)
+        return;
+    if (s.status[slot] != ST_ALIVE)
+        return;
+    along_step(p, s, slot);
+}
+
+//---------------------------------------------------------------------------//
+// pre-post: discrete select (phys/detail/DiscreteSelectExecutor.hh:37-63)
+// post: interaction / boundary / tracking cut, fused by post-step action id
+//---------------------------------------------------------------------------//
+__global__ void k_discrete_select(ParamsView const p, StateView s)
+{
+    u32 slot = thread_slot();
+    if (slot >= s.num_slots)
+        return;
+    if (s.status[slot] != ST_ALIVE)
+        return;
+    if (s.post_step_action[slot] != p.phys.model_to_action - 2)
+        return;
+    s.interaction_mfp[slot] = 0;
+    Particle particle = load_particle(p, s, slot);
+    PhysTrack phys(p, particle.id, s.material_id[slot]);
+    Rng rng;
+    rng.load(s, slot);
+    u32 action = select_discrete_interaction(p, s, slot, particle, phys, rng);
+    rng.store(s, slot);
+    s.post_step_action[slot] = action;
+}
+
+__global__ void k_interact(ParamsView const p, StateView s)
+{
+    u32 slot = thread_slot();
+    if (slot >= s.num_slots)
+        return;
+    if (s.status[slot] != ST_ALIVE)
+        return;
+    u32 action = s.post_step_action[slot];
+    if (action < p.phys.model_to_action || action >= p.phys.model_to_action + p.phys.num_models)
+        return;
+    Rng rng;
+    rng.load(s, slot);
+    run_interaction(p, s, slot, action, rng);
+    rng.store(s, slot);
+}
+
+// (geo/detail/BoundaryExecutor.hh:41-84)
+__global__ void k_boundary(ParamsView const p, StateView s)
+{
+    u32 slot = thread_slot();
+    if (slot >= s.num_slots)
+        return;
+    if (s.status[slot] != ST_ALIVE || s.post_step_action[slot] != p.scalars.boundary_action)
+        return;
+    GeoTrack geo(p, s, slot);
+    geo.cross_boundary();
+    bool errored = geo.failed;
+    if (!errored && !geo.is_outside())
+    {
+        u32 matid = p.geo.volume_material[geo.volume_id()];
+        if (matid == INVALID)
+            errored = true;
+        else
+            s.material_id[slot] = matid;
+    }
+    else if (!errored)
+    {
+        s.status[slot] = ST_KILLED;
+    }
+    if (errored)
+    {
+        s.status[slot] = ST_ERRORED;
+        s.along_step_action[slot] = INVALID;
+        s.post_step_action[slot] = p.scalars.tracking_cut_action;
+    }
+}
+
+// (phys/detail/TrackingCutExecutor.hh:48-83)
+__global__ void k_tracking_cut(ParamsView const p, StateView s)
+{
+    u32 slot = thread_slot();
+    if (slot >= s.num_slots)
+        return;
+    u8 status = s.status[slot];
+    if (status == ST_INACTIVE || status == ST_KILLED)
+        return;
+    if (s.post_step_action[slot] != p.scalars.tracking_cut_action)
+        return;
+    u32 pid = s.particle_id[slot];
+    real deposited = s.energy[slot];
+    if (particle_is_antiparticle(p, pid))
+        deposited += 2 * p.particle.mass[pid];
+    s.energy_deposition[slot] += deposited;
+    s.energy[slot] = 0;
+    s.status[slot] = ST_KILLED;
+}
+
+//---------------------------------------------------------------------------//
+// user_post: tallies (user/detail/SimpleCaloExecutor.hh:48-67,
+// app/celer-sim/Transporter.cc:109-111)
+//---------------------------------------------------------------------------//
+__global__ void k_tally(ParamsView const p, StateView s)
+{
+    u32 slot = thread_slot();
+    if (slot >= s.num_slots)
+        return;
+    if (s.status[slot] == ST_INACTIVE)
+        return;
+    if (s.calo_edep)
+    {
+        real edep = s.energy_deposition[slot];
+        if (edep != 0)
+        {
+            u32 det = s.calo_detector_of_volume[s.pre_volume[slot]];
+            if (det != INVALID)
+                atomicAdd(&s.calo_edep[det], edep);
+        }
+    }
+}
+
+//---------------------------------------------------------------------------//
+// end: secondaries -> initializers, vacancy compaction
+// (track/detail/LocateAliveExecutor.hh:60-106,
+//  track/detail/ProcessSecondariesExecutor.hh:69-183,
+//  track/detail/TrackInitAlgorithms.cu:34-78)
+//
+// Pass 1 (per block): alive flags and secondary counts, block-level exclusive
+//   scans, block totals to scratch.
+// Pass 2 (one block): scan of block totals -> block offsets, global counters.
+// Pass 3 (per block): write compacted vacancies and track initializers.
+//---------------------------------------------------------------------------//
+template<int B>
+B2_D u32 block_exclusive_scan(u32 value, u32* total)
+{
+    __shared__ u32 warp_sums[B / 32];
+    __shared__ u32 block_total;
+    u32 lane = threadIdx.x & 31;
+    u32 warp = threadIdx.x >> 5;
+    u32 incl = value;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1)
+    {
+        u32 n = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off)
+            incl += n;
+    }
+    if (lane == 31)
+        warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0)
+    {
+        u32 w = lane < B / 32 ? warp_sums[lane] : 0;
+        u32 wi = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1)
+        {
+            u32 n = __shfl_up_sync(0xffffffffu, wi, off);
+            if (lane >= off)
+                wi += n;
+        }
+        if (lane < B / 32)
+            warp_sums[lane] = wi - w;
+        if (lane == 31)
+            block_total = wi;
+    }
+    __syncthreads();
+    u32 result = warp_sums[warp] + incl - value;
+    *total = block_total;
+    __syncthreads();
+    return result;
+}
+
+struct SlotEnd
+{
+    u32 is_vacant;
+    u32 num_sec;
+    bool reuse_slot;  // first secondary replaces a dead parent in place
+};
+
+B2_D SlotEnd classify_slot(ParamsView const& p, StateView const& s, u32 slot)
+{
+    SlotEnd r{0, 0, false};
+    if (slot >= s.num_slots)
+        return r;
+    u8 status = s.status[slot];
+    if (status != ST_INACTIVE)
+    {
+        for (int i = 0; i < MAX_SECONDARIES; ++i)
+            r.num_sec += (s.sec_particle[i * s.num_slots + slot] != INVALID);
+    }
+    if (status == ST_ALIVE)
+    {
+        r.is_vacant = 0;
+    }
+    else if (r.num_sec > 0 && p.scalars.track_order != ORDER_INIT_CHARGE)
+    {
+        --r.num_sec;
+        r.reuse_slot = true;
+        r.is_vacant = 0;
+    }
+    else
+    {
+        r.is_vacant = 1;
+    }
+    return r;
+}
+
+__global__ void k_end_pass1(ParamsView const p, StateView s)
+{
+    u32 slot = thread_slot();
+    SlotEnd e = classify_slot(p, s, slot);
+    u32 tv, ts;
+    block_exclusive_scan<BLOCK>(e.is_vacant, &tv);
+    block_exclusive_scan<BLOCK>(e.num_sec, &ts);
+    if (threadIdx.x == 0)
+    {
+        s.block_scratch[blockIdx.x] = tv;
+        s.block_scratch[gridDim.x + blockIdx.x] = ts;
+    }
+}
+
+__global__ void k_end_pass2(StateView s, u32 num_blocks)
+{
+    // Single block: scan block totals (chunked)
+    constexpr int B = 1024;
+    __shared__ u32 carry[2];
+    if (threadIdx.x == 0)
+    {
+        carry[0] = 0;
+        carry[1] = 0;
+    }
+    __syncthreads();
+    for (u32 base = 0; base < num_blocks; base += B)
+    {
+        u32 i = base + threadIdx.x;
+        for (int a = 0; a < 2; ++a)
+        {
+            u32 v = i < num_blocks ? s.block_scratch[a * num_blocks + i] : 0;
+            u32 total;
+            u32 ex = block_exclusive_scan<B>(v, &total);
+            if (i < num_blocks)
+                s.block_scratch[a * num_blocks + i] = ex + carry[a];
+            __syncthreads();
+            if (threadIdx.x == 0)
+                carry[a] += total;
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0)
+    {
+        u32 num_vac = carry[0];
+        u32 num_sec = carry[1];
+        s.counters[CTR_NUM_VACANCIES] = num_vac;
+        s.counters[CTR_NUM_SECONDARIES] = num_sec;
+        u32 num_init = s.counters[CTR_NUM_INITIALIZERS] + num_sec;
+        s.counters[CTR_NUM_INITIALIZERS] = num_init;
+        s.counters[CTR_NUM_ALIVE] = s.num_slots - num_vac;
+        if (num_init > s.init_capacity)
+            s.counters[CTR_ERROR] = B200_ERR_INITIALIZER_CAPACITY;
+    }
+}
+
+__global__ void k_end_pass3(ParamsView const p, StateView s)
+{
+    u32 slot = thread_slot();
+    SlotEnd e = classify_slot(p, s, slot);
+    u32 tv, ts;
+    u32 vac_off = block_exclusive_scan<BLOCK>(e.is_vacant, &tv) + s.block_scratch[blockIdx.x];
+    u32 sec_off = block_exclusive_scan<BLOCK>(e.num_sec, &ts)
+                  + s.block_scratch[gridDim.x + blockIdx.x];
+    if (slot >= s.num_slots)
+        return;
+    if (s.counters[CTR_ERROR] != 0)
+        return;
+    if (e.is_vacant)
+        s.vacancies[vac_off] = slot;
+
+    u8 status = s.status[slot];
+    if (status == ST_INACTIVE)
+        return;
+
+    // Initializers created this step occupy [num_init - num_sec, num_init)
+    // in slot order (exclusive scan of the per-slot counts)
+    u32 const num_init = s.counters[CTR_NUM_INITIALIZERS];
+    u32 const num_sec_total = s.counters[CTR_NUM_SECONDARIES];
+    u32 out = num_init - num_sec_total + sec_off;
+    bool initialized = false;
+    u32 const n = s.num_slots;
+    u32 const event = s.event_id[slot];
+    u32 const parent_track = s.track_id[slot];
+    real const time = s.time[slot];
+    GeoTrack geo(p, s, slot);
+    Real3 const pos = geo.pos();
+
+    // Track ids: per-event counter (reference: atomic_add, detail/Utils.hh:107-116)
+    u32 nsec_here = e.num_sec + (e.reuse_slot ? 1 : 0);
+    u32 id_base = nsec_here ? atomicAdd(&s.track_counters[event], nsec_here) : 0;
+
+    for (int i = 0; i < MAX_SECONDARIES; ++i)
+    {
+        u32 spid = s.sec_particle[i * n + slot];
+        if (spid == INVALID)
+            continue;
+        real senergy = s.sec_energy[i * n + slot];
+        Real3 sdir = make_real3(s.sec_dir[(i * 3 + 0) * n + slot],
+                                s.sec_dir[(i * 3 + 1) * n + slot],
+                                s.sec_dir[(i * 3 + 2) * n + slot]);
+        u32 new_id = id_base++;
+        if (!initialized && e.reuse_slot)
+        {
+            // The first secondary takes over the dead parent's slot
+            s.track_id[slot] = new_id;
+            s.parent_id[slot] = parent_track;
+            s.num_steps[slot] = 0;
+            s.num_looping_steps[slot] = 0;
+            s.status[slot] = ST_INITIALIZING;
+            s.step_length[slot] = 0;
+            s.post_step_action[slot] = INVALID;
+            s.along_step_action[slot] = INVALID;
+            geo.initialize_from(slot, sdir);
+            s.particle_id[slot] = spid;
+            s.energy[slot] = senergy;
+            s.interaction_mfp[slot] = 0;
+            s.msc_range[slot] = 0;
+            s.msc_range[n + slot] = 0;
+            s.msc_range[2 * n + slot] = 0;
+            initialized = true;
+        }
+        else
+        {
+            s.ti_track_id[out] = new_id;
+            s.ti_parent_id[out] = parent_track;
+            s.ti_event_id[out] = event;
+            s.ti_time[out] = time;
+            s.ti_particle_id[out] = spid;
+            s.ti_energy[out] = senergy;
+            for (int k = 0; k < 3; ++k)
+            {
+                s.ti_pos[k * s.init_capacity + out] = pos[k];
+                s.ti_dir[k * s.init_capacity + out] = sdir[k];
+            }
+            ++out;
+        }
+    }
+    if (!initialized && status == ST_KILLED)
+        s.status[slot] = ST_INACTIVE;
+    if (status == ST_ERRORED && !initialized)
+    {
+        // errored tracks were killed by tracking-cut; nothing else to do
+    }
+}
+
+//---------------------------------------------------------------------------//
+// reseed (random/RngReseed.cu:29-74)
+//---------------------------------------------------------------------------//
+__global__ void k_reseed(ParamsView const p, StateView s, u64 event_id)
+{
+    u32 slot = thread_slot();
+    if (slot >= s.num_slots)
+        return;
+    Rng rng;
+    rng.initialize(p.rng, p.rng.seed, event_id * u64(s.num_slots) + slot, 0);
+    rng.store(s, slot);
+}
+
+__global__ void k_reset_generated(StateView s)
+{
+    s.counters[CTR_NUM_GENERATED] = 0;
+}
+
+__global__ void k_kill_active(ParamsView const p, StateView s)
+{
+    u32 slot = thread_slot();
+    if (slot >= s.num_slots)
+        return;
+    if (s.status[slot] == ST_INACTIVE)
+        return;
+    s.status[slot] = ST_ERRORED;
+    s.along_step_action[slot] = INVALID;
+    s.post_step_action[slot] = p.scalars.tracking_cut_action;
+}
+}  // namespace b200
+
+//---------------------------------------------------------------------------//
+// C-ABI launchers
+//---------------------------------------------------------------------------//
+using namespace b200;
+
+namespace
+{
+std::atomic<uint64_t> g_launches{0};
+#define B2_COUNT(n) g_launches.fetch_add(n, std::memory_order_relaxed)
+inline unsigned grid_for(u32 n)
+{
+    return (n + BLOCK - 1) / BLOCK;
+}
+inline int check_launch()
+{
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+inline ParamsView const& PV(B200ParamsView const* p)
+{
+    return *reinterpret_cast<ParamsView const*>(p);
+}
+inline StateView const& SV(B200StateView const* s)
+{
+    return *reinterpret_cast<StateView const*>(s);
+}
+}  // namespace
+
+extern "C" {
+uint64_t b200_launch_count(void)
+{
+    return g_launches.load();
+}
+
+int b200_step_extend_from_primaries(B200StateView const* state,
+                                    B200Primary const* d_primaries,
+                                    uint32_t const* d_rank_in_event,
+                                    uint32_t const* d_event_ids,
+                                    uint32_t const* d_event_counts,
+                                    uint32_t num_events,
+                                    uint32_t n,
+                                    cudaStream_t stream)
+{
+    if (n == 0)
+        return 0;
+    k_extend_from_primaries<<<grid_for(n), BLOCK, 0, stream>>>(
+        SV(state), d_primaries, d_rank_in_event, n);
+    k_primaries_finalize<<<grid_for(num_events), BLOCK, 0, stream>>>(
+        SV(state), d_event_ids, d_event_counts, num_events, n);
+    B2_COUNT(2);
+    return check_launch();
+}
+
+int b200_step_initialize_tracks(B200ParamsView const* params,
+                                B200StateView const* state,
+                                cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    k_initialize_tracks<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
+    k_initialize_finalize<<<1, 1, 0, stream>>>(s);
+    B2_COUNT(2);
+    return check_launch();
+}
+
+int b200_step_pre_step(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    k_pre_step<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
+    B2_COUNT(1);
+    return check_launch();
+}
+
+int b200_step_along_step(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    k_along_step<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
+    B2_COUNT(1);
+    return check_launch();
+}
+
+int b200_step_discrete_select(B200ParamsView const* params,
+                              B200StateView const* state,
+                              cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    k_discrete_select<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
+    B2_COUNT(1);
+    return check_launch();
+}
+
+int b200_step_interact(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    k_interact<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
+    B2_COUNT(1);
+    return check_launch();
+}
+
+int b200_step_boundary(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    k_boundary<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
+    B2_COUNT(1);
+    return check_launch();
+}
+
+int b200_step_tracking_cut(B200ParamsView const* params,
+                           B200StateView const* state,
+                           cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    k_tracking_cut<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
+    B2_COUNT(1);
+    return check_launch();
+}
+
+int b200_step_tally(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    k_tally<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
+    B2_COUNT(1);
+    return check_launch();
+}
+
+int b200_step_extend_from_secondaries(B200ParamsView const* params,
+                                      B200StateView const* state,
+                                      cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    unsigned nb = grid_for(s.num_slots);
+    k_end_pass1<<<nb, BLOCK, 0, stream>>>(PV(params), s);
+    k_end_pass2<<<1, 1024, 0, stream>>>(s, nb);
+    k_end_pass3<<<nb, BLOCK, 0, stream>>>(PV(params), s);
+    B2_COUNT(3);
+    return check_launch();
+}
+
+int b200_reseed(B200ParamsView const* params,
+                B200StateView const* state,
+                uint64_t event_id,
+                cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    k_reseed<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s, event_id);
+    B2_COUNT(1);
+    return check_launch();
+}
+
+int b200_reset_generated(B200StateView const* state, cudaStream_t stream)
+{
+    k_reset_generated<<<1, 1, 0, stream>>>(SV(state));
+    B2_COUNT(1);
+    return check_launch();
+}
+
+int b200_kill_active(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    k_kill_active<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
+    B2_COUNT(1);
+    return check_launch();
+}
+}  // extern "C"

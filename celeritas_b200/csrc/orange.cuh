@@ -1,0 +1,1213 @@
+//---------------------------------------------------------------------------//
+// ORANGE navigation on structure-of-arrays track state.
+//
+// Implements the behaviour of the reference's OrangeTrackView
+// (/root/reference/src/orange/OrangeTrackView.hh:265-842) and
+// SimpleUnitTracker (/root/reference/src/orange/univ/SimpleUnitTracker.hh:162-675)
+// for multi-level geometries of "simple unit" universes: point location through
+// a bounding-interval hierarchy, distance-to-boundary over a volume's faces
+// with simple / complex (internal surfaces) / background handling, boundary
+// crossing through surface connectivity, and the quadric surface family.
+//
+// Per-thread scratch (face senses, intersection distances) lives in registers /
+// local memory sized by the compile-time caps below instead of the reference's
+// per-track global scratch arrays (OrangeTrackView.hh:1042-1067).
+//---------------------------------------------------------------------------//
+#pragma once
+
+#include "views.cuh"
+
+namespace b200
+{
+constexpr int ORANGE_MAX_FACES = 32;
+constexpr int ORANGE_MAX_ISECT = 32;
+
+struct Propagation
+{
+    real distance;
+    bool boundary;
+    bool looping;
+};
+
+//---------------------------------------------------------------------------//
+// SURFACES
+//---------------------------------------------------------------------------//
+//! Sense of a quadric value: -1 inside, 0 on, +1 outside (NaN -> outside)
+B2_D int real_to_sense(real q)
+{
+    return static_cast<int>(!(q <= 0)) - static_cast<int>(q < 0);
+}
+
+struct SurfaceRef
+{
+    u8 type;
+    real const* d;
+};
+
+B2_D SurfaceRef get_surface(GeoParams const& g, SimpleUnit const& u, u32 local_surface)
+{
+    SurfaceRef s;
+    s.type = g.surface_types[u.surf_begin + local_surface];
+    s.d = g.reals + g.real_ids[u.real_id_begin + local_surface];
+    return s;
+}
+
+B2_D int surface_sense(SurfaceRef const& s, Real3 const& pos)
+{
+    real const* d = s.d;
+    switch (s.type)
+    {
+        case SURF_PX: return real_to_sense(pos[0] - d[0]);
+        case SURF_PY: return real_to_sense(pos[1] - d[0]);
+        case SURF_PZ: return real_to_sense(pos[2] - d[0]);
+        case SURF_CXC: return real_to_sense(ipow2(pos[1]) + ipow2(pos[2]) - d[0]);
+        case SURF_CYC: return real_to_sense(ipow2(pos[0]) + ipow2(pos[2]) - d[0]);
+        case SURF_CZC: return real_to_sense(ipow2(pos[0]) + ipow2(pos[1]) - d[0]);
+        case SURF_SC: return real_to_sense(dot(pos, pos) - d[0]);
+        case SURF_CX:
+        {
+            real u = pos[1] - d[0], v = pos[2] - d[1];
+            return real_to_sense(ipow2(u) + ipow2(v) - d[2]);
+        }
+        case SURF_CY:
+        {
+            real u = pos[0] - d[0], v = pos[2] - d[1];
+            return real_to_sense(ipow2(u) + ipow2(v) - d[2]);
+        }
+        case SURF_CZ:
+        {
+            real u = pos[0] - d[0], v = pos[1] - d[1];
+            return real_to_sense(ipow2(u) + ipow2(v) - d[2]);
+        }
+        case SURF_P:
+        {
+            Real3 n = make_real3(d[0], d[1], d[2]);
+            return real_to_sense(dot(n, pos) - d[3]);
+        }
+        case SURF_S:
+        {
+            Real3 t = make_real3(pos[0] - d[0], pos[1] - d[1], pos[2] - d[2]);
+            return real_to_sense(dot(t, t) - d[3]);
+        }
+        case SURF_KX:
+        case SURF_KY:
+        case SURF_KZ:
+        {
+            int T = s.type - SURF_KX;
+            int U = (T == 0) ? 1 : 0;
+            int V = (T == 2) ? 1 : 2;
+            real x = pos[T] - d[T], y = pos[U] - d[U], z = pos[V] - d[V];
+            return real_to_sense((-d[3] * ipow2(x)) + ipow2(y) + ipow2(z));
+        }
+        case SURF_SQ:
+        {
+            real x = pos[0], y = pos[1], z = pos[2];
+            return real_to_sense((d[0] * ipow2(x) + d[1] * ipow2(y) + d[2] * ipow2(z))
+                                 + (d[3] * x + d[4] * y + d[5] * z) + (d[6]));
+        }
+        case SURF_GQ:
+        {
+            real x = pos[0], y = pos[1], z = pos[2];
+            real r = (d[0] * x + d[3] * y + d[5] * z + d[6]) * x
+                     + (d[1] * y + d[4] * z + d[7]) * y + (d[2] * z + d[8]) * z + d[9];
+            return real_to_sense(r);
+        }
+        default: return 1;
+    }
+}
+
+// Quadratic solver (reference surf/detail/QuadraticSolver.hh:60-230)
+struct Roots
+{
+    real r[2];
+};
+
+constexpr real SQRT_QUADRATIC = 1e-5;
+constexpr real MIN_A = SQRT_QUADRATIC * SQRT_QUADRATIC;
+
+B2_D Roots quad_solve_off(real a_inv, real hba, real c)
+{
+    c *= a_inv;
+    real b2_4 = ipow2(hba);
+    Roots res;
+    if (b2_4 > c)
+    {
+        real t2 = sqrt(b2_4 - c);
+        res.r[0] = -hba - t2;
+        res.r[1] = -hba + t2;
+        if (res.r[1] <= 0)
+        {
+            res.r[0] = real_inf();
+            res.r[1] = real_inf();
+        }
+        else if (res.r[0] <= 0)
+        {
+            res.r[0] = real_inf();
+        }
+    }
+    else if (b2_4 == c)
+    {
+        res.r[0] = -hba;
+        res.r[1] = real_inf();
+        if (res.r[0] <= 0)
+            res.r[0] = real_inf();
+    }
+    else
+    {
+        res.r[0] = real_inf();
+        res.r[1] = real_inf();
+    }
+    return res;
+}
+
+B2_D Roots quad_solve_on(real hba)
+{
+    Roots res;
+    res.r[0] = -2 * hba;
+    res.r[1] = real_inf();
+    if (res.r[0] <= 0)
+        res.r[0] = real_inf();
+    return res;
+}
+
+//! Solve a x^2 + 2 half_b x + c = 0 given normalised-by-a helper
+B2_D Roots quad_solve(real a, real half_b, real c, bool on_surface)
+{
+    real a_inv = 1 / a;
+    real hba = half_b * a_inv;
+    return on_surface ? quad_solve_on(hba) : quad_solve_off(a_inv, hba, c);
+}
+
+B2_D Roots quad_solve_general(real a, real half_b, real c, bool on_surface)
+{
+    if (fabs(a) >= MIN_A)
+        return quad_solve(a, half_b, c, on_surface);
+    Roots res;
+    res.r[0] = real_inf();
+    res.r[1] = real_inf();
+    if (!on_surface)
+    {
+        // travelling along the surface: linear equation
+        if (fabs(half_b) > MIN_A)
+        {
+            res.r[0] = -c / (2 * half_b);
+            if (res.r[0] < 0)
+                res.r[0] = real_inf();
+        }
+    }
+    return res;
+}
+
+//! Number of possible intersections for a surface type
+B2_D int surface_num_isect(u8 type)
+{
+    return (type <= SURF_PZ || type == SURF_P) ? 1 : 2;
+}
+
+//! Distances to a surface along (pos, dir); roots are +inf when absent
+B2_D Roots surface_intersect(SurfaceRef const& s, Real3 const& pos, Real3 const& dir, bool on_surface)
+{
+    real const* d = s.d;
+    Roots none;
+    none.r[0] = real_inf();
+    none.r[1] = real_inf();
+    switch (s.type)
+    {
+        case SURF_PX:
+        case SURF_PY:
+        case SURF_PZ:
+        {
+            int T = s.type;
+            real n_dir = dir[T];
+            if (!on_surface && n_dir != 0)
+            {
+                real dist = (d[0] - pos[T]) / n_dir;
+                if (dist > 0)
+                    none.r[0] = dist;
+            }
+            return none;
+        }
+        case SURF_CXC:
+        case SURF_CYC:
+        case SURF_CZC:
+        {
+            int T = s.type - SURF_CXC;
+            int U = (T == 0) ? 1 : 0;
+            int V = (T == 2) ? 1 : 2;
+            real a = 1 - ipow2(dir[T]);
+            if (a < MIN_A)
+                return none;
+            real u = pos[U], v = pos[V];
+            real half_b = dir[U] * u + dir[V] * v;
+            return quad_solve(a, half_b, ipow2(u) + ipow2(v) - d[0], on_surface);
+        }
+        case SURF_SC:
+        {
+            return quad_solve(1, dot(pos, dir), dot(pos, pos) - d[0], on_surface);
+        }
+        case SURF_CX:
+        case SURF_CY:
+        case SURF_CZ:
+        {
+            int T = s.type - SURF_CX;
+            int U = (T == 0) ? 1 : 0;
+            int V = (T == 2) ? 1 : 2;
+            real a = 1 - ipow2(dir[T]);
+            if (a < MIN_A)
+                return none;
+            real u = pos[U] - d[0], v = pos[V] - d[1];
+            real half_b = dir[U] * u + dir[V] * v;
+            return quad_solve(a, half_b, ipow2(u) + ipow2(v) - d[2], on_surface);
+        }
+        case SURF_P:
+        {
+            Real3 n = make_real3(d[0], d[1], d[2]);
+            real n_dir = dot(n, dir);
+            if (!on_surface && n_dir != 0)
+            {
+                real n_pos = dot(n, pos);
+                real dist = (d[3] - n_pos) / n_dir;
+                if (dist > 0)
+                    none.r[0] = dist;
+            }
+            return none;
+        }
+        case SURF_S:
+        {
+            Real3 t = make_real3(pos[0] - d[0], pos[1] - d[1], pos[2] - d[2]);
+            return quad_solve(1, dot(t, dir), dot(t, t) - d[3], on_surface);
+        }
+        case SURF_KX:
+        case SURF_KY:
+        case SURF_KZ:
+        {
+            int T = s.type - SURF_KX;
+            int U = (T == 0) ? 1 : 0;
+            int V = (T == 2) ? 1 : 2;
+            real x = pos[T] - d[T], y = pos[U] - d[U], z = pos[V] - d[V];
+            real u = dir[T], v = dir[U], w = dir[V];
+            real tsq = d[3];
+            real a = (-tsq * ipow2(u)) + ipow2(v) + ipow2(w);
+            real half_b = (-tsq * x * u) + (y * v) + (z * w);
+            real c = (-tsq * ipow2(x)) + ipow2(y) + ipow2(z);
+            return quad_solve_general(a, half_b, c, on_surface);
+        }
+        case SURF_SQ:
+        {
+            real x = pos[0], y = pos[1], z = pos[2];
+            real u = dir[0], v = dir[1], w = dir[2];
+            real a = (d[0] * u) * u + (d[1] * v) * v + (d[2] * w) * w;
+            real b = (2 * d[0] * x + d[3]) * u + (2 * d[1] * y + d[4]) * v
+                     + (2 * d[2] * z + d[5]) * w;
+            real c = (d[0] * x + d[3]) * x + (d[1] * y + d[4]) * y + (d[2] * z + d[5]) * z
+                     + d[6];
+            return quad_solve_general(a, b / 2, c, on_surface);
+        }
+        case SURF_GQ:
+        {
+            real x = pos[0], y = pos[1], z = pos[2];
+            real u = dir[0], v = dir[1], w = dir[2];
+            real a = (d[0] * u + d[3] * v) * u + (d[1] * v + d[4] * w) * v
+                     + (d[2] * w + d[5] * u) * w;
+            real b = (2 * d[0] * x + d[3] * y + d[5] * z + d[6]) * u
+                     + (2 * d[1] * y + d[3] * x + d[4] * z + d[7]) * v
+                     + (2 * d[2] * z + d[4] * y + d[5] * x + d[8]) * w;
+            real c = ((d[0] * x + d[3] * y + d[6]) * x + (d[1] * y + d[4] * z + d[7]) * y
+                      + (d[2] * z + d[5] * x + d[8]) * z + d[9]);
+            return quad_solve_general(a, b / 2, c, on_surface);
+        }
+        default: return none;
+    }
+}
+
+//! Outward normal at pos
+B2_D Real3 surface_normal(SurfaceRef const& s, Real3 const& pos)
+{
+    real const* d = s.d;
+    switch (s.type)
+    {
+        case SURF_PX: return make_real3(1, 0, 0);
+        case SURF_PY: return make_real3(0, 1, 0);
+        case SURF_PZ: return make_real3(0, 0, 1);
+        case SURF_CXC: return make_unit_vector(make_real3(0, pos[1], pos[2]));
+        case SURF_CYC: return make_unit_vector(make_real3(pos[0], 0, pos[2]));
+        case SURF_CZC: return make_unit_vector(make_real3(pos[0], pos[1], 0));
+        case SURF_SC: return make_unit_vector(pos);
+        case SURF_CX: return make_unit_vector(make_real3(0, pos[1] - d[0], pos[2] - d[1]));
+        case SURF_CY: return make_unit_vector(make_real3(pos[0] - d[0], 0, pos[2] - d[1]));
+        case SURF_CZ: return make_unit_vector(make_real3(pos[0] - d[0], pos[1] - d[1], 0));
+        case SURF_P: return make_real3(d[0], d[1], d[2]);
+        case SURF_S:
+            return make_unit_vector(make_real3(pos[0] - d[0], pos[1] - d[1], pos[2] - d[2]));
+        case SURF_KX:
+        case SURF_KY:
+        case SURF_KZ:
+        {
+            int T = s.type - SURF_KX;
+            Real3 n = make_real3(pos[0] - d[0], pos[1] - d[1], pos[2] - d[2]);
+            n[T] *= -d[3];
+            return make_unit_vector(n);
+        }
+        case SURF_SQ:
+        {
+            return make_unit_vector(make_real3(2 * d[0] * pos[0] + d[3],
+                                               2 * d[1] * pos[1] + d[4],
+                                               2 * d[2] * pos[2] + d[5]));
+        }
+        case SURF_GQ:
+        {
+            real x = pos[0], y = pos[1], z = pos[2];
+            return make_unit_vector(
+                make_real3(2 * d[0] * x + d[3] * y + d[5] * z + d[6],
+                           2 * d[1] * y + d[3] * x + d[4] * z + d[7],
+                           2 * d[2] * z + d[4] * y + d[5] * x + d[8]));
+        }
+        default: return make_real3(0, 0, 1);
+    }
+}
+
+B2_D bool surface_simple_safety(u8 type)
+{
+    return type <= SURF_SC || type == SURF_P || type == SURF_S;
+}
+
+//! Safety distance to one surface (CalcSafetyDistance, SurfaceFunctors.hh)
+B2_D real surface_safety(SurfaceRef const& s, Real3 const& pos)
+{
+    if (!surface_simple_safety(s.type))
+        return 0;
+    Real3 dir = surface_normal(s, pos);
+    if (isnan(dir[0]))
+        return real_inf();
+    int sense = surface_sense(s, pos);
+    if (sense > 0)
+    {
+        dir[0] *= -1;
+        dir[1] *= -1;
+        dir[2] *= -1;
+    }
+    else if (sense == 0)
+    {
+        return 0;
+    }
+    Roots r = surface_intersect(s, pos, dir, false);
+    if (surface_num_isect(s.type) == 1)
+        return r.r[0];
+    return r.r[1] < r.r[0] ? r.r[1] : r.r[0];
+}
+
+//---------------------------------------------------------------------------//
+// VOLUMES, LOGIC
+//---------------------------------------------------------------------------//
+struct VolumeRef
+{
+    u32 face_begin;
+    u32 num_faces;
+    u32 logic_begin;
+    u32 logic_end;
+    u32 flags;
+    u32 max_isect;
+};
+
+B2_D VolumeRef get_volume(GeoParams const& g, SimpleUnit const& u, u32 local_volume)
+{
+    u32 rec = u.vol_begin + local_volume;
+    VolumeRef v;
+    v.face_begin = g.vol_face_begin[rec];
+    v.num_faces = g.vol_face_end[rec] - v.face_begin;
+    v.logic_begin = g.vol_logic_begin[rec];
+    v.logic_end = g.vol_logic_end[rec];
+    v.flags = g.vol_flags[rec];
+    v.max_isect = g.vol_max_isect[rec];
+    return v;
+}
+
+B2_D u32 volume_surface(GeoParams const& g, VolumeRef const& v, u32 face)
+{
+    return g.local_surface_ids[v.face_begin + face];
+}
+
+//! Face index of a local surface in this volume (sorted face list) or INVALID
+B2_D u32 volume_find_face(GeoParams const& g, VolumeRef const& v, u32 surface)
+{
+    u32 lo = 0, len = v.num_faces;
+    while (len > 0)
+    {
+        u32 half = len >> 1;
+        u32 mid = lo + half;
+        if (g.local_surface_ids[v.face_begin + mid] < surface)
+        {
+            lo = mid + 1;
+            len -= half + 1;
+        }
+        else
+            len = half;
+    }
+    if (lo == v.num_faces || g.local_surface_ids[v.face_begin + lo] != surface)
+        return INVALID;
+    return lo;
+}
+
+//! Evaluate RPN logic over a bitmask of face senses (bit i set = outside)
+B2_D bool eval_logic(GeoParams const& g, VolumeRef const& v, u32 senses)
+{
+    u32 stack = 0;
+    for (u32 i = v.logic_begin; i < v.logic_end; ++i)
+    {
+        u32 tok = g.logic_ints[i];
+        if (tok < LOGIC_BEGIN)
+        {
+            stack = (stack << 1) | ((senses >> tok) & 1u);
+        }
+        else if (tok == LOGIC_TRUE)
+        {
+            stack = (stack << 1) | 1u;
+        }
+        else if (tok == LOGIC_OR)
+        {
+            stack = (stack >> 1) | (stack & 1u);
+        }
+        else if (tok == LOGIC_AND)
+        {
+            u32 t = stack & 1u;
+            stack = (stack >> 1) & (t | ~u32(1));
+        }
+        else if (tok == LOGIC_NOT)
+        {
+            stack ^= 1u;
+        }
+    }
+    return stack & 1u;
+}
+
+struct OnFace
+{
+    u32 face;   // INVALID when not on a face
+    u8 sense;   // 0 inside, 1 outside
+};
+
+//! Senses of all faces of a volume as a bitmask; reports first "on" face
+//! (SenseCalculator.hh)
+B2_D u32 calc_senses(GeoParams const& g,
+                     SimpleUnit const& u,
+                     VolumeRef const& v,
+                     Real3 const& pos,
+                     OnFace& face)
+{
+    u32 senses = 0;
+    for (u32 f = 0; f < v.num_faces; ++f)
+    {
+        u32 cur;
+        if (f != face.face)
+        {
+            int ss = surface_sense(get_surface(g, u, volume_surface(g, v, f)), pos);
+            cur = ss >= 0;
+            if (face.face == INVALID && ss == 0)
+            {
+                face.face = f;
+                face.sense = cur;
+            }
+        }
+        else
+        {
+            cur = face.sense;
+        }
+        senses |= cur << f;
+    }
+    return senses;
+}
+
+//---------------------------------------------------------------------------//
+// BIH TRAVERSAL (reference detail/BIHTraverser.hh:103-295)
+//---------------------------------------------------------------------------//
+B2_D bool bbox_contains(float const* bb, Real3 const& p)
+{
+    // BoundingBox<float> is_inside: lower <= p <= upper per axis
+    for (int ax = 0; ax < 3; ++ax)
+    {
+        if (!(p[ax] >= bb[ax] && p[ax] <= bb[3 + ax]))
+            return false;
+    }
+    return true;
+}
+
+template<class F>
+B2_D u32 bih_find_volume(GeoParams const& g, SimpleUnit const& u, Real3 const& pos, F&& is_inside)
+{
+    u32 const leaf_offset = u.inner_count;
+    u32 previous = INVALID;
+    u32 current = 0;
+    do
+    {
+        u32 next;
+        if (current >= leaf_offset)
+        {
+            // leaf: test its volumes
+            u32 leaf = u.leaf_begin + (current - leaf_offset);
+            u32 vb = g.bih_leaf_vol_begin[leaf];
+            u32 ve = g.bih_leaf_vol_end[leaf];
+            for (u32 i = vb; i < ve; ++i)
+            {
+                u32 id = g.bih_local_volume_ids[i];
+                if (bbox_contains(g.bih_bboxes + 6 * (u.bbox_begin + id), pos) && is_inside(id))
+                    return id;
+            }
+            next = previous;
+        }
+        else
+        {
+            u32 node = u.inner_begin + current;
+            u32 parent = g.bih_inner_parent[node];
+            u32 axis = g.bih_inner_axis[node];
+            u32 lchild = g.bih_inner_left_child[node];
+            u32 rchild = g.bih_inner_right_child[node];
+            real pp = pos[axis];
+            if (previous == parent)
+            {
+                // visit left if the point is below the left plane, else right
+                if (pp < g.bih_inner_left_pos[node])
+                    next = lchild;
+                else
+                    next = rchild;
+            }
+            else if (previous == lchild)
+            {
+                if (g.bih_inner_right_pos[node] < pp)
+                    next = rchild;
+                else
+                    next = parent;
+            }
+            else
+            {
+                next = parent;
+            }
+        }
+        previous = current;
+        current = next;
+    } while (current != INVALID);
+
+    for (u32 i = 0; i < u.inf_count; ++i)
+    {
+        u32 id = g.bih_local_volume_ids[u.inf_begin + i];
+        if (is_inside(id))
+            return id;
+    }
+    return INVALID;
+}
+
+//---------------------------------------------------------------------------//
+// SIMPLE UNIT TRACKER
+//---------------------------------------------------------------------------//
+struct LocalState
+{
+    Real3 pos;
+    Real3 dir;
+    u32 volume;
+    u32 surface;     // local surface id or INVALID
+    u8 sense;
+};
+
+struct Initialization
+{
+    u32 volume;
+    u32 surface;
+    u8 sense;
+};
+
+struct Intersection
+{
+    u32 surface;  // INVALID = none
+    u8 sense;
+    real distance;
+};
+
+B2_D Initialization unit_initialize(GeoParams const& g, SimpleUnit const& u, Real3 const& pos)
+{
+    bool on_surface = false;
+    auto is_inside = [&](u32 id) -> bool {
+        VolumeRef vol = get_volume(g, u, id);
+        OnFace face{INVALID, 0};
+        u32 senses = calc_senses(g, u, vol, pos, face);
+        on_surface = (face.face != INVALID);
+        return eval_logic(g, vol, senses);
+    };
+    u32 id = bih_find_volume(g, u, pos, is_inside);
+    if (on_surface)
+        id = INVALID;
+    else if (id == INVALID)
+        id = u.background;
+    return Initialization{id, INVALID, 0};
+}
+
+B2_D Initialization unit_cross_boundary(GeoParams const& g, SimpleUnit const& u, LocalState const& st)
+{
+    u32 on_surf = INVALID;
+    u8 on_sense = 0;
+    auto is_inside = [&](u32 id) -> bool {
+        if (id == st.volume)
+            return false;
+        VolumeRef vol = get_volume(g, u, id);
+        OnFace face{volume_find_face(g, vol, st.surface), st.sense};
+        u32 senses = calc_senses(g, u, vol, st.pos, face);
+        if (eval_logic(g, vol, senses))
+        {
+            on_surf = (face.face != INVALID) ? volume_surface(g, vol, face.face) : INVALID;
+            on_sense = face.sense;
+            return true;
+        }
+        return false;
+    };
+    u32 conn = u.conn_begin + st.surface;
+    u32 nb = g.conn_begin[conn], ne = g.conn_end[conn];
+    if (ne - nb < 3)
+    {
+        for (u32 i = nb; i < ne; ++i)
+        {
+            u32 id = g.local_volume_ids[i];
+            if (is_inside(id))
+                return Initialization{id, on_surf, on_sense};
+        }
+    }
+    else
+    {
+        u32 id = bih_find_volume(g, u, st.pos, is_inside);
+        if (id != INVALID)
+            return Initialization{id, on_surf, on_sense};
+    }
+    return Initialization{u.background, st.surface, st.sense};
+}
+
+//! Distance to the boundary of the current volume. max_dist < 0 = unlimited.
+B2_D Intersection unit_intersect(GeoParams const& g,
+                                 SimpleUnit const& u,
+                                 LocalState const& st,
+                                 bool limited,
+                                 real max_dist)
+{
+    VolumeRef vol = get_volume(g, u, st.volume);
+    u32 on_face = (st.surface != INVALID) ? volume_find_face(g, vol, st.surface) : INVALID;
+    bool const simple = !(vol.flags & (VOL_INTERNAL_SURFACES | VOL_IMPLICIT));
+
+    real dist[ORANGE_MAX_ISECT];
+    u8 face_of[ORANGE_MAX_ISECT];
+    u32 num_isect = 0;
+    for (u32 f = 0; f < vol.num_faces; ++f)
+    {
+        SurfaceRef s = get_surface(g, u, volume_surface(g, vol, f));
+        bool on = (f == on_face);
+        int nroots = surface_num_isect(s.type);
+        if (nroots == 1 && on)
+            continue;
+        Roots r = surface_intersect(s, st.pos, st.dir, on);
+        for (int k = 0; k < nroots; ++k)
+        {
+            real d = r.r[k];
+            bool valid = limited ? (d <= max_dist) : (d < real_max());
+            if (valid)
+            {
+                dist[num_isect] = d;
+                face_of[num_isect] = f;
+                ++num_isect;
+            }
+        }
+    }
+    Intersection result{INVALID, 0, real_inf()};
+    if (num_isect == 0)
+    {
+        // fallthrough
+    }
+    else if (simple)
+    {
+        u32 best = 0;
+        for (u32 i = 1; i < num_isect; ++i)
+            if (dist[i] < dist[best])
+                best = i;
+        u32 surface = volume_surface(g, vol, face_of[best]);
+        u8 cur_sense;
+        if (surface == st.surface)
+            cur_sense = st.sense;
+        else
+            cur_sense = surface_sense(get_surface(g, u, surface), st.pos) >= 0;
+        result.surface = surface;
+        result.sense = cur_sense;
+        result.distance = dist[best];
+    }
+    else
+    {
+        // Sort intersection indices by distance (insertion sort: tiny N)
+        u8 order[ORANGE_MAX_ISECT];
+        for (u32 i = 0; i < num_isect; ++i)
+        {
+            u32 j = i;
+            while (j > 0 && dist[i] < dist[order[j - 1]])
+            {
+                order[j] = order[j - 1];
+                --j;
+            }
+            order[j] = i;
+        }
+        if (vol.flags & VOL_INTERNAL_SURFACES)
+        {
+            OnFace face{on_face, st.sense};
+            u32 senses = calc_senses(g, u, vol, st.pos, face);
+            for (u32 k = 0; k < num_isect; ++k)
+            {
+                u32 isect = order[k];
+                u32 f = face_of[isect];
+                senses ^= (1u << f);
+                u32 new_sense = (senses >> f) & 1u;
+                if (!eval_logic(g, vol, senses))
+                {
+                    result.surface = volume_surface(g, vol, f);
+                    result.sense = new_sense ^ 1u;
+                    result.distance = dist[isect];
+                    break;
+                }
+            }
+        }
+        else if (vol.flags & VOL_IMPLICIT)
+        {
+            // Background volume: faces are *all* unit surfaces (face id ==
+            // local surface id); test neighbours just past each crossing
+            real bump = g.tol_abs;
+            for (int ax = 0; ax < 3; ++ax)
+            {
+                real t = g.tol_rel * fabs(st.pos[ax]);
+                bump = t > bump ? t : bump;
+            }
+            for (u32 k = 0; k < num_isect && result.surface == INVALID; ++k)
+            {
+                u32 isect = order[k];
+                u32 surface = volume_surface(g, vol, face_of[isect]);
+                Real3 pos = st.pos;
+                axpy(dist[isect] + bump, st.dir, pos);
+                u32 conn = u.conn_begin + surface;
+                for (u32 i = g.conn_begin[conn]; i < g.conn_end[conn]; ++i)
+                {
+                    u32 vid = g.local_volume_ids[i];
+                    VolumeRef nv = get_volume(g, u, vid);
+                    OnFace face{INVALID, 0};
+                    u32 senses = calc_senses(g, u, nv, pos, face);
+                    if (eval_logic(g, nv, senses))
+                    {
+                        u32 nf = volume_find_face(g, nv, surface);
+                        result.distance = dist[isect];
+                        result.surface = surface;
+                        result.sense = ((senses >> nf) & 1u) ^ 1u;
+                        break;
+                    }
+                }
+            }
+        }
+    }
+    if (limited && result.surface == INVALID)
+        result.distance = max_dist;
+    return result;
+}
+
+B2_D real unit_safety(GeoParams const& g, SimpleUnit const& u, Real3 const& pos, u32 volid)
+{
+    VolumeRef vol = get_volume(g, u, volid);
+    if (!(vol.flags & VOL_SIMPLE_SAFETY))
+        return 0;
+    real result = real_inf();
+    for (u32 f = 0; f < vol.num_faces; ++f)
+    {
+        real d = surface_safety(get_surface(g, u, volume_surface(g, vol, f)), pos);
+        result = d < result ? d : result;
+    }
+    return result;
+}
+
+B2_D u32 unit_daughter(GeoParams const& g, SimpleUnit const& u, u32 volid)
+{
+    return g.vol_daughter[u.vol_begin + volid];
+}
+
+//---------------------------------------------------------------------------//
+// TRANSFORMS
+//---------------------------------------------------------------------------//
+B2_D void transform_down(GeoParams const& g, u32 transform_id, Real3& pos, Real3& dir)
+{
+    u8 type = g.transform_type[transform_id];
+    real const* d = g.reals + g.transform_offset[transform_id];
+    if (type == TRANSFORM_TRANSLATION)
+    {
+        pos[0] -= d[0];
+        pos[1] -= d[1];
+        pos[2] -= d[2];
+    }
+    else if (type == TRANSFORM_TRANSFORMATION)
+    {
+        // r_d = R^T (r_p - t): rot stored row-major in d[0..8], tra in d[9..11]
+        Real3 t = make_real3(pos[0] - d[9], pos[1] - d[10], pos[2] - d[11]);
+        Real3 np, nd;
+        for (int i = 0; i < 3; ++i)
+        {
+            np[i] = 0;
+            nd[i] = 0;
+            for (int j = 0; j < 3; ++j)
+            {
+                np[i] = fma(d[3 * j + i], t[j], np[i]);
+                nd[i] = fma(d[3 * j + i], dir[j], nd[i]);
+            }
+        }
+        pos = np;
+        dir = nd;
+    }
+}
+
+B2_D Real3 rotate_up(GeoParams const& g, u32 transform_id, Real3 const& dir)
+{
+    u8 type = g.transform_type[transform_id];
+    if (type != TRANSFORM_TRANSFORMATION)
+        return dir;
+    real const* d = g.reals + g.transform_offset[transform_id];
+    Real3 nd;
+    for (int i = 0; i < 3; ++i)
+    {
+        nd[i] = 0;
+        for (int j = 0; j < 3; ++j)
+            nd[i] = fma(d[3 * i + j], dir[j], nd[i]);
+    }
+    return nd;
+}
+
+//---------------------------------------------------------------------------//
+// TRACK VIEW
+//---------------------------------------------------------------------------//
+struct GeoTrack
+{
+    GeoParams const& g;
+    StateView const& s;
+    u32 slot;
+    bool failed;
+
+    B2_D GeoTrack(ParamsView const& p, StateView const& st, u32 sl)
+        : g(p.geo), s(st), slot(sl), failed(false)
+    {
+    }
+
+    // --- per-level accessors
+    B2_D u32 lidx(u32 level) const { return level * s.num_slots + slot; }
+    B2_D Real3 pos(u32 level) const
+    {
+        u32 n = s.num_slots * s.max_depth;
+        u32 i = lidx(level);
+        return make_real3(s.geo_pos[i], s.geo_pos[n + i], s.geo_pos[2 * n + i]);
+    }
+    B2_D Real3 dir(u32 level) const
+    {
+        u32 n = s.num_slots * s.max_depth;
+        u32 i = lidx(level);
+        return make_real3(s.geo_dir[i], s.geo_dir[n + i], s.geo_dir[2 * n + i]);
+    }
+    B2_D void set_pos(u32 level, Real3 const& v) const
+    {
+        u32 n = s.num_slots * s.max_depth;
+        u32 i = lidx(level);
+        s.geo_pos[i] = v[0];
+        s.geo_pos[n + i] = v[1];
+        s.geo_pos[2 * n + i] = v[2];
+    }
+    B2_D void set_dir(u32 level, Real3 const& v) const
+    {
+        u32 n = s.num_slots * s.max_depth;
+        u32 i = lidx(level);
+        s.geo_dir[i] = v[0];
+        s.geo_dir[n + i] = v[1];
+        s.geo_dir[2 * n + i] = v[2];
+    }
+    B2_D u32 vol(u32 level) const { return s.geo_vol[lidx(level)]; }
+    B2_D u32 univ(u32 level) const { return s.geo_univ[lidx(level)]; }
+
+    B2_D u32 level() const { return s.geo_level[slot]; }
+    B2_D Real3 pos() const { return pos(0); }
+    B2_D Real3 dir() const { return dir(0); }
+    B2_D bool is_on_boundary() const { return s.geo_surface_level[slot] != INVALID; }
+    B2_D bool is_outside() const { return vol(0) == 0; }
+
+    B2_D u32 volume_id() const
+    {
+        u32 lev = level();
+        return g.universe_volume_offset[univ(lev)] + vol(lev);
+    }
+    B2_D u32 surface_id() const
+    {
+        u32 sl = s.geo_surface_level[slot];
+        if (sl == INVALID)
+            return INVALID;
+        return g.universe_surface_offset[univ(sl)] + s.geo_surf[slot];
+    }
+
+    B2_D void clear_next() const
+    {
+        s.geo_next_step[slot] = 0;
+        s.geo_next_surf[slot] = INVALID;
+    }
+    B2_D void clear_surface() const { s.geo_surface_level[slot] = INVALID; }
+
+    B2_D SimpleUnit const& unit_of(u32 universe) const
+    {
+        return g.simple_units[g.universe_index[universe]];
+    }
+
+    B2_D u32 daughter_of(u32 universe, u32 volume) const
+    {
+        return unit_daughter(g, unit_of(universe), volume);
+    }
+
+    //! Locate a track from scratch (OrangeTrackView::operator=(Initializer))
+    B2_D void initialize(Real3 const& ipos, Real3 const& idir)
+    {
+        failed = false;
+        Real3 lpos = ipos, ldir = idir;
+        u32 uid = 0;
+        u32 lev = 0;
+        u32 daughter;
+        do
+        {
+            SimpleUnit const& u = unit_of(uid);
+            Initialization tinit = unit_initialize(g, u, lpos);
+            if (tinit.volume == INVALID || tinit.surface != INVALID)
+            {
+                failed = true;
+                tinit.volume = 0;
+            }
+            s.geo_vol[lidx(lev)] = tinit.volume;
+            s.geo_univ[lidx(lev)] = uid;
+            set_pos(lev, lpos);
+            set_dir(lev, ldir);
+            daughter = unit_daughter(g, u, tinit.volume);
+            if (daughter != INVALID)
+            {
+                transform_down(g, g.daughter_transform[daughter], lpos, ldir);
+                uid = g.daughter_universe[daughter];
+                ++lev;
+            }
+        } while (daughter != INVALID);
+        s.geo_level[slot] = lev;
+        s.geo_boundary[slot] = 1;
+        clear_surface();
+        clear_next();
+    }
+
+    //! Copy another slot's location with a new direction (DetailedInitializer)
+    B2_D void initialize_from(u32 other, Real3 const& newdir)
+    {
+        failed = false;
+        u32 lev = s.geo_level[other];
+        if (other != slot)
+        {
+            s.geo_level[slot] = lev;
+            s.geo_surface_level[slot] = s.geo_surface_level[other];
+            s.geo_surf[slot] = s.geo_surf[other];
+            s.geo_sense[slot] = s.geo_sense[other];
+            s.geo_boundary[slot] = s.geo_boundary[other];
+            u32 n = s.num_slots * s.max_depth;
+            for (u32 l = 0; l <= lev; ++l)
+            {
+                u32 src = l * s.num_slots + other;
+                u32 dst = lidx(l);
+                for (int k = 0; k < 3; ++k)
+                {
+                    s.geo_pos[k * n + dst] = s.geo_pos[k * n + src];
+                    s.geo_dir[k * n + dst] = s.geo_dir[k * n + src];
+                }
+                s.geo_vol[dst] = s.geo_vol[src];
+                s.geo_univ[dst] = s.geo_univ[src];
+            }
+        }
+        clear_next();
+        set_dir_all_levels(newdir);
+    }
+
+    B2_D void set_dir_all_levels(Real3 const& newdir)
+    {
+        Real3 ldir = newdir;
+        u32 lev = level();
+        for (u32 l = 0; l < lev; ++l)
+        {
+            set_dir(l, ldir);
+            u32 daughter = daughter_of(univ(l), vol(l));
+            Real3 dummy = make_real3(0, 0, 0);
+            transform_down(g, g.daughter_transform[daughter], dummy, ldir);
+        }
+        set_dir(lev, ldir);
+    }
+
+    B2_D LocalState local_state(u32 lev) const
+    {
+        LocalState st;
+        st.pos = pos(lev);
+        st.dir = dir(lev);
+        st.volume = vol(lev);
+        if (lev == s.geo_surface_level[slot])
+        {
+            st.surface = s.geo_surf[slot];
+            st.sense = s.geo_sense[slot];
+        }
+        else
+        {
+            st.surface = INVALID;
+            st.sense = 0;
+        }
+        return st;
+    }
+
+    //! Distance to next boundary over all levels (find_next_step[_impl])
+    B2_D Propagation find_next_step(bool limited, real max_step)
+    {
+        if (s.geo_boundary[slot] == 0)
+        {
+            // reentrant: already "at" the next boundary
+            return Propagation{0, true, false};
+        }
+        Intersection isect = unit_intersect(g, unit_of(0), local_state(0), limited, max_step);
+        u32 min_level = 0;
+        u32 lev = level();
+        for (u32 l = 1; l <= lev; ++l)
+        {
+            Intersection li
+                = unit_intersect(g, unit_of(univ(l)), local_state(l), true, isect.distance);
+            if (li.distance < isect.distance)
+            {
+                isect = li;
+                min_level = l;
+            }
+        }
+        s.geo_next_step[slot] = isect.distance;
+        s.geo_next_surf[slot] = isect.surface;
+        s.geo_next_sense[slot] = isect.sense;
+        if (isect.surface != INVALID)
+            s.geo_next_level[slot] = min_level;
+        return Propagation{isect.distance, isect.surface != INVALID, false};
+    }
+
+    B2_D void move_to_boundary()
+    {
+        real dist = s.geo_next_step[slot];
+        u32 lev = level();
+        for (u32 l = 0; l <= lev; ++l)
+        {
+            Real3 p = pos(l);
+            axpy(dist, dir(l), p);
+            set_pos(l, p);
+        }
+        s.geo_surface_level[slot] = s.geo_next_level[slot];
+        s.geo_surf[slot] = s.geo_next_surf[slot];
+        s.geo_sense[slot] = s.geo_next_sense[slot];
+        clear_next();
+    }
+
+    B2_D void move_internal(real dist)
+    {
+        u32 lev = level();
+        for (u32 l = 0; l <= lev; ++l)
+        {
+            Real3 p = pos(l);
+            axpy(dist, dir(l), p);
+            set_pos(l, p);
+        }
+        s.geo_next_step[slot] = s.geo_next_step[slot] - dist;
+        clear_surface();
+    }
+
+    B2_D void move_internal_pos(Real3 const& newpos)
+    {
+        Real3 lpos = newpos;
+        u32 lev = level();
+        for (u32 l = 0; l < lev; ++l)
+        {
+            set_pos(l, lpos);
+            u32 daughter = daughter_of(univ(l), vol(l));
+            Real3 dummy = make_real3(0, 0, 0);
+            // translate only: rotate position with a throwaway direction
+            transform_down(g, g.daughter_transform[daughter], lpos, dummy);
+        }
+        set_pos(lev, lpos);
+        clear_surface();
+        clear_next();
+    }
+
+    B2_D void cross_boundary()
+    {
+        if (s.geo_boundary[slot] == 0)
+        {
+            s.geo_boundary[slot] = 1;
+            return;
+        }
+        s.geo_sense[slot] ^= 1;
+        s.geo_boundary[slot] = 1;
+
+        u32 lev = s.geo_surface_level[slot];
+        u32 universe = univ(lev);
+        LocalState local;
+        local.pos = pos(lev);
+        local.dir = dir(lev);
+        local.volume = vol(lev);
+        local.surface = s.geo_surf[slot];
+        local.sense = s.geo_sense[slot];
+
+        Initialization ci = unit_cross_boundary(g, unit_of(universe), local);
+        u32 volume = ci.volume;
+        if (volume == INVALID)
+        {
+            failed = true;
+            volume = 0;
+        }
+        s.geo_vol[lidx(lev)] = volume;
+        u32 daughter = daughter_of(universe, volume);
+        while (daughter != INVALID)
+        {
+            ++lev;
+            transform_down(g, g.daughter_transform[daughter], local.pos, local.dir);
+            universe = g.daughter_universe[daughter];
+            Initialization ti = unit_initialize(g, unit_of(universe), local.pos);
+            volume = ti.volume;
+            if (volume == INVALID)
+            {
+                failed = true;
+                volume = 0;
+            }
+            daughter = daughter_of(universe, volume);
+            s.geo_vol[lidx(lev)] = volume;
+            s.geo_univ[lidx(lev)] = universe;
+            set_pos(lev, local.pos);
+            set_dir(lev, local.dir);
+        }
+        s.geo_level[slot] = lev;
+    }
+
+    B2_D void set_dir(Real3 const& newdir)
+    {
+        if (is_on_boundary())
+        {
+            u32 sl = s.geo_surface_level[slot];
+            SimpleUnit const& u = unit_of(univ(sl));
+            Real3 normal = surface_normal(get_surface(g, u, s.geo_surf[slot]), pos(sl));
+            for (int l = int(level()) - 1; l >= 0; --l)
+            {
+                u32 daughter = daughter_of(univ(l), vol(l));
+                normal = rotate_up(g, g.daughter_transform[daughter], normal);
+            }
+            if ((dot(normal, newdir) >= 0) != (dot(normal, dir()) >= 0))
+                s.geo_boundary[slot] ^= 1;
+        }
+        set_dir_all_levels(newdir);
+        clear_next();
+    }
+
+    B2_D real find_safety()
+    {
+        real min_safety = real_inf();
+        u32 lev = level();
+        for (u32 l = 0; l <= lev; ++l)
+        {
+            real sd = unit_safety(g, unit_of(univ(l)), pos(l), vol(l));
+            min_safety = sd < min_safety ? sd : min_safety;
+        }
+        return min_safety;
+    }
+};
+}  // namespace b200

@@ -1,0 +1,160 @@
+//---------------------------------------------------------------------------//
+// Basic types and small-vector math shared by every kernel.
+//
+// Arithmetic notes (they matter for bit-level agreement with the reference's
+// host build, which is compiled without FMA contraction):
+//  * this code is compiled with --fmad=false, so a*b+c is two roundings;
+//  * where the reference calls fma() explicitly (dot_product, axpy, the
+//    interpolator: /root/reference/src/corecel/math/ArrayUtils.hh:78-100,
+//    /root/reference/src/corecel/grid/Interpolator.hh) we call fma() too.
+//---------------------------------------------------------------------------//
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200
+{
+using u8 = uint8_t;
+using u16 = uint16_t;
+using u32 = uint32_t;
+using u64 = uint64_t;
+using real = double;
+
+constexpr u32 INVALID = 0xffffffffu;
+
+#define B2_HD __host__ __device__ __forceinline__
+#define B2_D __device__ __forceinline__
+
+//! Track status: same numbering as the reference's TrackStatus
+//! (/root/reference/src/celeritas/Types.hh:113-122)
+enum TrackStatus : u8
+{
+    ST_INACTIVE = 0,
+    ST_INITIALIZING = 1,
+    ST_ALIVE = 2,
+    ST_ERRORED = 3,
+    ST_KILLED = 4
+};
+
+//! Track ordering (reference TrackOrder, Types.hh:151-171)
+enum TrackOrder : u32
+{
+    ORDER_NONE = 0,
+    ORDER_INIT_CHARGE = 1,
+};
+
+struct Real3
+{
+    real v[3];
+    B2_HD real& operator[](int i) { return v[i]; }
+    B2_HD real const& operator[](int i) const { return v[i]; }
+};
+
+B2_HD Real3 make_real3(real x, real y, real z)
+{
+    Real3 r;
+    r.v[0] = x;
+    r.v[1] = y;
+    r.v[2] = z;
+    return r;
+}
+
+B2_HD real ipow2(real x)
+{
+    return x * x;
+}
+
+//! fma-chained dot product (ArrayUtils.hh:91-100)
+B2_HD real dot(Real3 const& a, Real3 const& b)
+{
+    real r = 0;
+    r = fma(a[0], b[0], r);
+    r = fma(a[1], b[1], r);
+    r = fma(a[2], b[2], r);
+    return r;
+}
+
+//! y += a x with fma (ArrayUtils.hh:77-85)
+B2_HD void axpy(real a, Real3 const& x, Real3& y)
+{
+    y[0] = fma(a, x[0], y[0]);
+    y[1] = fma(a, x[1], y[1]);
+    y[2] = fma(a, x[2], y[2]);
+}
+
+B2_HD real norm(Real3 const& a)
+{
+    return sqrt(dot(a, a));
+}
+
+B2_HD Real3 make_unit_vector(Real3 const& a)
+{
+    real scale = 1 / norm(a);
+    return make_real3(a[0] * scale, a[1] * scale, a[2] * scale);
+}
+
+//! Direction from polar cosine and azimuth (ArrayUtils.hh:167-173)
+B2_HD Real3 from_spherical(real costheta, real phi)
+{
+    real sintheta = sqrt(1 - costheta * costheta);
+    return make_real3(sintheta * cos(phi), sintheta * sin(phi), costheta);
+}
+
+//! Rotate `dir` (given relative to +z) into the frame whose z axis is `rot`
+//! (ArrayUtils.hh:215-263)
+B2_HD Real3 rotate(Real3 const& dir, Real3 const& rot)
+{
+    real sintheta = sqrt(1 - ipow2(rot[2]));
+    real cosphi, sinphi;
+    if (sintheta >= 0.005)
+    {
+        real inv = 1 / sintheta;
+        cosphi = rot[0] * inv;
+        sinphi = rot[1] * inv;
+    }
+    else if (sintheta > 0)
+    {
+        cosphi = rot[0] / sqrt(ipow2(rot[0]) + ipow2(rot[1]));
+        sinphi = sqrt(1 - ipow2(cosphi));
+    }
+    else
+    {
+        cosphi = 1;
+        sinphi = 0;
+    }
+    Real3 r = make_real3(
+        (rot[2] * dir[0] + sintheta * dir[2]) * cosphi - sinphi * dir[1],
+        (rot[2] * dir[0] + sintheta * dir[2]) * sinphi + cosphi * dir[1],
+        -sintheta * dir[0] + rot[2] * dir[2]);
+    return make_unit_vector(r);
+}
+
+B2_HD real real_inf()
+{
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double(0x7ff0000000000000LL);
+#else
+    return __builtin_huge_val();
+#endif
+}
+
+B2_HD real real_max()
+{
+    return 1.7976931348623157e308;
+}
+
+//! Linear interpolation through (xl,yl),(xr,yr) as the reference computes it
+//! (Interpolator.hh: slope = (yr-yl)/(xr-xl); y = fma(slope, x-xl, yl))
+B2_HD real lerp_points(real xl, real yl, real xr, real yr, real x)
+{
+    real slope = (yr - yl) / (xr - xl);
+    return fma(slope, x - xl, yl);
+}
+
+namespace constants
+{
+constexpr real pi = 3.14159265358979323846;
+constexpr real c_light = 2.99792458e10;  // cm/s (CGS native)
+}  // namespace constants
+}  // namespace b200

@@ -1,0 +1,409 @@
+//---------------------------------------------------------------------------//
+// Device views: plain structs of raw device pointers and scalars.
+//
+// ParamsView is the immutable problem (what the reference keeps in
+// CoreParamsData, /root/reference/src/celeritas/global/CoreTrackData.hh:65-106)
+// re-laid out as flat columns in HBM. StateView is the mutable per-track-slot
+// state (CoreStateData, CoreTrackData.hh:114-160) as a structure of arrays:
+// every field is its own contiguous array indexed by track slot, so that a
+// warp touching one field of 32 consecutive slots issues one coalesced access.
+// Multi-level fields (ORANGE per-level position/direction/volume) are stored
+// level-major: index = level * num_slots + slot.
+//---------------------------------------------------------------------------//
+#pragma once
+
+#include "types.cuh"
+
+namespace b200
+{
+//---------------------------------------------------------------------------//
+// GEOMETRY (ORANGE)
+//---------------------------------------------------------------------------//
+enum SurfaceType : u8
+{
+    SURF_PX = 0, SURF_PY, SURF_PZ, SURF_CXC, SURF_CYC, SURF_CZC, SURF_SC,
+    SURF_CX, SURF_CY, SURF_CZ, SURF_P, SURF_S, SURF_KX, SURF_KY, SURF_KZ,
+    SURF_SQ, SURF_GQ, SURF_INV, SURF_SIZE
+};
+
+enum UniverseType : u8
+{
+    UNIV_SIMPLE = 0,
+    UNIV_RECT_ARRAY = 1
+};
+
+enum TransformType : u8
+{
+    TRANSFORM_NONE = 0,
+    TRANSFORM_TRANSLATION = 1,
+    TRANSFORM_TRANSFORMATION = 2
+};
+
+enum VolumeFlags : u32
+{
+    VOL_INTERNAL_SURFACES = 0x1,
+    VOL_IMPLICIT = 0x2,
+    VOL_SIMPLE_SAFETY = 0x4,
+    VOL_EMBEDDED_UNIVERSE = 0x8
+};
+
+//! Logic tokens (reference logic::OperatorToken, OrangeTypes.hh:244-254)
+constexpr u32 LOGIC_BEGIN = 0xfff9u;
+constexpr u32 LOGIC_TRUE = 0xfffbu;
+constexpr u32 LOGIC_OR = 0xfffcu;
+constexpr u32 LOGIC_AND = 0xfffdu;
+constexpr u32 LOGIC_NOT = 0xfffeu;
+
+//! One row per simple unit (16 x u32), see Params.cc for the column order
+struct SimpleUnit
+{
+    u32 surf_begin;      // first entry in surface_types / real_ids
+    u32 surf_end;
+    u32 real_id_begin;   // first entry in real_ids for this unit's surfaces
+    u32 conn_begin;      // first connectivity record (indexed by local surface)
+    u32 vol_begin;       // first volume record
+    u32 vol_count;
+    u32 background;      // local volume id or INVALID
+    u32 simple_safety;
+    u32 bbox_begin;      // first bbox (indexed by local volume)
+    u32 inner_begin;
+    u32 inner_count;
+    u32 leaf_begin;
+    u32 leaf_count;
+    u32 inf_begin;       // into bih_local_volume_ids
+    u32 inf_count;
+    u32 pad;
+};
+
+struct RectArray
+{
+    u32 daughter_begin;
+    u32 daughter_count;
+    u32 dims[3];
+    u32 grid_begin[3];  // interleaved below as begin/end pairs in the image
+    u32 grid_end[3];
+    u32 surf_offsets[4];
+    u32 pad;
+};
+
+struct GeoParams
+{
+    u32 max_depth;
+    u32 max_faces;
+    u32 max_intersections;
+    u32 num_universes;
+    real tol_rel;
+    real tol_abs;
+
+    u8 const* universe_type;
+    u32 const* universe_index;
+    u32 const* universe_surface_offset;
+    u32 const* universe_volume_offset;
+
+    SimpleUnit const* simple_units;
+    u32 const* rect_arrays;  // 16 u32 per array (see orange.cuh)
+
+    u32 const* local_surface_ids;
+    u32 const* local_volume_ids;
+    u32 const* real_ids;
+    u16 const* logic_ints;
+    real const* reals;
+    u8 const* surface_types;
+
+    u32 const* vol_face_begin;
+    u32 const* vol_face_end;
+    u32 const* vol_logic_begin;
+    u32 const* vol_logic_end;
+    u32 const* vol_max_isect;
+    u32 const* vol_flags;
+    u32 const* vol_daughter;
+
+    u32 const* conn_begin;
+    u32 const* conn_end;
+
+    u32 const* daughter_universe;
+    u32 const* daughter_transform;
+    u8 const* transform_type;
+    u32 const* transform_offset;
+
+    float const* bih_bboxes;  // 6 per bbox: lower xyz, upper xyz
+    u32 const* bih_local_volume_ids;
+    u32 const* bih_inner_parent;
+    u32 const* bih_inner_axis;
+    float const* bih_inner_left_pos;
+    u32 const* bih_inner_left_child;
+    float const* bih_inner_right_pos;
+    u32 const* bih_inner_right_child;
+    u32 const* bih_leaf_parent;
+    u32 const* bih_leaf_vol_begin;
+    u32 const* bih_leaf_vol_end;
+
+    u32 const* volume_material;  // global volume id -> material id
+};
+
+//---------------------------------------------------------------------------//
+// MATERIALS / PARTICLES / CUTOFFS
+//---------------------------------------------------------------------------//
+struct MatParams
+{
+    u32 num_materials;
+    u32 num_elements;
+    u32 max_element_components;
+    u32 const* element_z;
+    real const* element_reals;   // 6 per element: mass, cbrt_z, cbrt_zzp, log_z, coulomb, mass_rad_coeff
+    u32 const* elcomp_element;
+    real const* elcomp_fraction;
+    u32 const* material_elcomp_begin;
+    u32 const* material_elcomp_end;
+    real const* material_reals;  // 8 per material: number_density, temperature, zeff, density, electron_density, rad_length, mean_exc_energy, log_mean_exc_energy
+};
+
+enum ElementReal { EL_MASS = 0, EL_CBRT_Z, EL_CBRT_ZZP, EL_LOG_Z, EL_COULOMB, EL_MASS_RAD_COEFF, EL_NUM_REALS };
+enum MaterialReal { MAT_NUMBER_DENSITY = 0, MAT_TEMPERATURE, MAT_ZEFF, MAT_DENSITY, MAT_ELECTRON_DENSITY, MAT_RAD_LENGTH, MAT_MEAN_EXC, MAT_LOG_MEAN_EXC, MAT_NUM_REALS };
+
+struct ParticleParams
+{
+    u32 num_particles;
+    real const* mass;
+    real const* charge;
+    real const* decay_constant;
+    u8 const* matter;  // 1 = antiparticle
+};
+
+struct CutoffParams
+{
+    u32 num_particles;
+    u32 num_materials;
+    u32 apply_post_interaction;
+    u32 id_gamma, id_electron, id_positron;
+    real const* energy;  // [index][material]
+    real const* range;
+    u32 const* id_to_index;
+};
+
+//---------------------------------------------------------------------------//
+// PHYSICS TABLES
+//---------------------------------------------------------------------------//
+struct PhysParams
+{
+    u32 num_particles;
+    u32 max_processes;  // P
+    u32 num_materials;
+    u32 num_models;
+
+    real min_range;
+    real max_step_over_range;
+    real min_eprime_over_e;
+    real lowest_electron_energy;
+    real linear_loss_limit;
+    real fixed_step_limiter;
+    real lambda_limit;
+    real range_factor;
+    real safety_factor;
+
+    u32 model_to_action;
+    u32 step_limit_algorithm;
+    u32 fixed_step_action;
+
+    // Grids
+    u32 const* grid_size;
+    real const* grid_log_front;
+    real const* grid_log_back;
+    real const* grid_log_delta;
+    u32 const* grid_prime;
+    u32 const* grid_value_offset;
+    real const* reals;
+
+    // Per (particle, ppid)
+    u32 const* pp_num;        // [particle]
+    u32 const* pp_eloss_ppid; // [particle]
+    u32 const* pp_has_at_rest;
+    u32 const* pp_process;    // [particle][P]
+    u32 const* pp_grid;       // [3][particle][P][material]
+    u8 const* pp_integral;    // [particle][P]
+    real const* pp_energy_max_xs;  // [particle][P][material]
+    u32 const* pp_model_begin;     // [particle][P] -> pm_pmid
+    u32 const* pp_model_count;
+    u32 const* pm_energy_begin;    // [particle][P] -> pm_energy
+    real const* pm_energy;
+    u32 const* pm_pmid;
+    u32 const* pmid_model;         // [pmid] -> model id
+    u32 const* elsel_begin;        // [pmid][material] -> elsel_grid or INVALID
+    u32 const* elsel_count;
+    u32 const* elsel_grid;
+
+    // Hardwired (on-the-fly xs) models
+    u32 hw_photoelectric;       // process id
+    u32 hw_livermore_pe;        // model id
+    u32 hw_positron_annihilation;
+    u32 hw_eplusgg;
+    real hw_photoelectric_table_thresh;
+};
+
+enum ValueGridType { VGT_MACRO_XS = 0, VGT_ENERGY_LOSS = 1, VGT_RANGE = 2 };
+
+//---------------------------------------------------------------------------//
+// MODEL DATA
+//---------------------------------------------------------------------------//
+struct KleinNishinaParams
+{
+    u32 action;
+    u32 electron;
+    u32 gamma;
+    real inv_electron_mass;
+};
+
+struct ModelParams
+{
+    KleinNishinaParams kn;
+};
+
+//---------------------------------------------------------------------------//
+// RNG / SIM / INIT / CORE SCALARS
+//---------------------------------------------------------------------------//
+struct RngParams
+{
+    u32 seed;
+    u32 const* jump;              // [32][5]
+    u32 const* jump_subsequence;  // [32][5]
+};
+
+struct SimParams
+{
+    u32 has_looping;
+    u32 const* looping_steps;  // 2 per particle: max_subthreshold_steps, max_steps
+    real const* looping_energy;
+};
+
+struct CoreScalars
+{
+    u32 boundary_action;
+    u32 propagation_limit_action;
+    u32 tracking_cut_action;
+    u32 along_step_user_action;
+    u32 along_step_neutral_action;
+    u32 track_order;
+};
+
+struct ParamsView
+{
+    CoreScalars scalars;
+    GeoParams geo;
+    MatParams mat;
+    ParticleParams particle;
+    CutoffParams cutoff;
+    PhysParams phys;
+    ModelParams model;
+    RngParams rng;
+    SimParams sim;
+};
+
+//---------------------------------------------------------------------------//
+// STATE
+//---------------------------------------------------------------------------//
+constexpr int MAX_SECONDARIES = 2;
+
+struct StateView
+{
+    u32 num_slots;
+    u32 max_depth;
+    u32 max_processes;
+
+    // sim
+    u8* status;
+    u32* track_id;
+    u32* parent_id;
+    u32* event_id;
+    u32* num_steps;
+    u32* num_looping_steps;
+    real* time;
+    real* step_length;
+    u32* post_step_action;
+    u32* along_step_action;
+
+    // particle
+    u32* particle_id;
+    real* energy;
+
+    // material
+    u32* material_id;
+
+    // geometry
+    u32* geo_level;
+    u32* geo_surface_level;  // INVALID = not on a boundary
+    u32* geo_surf;
+    u8* geo_sense;
+    u8* geo_boundary;        // 1 = exiting, 0 = reentrant
+    u32* geo_next_level;
+    real* geo_next_step;
+    u32* geo_next_surf;
+    u8* geo_next_sense;
+    real* geo_pos;   // [3][level][slot]
+    real* geo_dir;   // [3][level][slot]
+    u32* geo_vol;    // [level][slot]
+    u32* geo_univ;   // [level][slot]
+
+    // physics
+    real* interaction_mfp;
+    real* macro_xs;
+    real* energy_deposition;
+    real* dedx_range;
+    real* msc_range;         // [3][slot]: range_init, range_factor, limit_min
+    u8* msc_is_displaced;
+    real* msc_true_path;
+    real* msc_geom_path;
+    real* msc_alpha;
+    real* per_process_xs;    // [P][slot]
+    u32* element;            // sampled element component
+    // secondaries produced this step, fixed storage per slot
+    u32* sec_particle;       // [MAX_SECONDARIES][slot]; INVALID = none
+    real* sec_energy;        // [MAX_SECONDARIES][slot]
+    real* sec_dir;           // [MAX_SECONDARIES][3][slot]
+
+    // rng: xorstate[5], weyl
+    u32* rng;                // [6][slot]
+
+    // track initialization
+    u32* vacancies;          // [slot]
+    u32* secondary_counts;   // [slot + 1]
+    u32* parents;            // [slot]
+    u32* indices;            // [slot]
+    u32* track_counters;     // [max_events]
+    u32 init_capacity;
+    // initializers, SoA
+    u32* ti_track_id;
+    u32* ti_parent_id;
+    u32* ti_event_id;
+    u32* ti_particle_id;
+    real* ti_time;
+    real* ti_energy;
+    real* ti_pos;            // [3][capacity]
+    real* ti_dir;            // [3][capacity]
+
+    // device-resident counters (mirrors CoreStateCounters) + scratch
+    u32* counters;           // see Counter enum
+    u32* block_scratch;      // [2 * num_blocks] per-block totals for the end-of-step scans
+
+    // scoring (null when no detectors are registered)
+    u32* pre_volume;                     // [slot] global volume id at the pre-step point
+    u32 const* calo_detector_of_volume;  // [volume] detector id or INVALID
+    real* calo_edep;                     // [detector] accumulated energy deposition [MeV]
+
+    // step counters accumulated on device: {track-steps, step iterations}
+    u64* step_counters;
+};
+
+enum Counter : u32
+{
+    CTR_NUM_GENERATED = 0,
+    CTR_NUM_INITIALIZERS,
+    CTR_NUM_VACANCIES,
+    CTR_NUM_ACTIVE,
+    CTR_NUM_SECONDARIES,
+    CTR_NUM_ALIVE,
+    CTR_NUM_NEW_TRACKS,
+    CTR_ERROR,
+    CTR_SIZE = 16
+};
+
+}  // namespace b200

@@ -1,0 +1,293 @@
+//---------------------------------------------------------------------------//
+// Load a problem image into HBM and build the device ParamsView.
+//---------------------------------------------------------------------------//
+#include "CoreParams.hh"
+
+#include <sstream>
+
+#include "../csrc/orange.cuh"
+
+using namespace b200;
+
+namespace celeritas_b200
+{
+namespace
+{
+std::vector<std::string> split_lines(std::string const& s)
+{
+    std::vector<std::string> out;
+    std::istringstream is(s);
+    std::string line;
+    while (std::getline(is, line))
+        out.push_back(line);
+    return out;
+}
+}  // namespace
+
+std::shared_ptr<CoreParams> CoreParams::from_image(std::string const& path)
+{
+    return from_image(Image::read(path));
+}
+
+std::shared_ptr<CoreParams> CoreParams::from_image(Image const& img)
+{
+    std::shared_ptr<CoreParams> p(new CoreParams);
+    p->load(img);
+    return p;
+}
+
+uint32_t CoreParams::find_particle(int pdg) const
+{
+    for (size_t i = 0; i < particle_pdg_.size(); ++i)
+        if (particle_pdg_[i] == pdg)
+            return i;
+    return 0xffffffffu;
+}
+
+void CoreParams::load(Image const& img)
+{
+    auto U32 = [&](char const* n) { return arena_.upload(img.get<uint32_t>(n)); };
+    auto F64 = [&](char const* n) { return arena_.upload(img.get<double>(n)); };
+    auto F32 = [&](char const* n) { return arena_.upload(img.get<float>(n)); };
+    auto U8 = [&](char const* n) { return arena_.upload(img.get<uint8_t>(n)); };
+
+    //// CORE ////
+    {
+        auto a = img.get<uint32_t>("core.actions");
+        view_.scalars.boundary_action = a.at(0);
+        view_.scalars.propagation_limit_action = a.at(1);
+        view_.scalars.tracking_cut_action = a.at(2);
+        view_.scalars.along_step_user_action = a.at(3);
+        view_.scalars.along_step_neutral_action = a.at(4);
+        auto labels = split_lines(img.get_string("core.action_labels"));
+        auto order = img.get<uint32_t>("core.action_order");
+        for (uint32_t i = 0; i < labels.size(); ++i)
+            actions_.push_back({i, labels[i], order.at(i)});
+        auto init = img.get<uint32_t>("init.scalars");
+        init_capacity_ = init.at(0);
+        max_events_ = init.at(1);
+        view_.scalars.track_order = init.at(2);
+        if (init.at(2) > ORDER_INIT_CHARGE)
+            throw std::runtime_error("unsupported track_order in image");
+    }
+
+    //// GEOMETRY ////
+    {
+        GeoParams& g = view_.geo;
+        auto sc = img.get<uint32_t>("geo.scalars");
+        g.max_depth = sc.at(0);
+        g.max_faces = sc.at(1);
+        g.max_intersections = sc.at(2);
+        if (g.max_faces > ORANGE_MAX_FACES || g.max_intersections > ORANGE_MAX_ISECT)
+        {
+            throw std::runtime_error(
+                "geometry exceeds compiled face/intersection limits: max_faces="
+                + std::to_string(g.max_faces)
+                + " max_intersections=" + std::to_string(g.max_intersections));
+        }
+        auto tol = img.get<double>("geo.tol");
+        g.tol_rel = tol.at(0);
+        g.tol_abs = tol.at(1);
+        auto utype = img.get<uint8_t>("geo.universe_type");
+        g.num_universes = utype.size();
+        for (auto t : utype)
+            if (t != UNIV_SIMPLE)
+                throw std::runtime_error("only simple-unit universes are supported");
+        g.universe_type = U8("geo.universe_type");
+        g.universe_index = U32("geo.universe_index");
+        g.universe_surface_offset = U32("geo.universe_surface_offset");
+        g.universe_volume_offset = U32("geo.universe_volume_offset");
+        static_assert(sizeof(SimpleUnit) == 16 * sizeof(uint32_t), "unit row layout");
+        g.simple_units
+            = reinterpret_cast<SimpleUnit const*>(U32("geo.simple_units"));
+        g.rect_arrays = U32("geo.rect_arrays");
+        g.local_surface_ids = U32("geo.local_surface_ids");
+        g.local_volume_ids = U32("geo.local_volume_ids");
+        g.real_ids = U32("geo.real_ids");
+        {
+            auto li = img.get<uint32_t>("geo.logic_ints");
+            std::vector<uint16_t> l16(li.begin(), li.end());
+            g.logic_ints = arena_.upload(l16);
+        }
+        g.reals = F64("geo.reals");
+        g.surface_types = U8("geo.surface_types");
+        for (auto t : img.get<uint8_t>("geo.surface_types"))
+            if (t >= SURF_INV)
+                throw std::runtime_error("involute surfaces are not supported");
+        g.vol_face_begin = U32("geo.vol_face_begin");
+        g.vol_face_end = U32("geo.vol_face_end");
+        g.vol_logic_begin = U32("geo.vol_logic_begin");
+        g.vol_logic_end = U32("geo.vol_logic_end");
+        g.vol_max_isect = U32("geo.vol_max_isect");
+        g.vol_flags = U32("geo.vol_flags");
+        g.vol_daughter = U32("geo.vol_daughter");
+        g.conn_begin = U32("geo.conn_begin");
+        g.conn_end = U32("geo.conn_end");
+        g.daughter_universe = U32("geo.daughter_universe");
+        g.daughter_transform = U32("geo.daughter_transform");
+        g.transform_type = U8("geo.transform_type");
+        g.transform_offset = U32("geo.transform_offset");
+        g.bih_bboxes = F32("geo.bih_bboxes");
+        g.bih_local_volume_ids = U32("geo.bih_local_volume_ids");
+        g.bih_inner_parent = U32("geo.bih_inner_parent");
+        g.bih_inner_axis = U32("geo.bih_inner_axis");
+        g.bih_inner_left_pos = F32("geo.bih_inner_left_pos");
+        g.bih_inner_left_child = U32("geo.bih_inner_left_child");
+        g.bih_inner_right_pos = F32("geo.bih_inner_right_pos");
+        g.bih_inner_right_child = U32("geo.bih_inner_right_child");
+        g.bih_leaf_parent = U32("geo.bih_leaf_parent");
+        g.bih_leaf_vol_begin = U32("geo.bih_leaf_vol_begin");
+        g.bih_leaf_vol_end = U32("geo.bih_leaf_vol_end");
+        g.volume_material = U32("geomat.volume_material");
+        volume_labels_ = split_lines(img.get_string("geo.volume_labels"));
+    }
+
+    //// MATERIALS ////
+    {
+        MatParams& m = view_.mat;
+        m.num_elements = img.get<uint32_t>("mat.element_z").size();
+        m.num_materials = img.get<uint32_t>("mat.material_state").size();
+        m.max_element_components = img.get_scalar<uint32_t>("mat.max_element_components");
+        m.element_z = U32("mat.element_z");
+        m.element_reals = F64("mat.element_reals");
+        m.elcomp_element = U32("mat.elcomp_element");
+        m.elcomp_fraction = F64("mat.elcomp_fraction");
+        m.material_elcomp_begin = U32("mat.material_elcomp_begin");
+        m.material_elcomp_end = U32("mat.material_elcomp_end");
+        m.material_reals = F64("mat.material_reals");
+    }
+
+    //// PARTICLES / CUTOFFS ////
+    {
+        ParticleParams& pp = view_.particle;
+        pp.num_particles = img.get<double>("particle.mass").size();
+        pp.mass = F64("particle.mass");
+        pp.charge = F64("particle.charge");
+        pp.decay_constant = F64("particle.decay_constant");
+        pp.matter = U8("particle.matter");
+        particle_names_ = split_lines(img.get_string("particle.names"));
+        for (auto v : img.get<uint32_t>("particle.pdg"))
+            particle_pdg_.push_back(static_cast<int>(v));
+
+        CutoffParams& c = view_.cutoff;
+        auto sc = img.get<uint32_t>("cutoff.scalars");
+        c.num_particles = sc.at(0);
+        c.num_materials = sc.at(1);
+        c.apply_post_interaction = sc.at(2);
+        c.id_gamma = sc.at(3);
+        c.id_electron = sc.at(4);
+        c.id_positron = sc.at(5);
+        c.energy = F64("cutoff.energy");
+        c.range = F64("cutoff.range");
+        c.id_to_index = U32("cutoff.id_to_index");
+    }
+
+    //// PHYSICS ////
+    {
+        PhysParams& p = view_.phys;
+        auto dims = img.get<uint32_t>("phys.dims");
+        p.num_particles = dims.at(0);
+        p.max_processes = dims.at(1);
+        p.num_materials = dims.at(2);
+        p.num_models = dims.at(3);
+        auto f = img.get<double>("phys.scalars_f64");
+        p.min_range = f.at(0);
+        p.max_step_over_range = f.at(1);
+        p.min_eprime_over_e = f.at(2);
+        p.lowest_electron_energy = f.at(3);
+        p.linear_loss_limit = f.at(4);
+        p.fixed_step_limiter = f.at(5);
+        p.lambda_limit = f.at(6);
+        p.range_factor = f.at(7);
+        p.safety_factor = f.at(8);
+        auto u = img.get<uint32_t>("phys.scalars_u32");
+        p.model_to_action = u.at(0);
+        p.step_limit_algorithm = u.at(2);
+        p.fixed_step_action = u.at(3);
+        p.grid_size = U32("phys.grid_size");
+        p.grid_log_front = F64("phys.grid_log_front");
+        p.grid_log_back = F64("phys.grid_log_back");
+        p.grid_log_delta = F64("phys.grid_log_delta");
+        p.grid_prime = U32("phys.grid_prime");
+        p.grid_value_offset = U32("phys.grid_value_offset");
+        p.reals = F64("phys.reals");
+        p.pp_num = U32("phys.pp_num");
+        p.pp_eloss_ppid = U32("phys.pp_eloss_ppid");
+        p.pp_has_at_rest = U32("phys.pp_has_at_rest");
+        p.pp_process = U32("phys.pp_process");
+        p.pp_grid = U32("phys.pp_grid");
+        p.pp_integral = U8("phys.pp_integral");
+        p.pp_energy_max_xs = F64("phys.pp_energy_max_xs");
+        p.pp_model_begin = U32("phys.pp_model_begin");
+        p.pp_model_count = U32("phys.pp_model_count");
+        p.pm_energy_begin = U32("phys.pm_energy_begin");
+        p.pm_energy = F64("phys.pm_energy");
+        p.pm_pmid = U32("phys.pm_pmid");
+        p.pmid_model = U32("phys.pmid_model");
+        p.elsel_begin = U32("phys.elsel_begin");
+        p.elsel_count = U32("phys.elsel_count");
+        p.elsel_grid = U32("phys.elsel_grid");
+        auto hw = img.get<uint32_t>("phys.hardwired");
+        p.hw_photoelectric = hw.at(0);
+        p.hw_livermore_pe = hw.at(1);
+        p.hw_positron_annihilation = hw.at(2);
+        p.hw_eplusgg = hw.at(3);
+        p.hw_photoelectric_table_thresh
+            = img.get_scalar<double>("phys.photoelectric_table_thresh");
+    }
+
+    //// MODELS ////
+    {
+        ModelParams& m = view_.model;
+        m.kn.action = INVALID;
+        if (img.has("model.kn.ids"))
+        {
+            auto ids = img.get<uint32_t>("model.kn.ids");
+            m.kn.electron = ids.at(0);
+            m.kn.gamma = ids.at(1);
+            m.kn.inv_electron_mass = img.get_scalar<double>("model.kn.inv_electron_mass");
+            m.kn.action = img.get_scalar<uint32_t>("model.kn.action");
+        }
+    }
+
+    //// RNG / SIM ////
+    {
+        auto r = img.get<uint32_t>("rng.params");
+        view_.rng.seed = r.at(0);
+        std::vector<uint32_t> jump(r.begin() + 1, r.begin() + 1 + 160);
+        std::vector<uint32_t> jump_sub(r.begin() + 161, r.begin() + 161 + 160);
+        view_.rng.jump = arena_.upload(jump);
+        view_.rng.jump_subsequence = arena_.upload(jump_sub);
+
+        auto ls = img.get<uint32_t>("sim.looping_steps");
+        view_.sim.has_looping = !ls.empty();
+        view_.sim.looping_steps = U32("sim.looping_steps");
+        view_.sim.looping_energy = F64("sim.looping_energy");
+    }
+
+    //// DETECTORS ////
+    {
+        detector_volumes_ = split_lines(img.get_string("calo.volumes"));
+        if (!detector_volumes_.empty())
+        {
+            std::vector<uint32_t> det(volume_labels_.size(), INVALID);
+            for (uint32_t d = 0; d < detector_volumes_.size(); ++d)
+            {
+                bool found = false;
+                for (uint32_t v = 0; v < volume_labels_.size(); ++v)
+                {
+                    if (volume_labels_[v] == detector_volumes_[d])
+                    {
+                        det[v] = d;
+                        found = true;
+                    }
+                }
+                if (!found)
+                    throw std::runtime_error("detector volume '" + detector_volumes_[d]
+                                             + "' not found in geometry");
+            }
+            d_detector_of_volume_ = arena_.upload(det);
+        }
+    }
+}
+}  // namespace celeritas_b200

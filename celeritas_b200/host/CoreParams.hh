@@ -1,0 +1,86 @@
+//---------------------------------------------------------------------------//
+// CoreParams: immutable problem data resident in HBM.
+//
+// Mirrors the role of the reference's CoreParams
+// (/root/reference/src/celeritas/global/CoreParams.hh:42-146): it owns the
+// device copies of geometry, materials, particles, cutoffs, physics tables,
+// model data, RNG and sim parameters, plus the action table (ids, labels,
+// step order) that the action sequence is built from.
+//---------------------------------------------------------------------------//
+#pragma once
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../csrc/views.cuh"
+#include "DeviceMemory.hh"
+#include "Image.hh"
+
+namespace celeritas_b200
+{
+//! Ordering of step actions (reference StepActionOrder, ActionInterface.hh:29-46)
+enum class StepActionOrder : uint32_t
+{
+    generate,
+    start,
+    user_start,
+    sort_start,
+    pre,
+    user_pre,
+    sort_pre,
+    along,
+    sort_along,
+    pre_post,
+    sort_pre_post,
+    post,
+    user_post,
+    end,
+    size_
+};
+
+struct ActionRecord
+{
+    uint32_t id;
+    std::string label;
+    uint32_t order;  // StepActionOrder or 0xffffffff for implicit actions
+};
+
+class CoreParams
+{
+  public:
+    static std::shared_ptr<CoreParams> from_image(std::string const& path);
+    static std::shared_ptr<CoreParams> from_image(b200::Image const& img);
+
+    b200::ParamsView const& view() const { return view_; }
+    std::vector<ActionRecord> const& actions() const { return actions_; }
+    std::vector<std::string> const& volume_labels() const { return volume_labels_; }
+    std::vector<std::string> const& particle_names() const { return particle_names_; }
+    std::vector<int> const& particle_pdg() const { return particle_pdg_; }
+    std::vector<std::string> const& detector_volumes() const { return detector_volumes_; }
+    //! Device table: global volume id -> detector id (empty if no detectors)
+    uint32_t const* detector_of_volume() const { return d_detector_of_volume_; }
+    uint32_t num_detectors() const { return detector_volumes_.size(); }
+
+    uint32_t init_capacity() const { return init_capacity_; }
+    uint32_t max_events() const { return max_events_; }
+    uint32_t rng_seed() const { return view_.rng.seed; }
+    uint32_t find_particle(int pdg) const;
+    size_t device_bytes() const { return arena_.bytes(); }
+
+  private:
+    CoreParams() = default;
+    void load(b200::Image const& img);
+
+    DeviceArena arena_;
+    b200::ParamsView view_{};
+    std::vector<ActionRecord> actions_;
+    std::vector<std::string> volume_labels_;
+    std::vector<std::string> particle_names_;
+    std::vector<int> particle_pdg_;
+    std::vector<std::string> detector_volumes_;
+    uint32_t const* d_detector_of_volume_{nullptr};
+    uint32_t init_capacity_{0};
+    uint32_t max_events_{0};
+};
+}  // namespace celeritas_b200

@@ -1,0 +1,274 @@
+//---------------------------------------------------------------------------//
+// Allocate and initialise per-stream state.
+//---------------------------------------------------------------------------//
+#include "CoreState.hh"
+
+#include <cstring>
+#include <numeric>
+#include <random>
+
+using namespace b200;
+
+namespace celeritas_b200
+{
+CoreState::CoreState(std::shared_ptr<CoreParams const> params,
+                     uint32_t stream_id,
+                     uint32_t num_track_slots)
+    : params_(std::move(params)), stream_id_(stream_id)
+{
+    if (num_track_slots == 0)
+        throw std::runtime_error("num_track_slots must be positive");
+    B2_CUDA_CALL(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    ParamsView const& p = params_->view();
+    StateView& s = view_;
+    uint32_t const n = num_track_slots;
+    uint32_t const D = p.geo.max_depth;
+    uint32_t const P = p.phys.max_processes;
+    s.num_slots = n;
+    s.max_depth = D;
+    s.max_processes = P;
+
+    s.status = arena_.alloc<u8>(n);
+    s.track_id = arena_.alloc_fill<u32>(n, 0xff);
+    s.parent_id = arena_.alloc_fill<u32>(n, 0xff);
+    s.event_id = arena_.alloc_fill<u32>(n, 0xff);
+    s.num_steps = arena_.alloc<u32>(n);
+    s.num_looping_steps = arena_.alloc<u32>(n);
+    s.time = arena_.alloc<real>(n);
+    s.step_length = arena_.alloc<real>(n);
+    s.post_step_action = arena_.alloc_fill<u32>(n, 0xff);
+    s.along_step_action = arena_.alloc_fill<u32>(n, 0xff);
+    s.particle_id = arena_.alloc_fill<u32>(n, 0xff);
+    s.energy = arena_.alloc<real>(n);
+    s.material_id = arena_.alloc_fill<u32>(n, 0xff);
+
+    s.geo_level = arena_.alloc<u32>(n);
+    s.geo_surface_level = arena_.alloc_fill<u32>(n, 0xff);
+    s.geo_surf = arena_.alloc_fill<u32>(n, 0xff);
+    s.geo_sense = arena_.alloc<u8>(n);
+    s.geo_boundary = arena_.alloc<u8>(n);
+    s.geo_next_level = arena_.alloc_fill<u32>(n, 0xff);
+    s.geo_next_step = arena_.alloc<real>(n);
+    s.geo_next_surf = arena_.alloc_fill<u32>(n, 0xff);
+    s.geo_next_sense = arena_.alloc<u8>(n);
+    s.geo_pos = arena_.alloc<real>(size_t(3) * D * n);
+    s.geo_dir = arena_.alloc<real>(size_t(3) * D * n);
+    s.geo_vol = arena_.alloc<u32>(size_t(D) * n);
+    s.geo_univ = arena_.alloc<u32>(size_t(D) * n);
+
+    s.interaction_mfp = arena_.alloc<real>(n);
+    s.macro_xs = arena_.alloc<real>(n);
+    s.energy_deposition = arena_.alloc<real>(n);
+    s.dedx_range = arena_.alloc<real>(n);
+    s.msc_range = arena_.alloc<real>(size_t(3) * n);
+    s.msc_is_displaced = arena_.alloc<u8>(n);
+    s.msc_true_path = arena_.alloc<real>(n);
+    s.msc_geom_path = arena_.alloc<real>(n);
+    s.msc_alpha = arena_.alloc<real>(n);
+    s.per_process_xs = arena_.alloc<real>(size_t(P ? P : 1) * n);
+    s.element = arena_.alloc_fill<u32>(n, 0xff);
+    s.sec_particle = arena_.alloc_fill<u32>(size_t(MAX_SECONDARIES) * n, 0xff);
+    s.sec_energy = arena_.alloc<real>(size_t(MAX_SECONDARIES) * n);
+    s.sec_dir = arena_.alloc<real>(size_t(MAX_SECONDARIES) * 3 * n);
+
+    // RNG: same host-side seeding as the reference's initialize_xorwow
+    // (/root/reference/src/celeritas/random/XorwowRngData.cc:28-58)
+    {
+        std::vector<std::seed_seq::result_type> host_seeds{params_->rng_seed()};
+        if (stream_id != 0)
+            host_seeds.push_back(stream_id);
+        std::seed_seq seed_seq(host_seeds.begin(), host_seeds.end());
+        std::mt19937 rng(seed_seq);
+        std::uniform_int_distribution<uint32_t> sample;
+        std::vector<uint32_t> soa(size_t(6) * n);
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            for (int k = 0; k < 5; ++k)
+                soa[size_t(k) * n + i] = sample(rng);
+            soa[size_t(5) * n + i] = sample(rng);
+        }
+        s.rng = const_cast<u32*>(arena_.upload(soa));
+    }
+
+    // Track initialization
+    {
+        std::vector<uint32_t> seq(n);
+        std::iota(seq.begin(), seq.end(), 0u);
+        s.vacancies = const_cast<u32*>(arena_.upload(seq));
+        s.secondary_counts = arena_.alloc<u32>(size_t(n) + 1);
+        s.parents = arena_.alloc_fill<u32>(n, 0xff);
+        s.indices = arena_.alloc<u32>(n);
+        s.track_counters = arena_.alloc<u32>(params_->max_events());
+        uint32_t cap = params_->init_capacity();
+        s.init_capacity = cap;
+        s.ti_track_id = arena_.alloc<u32>(cap);
+        s.ti_parent_id = arena_.alloc<u32>(cap);
+        s.ti_event_id = arena_.alloc<u32>(cap);
+        s.ti_particle_id = arena_.alloc<u32>(cap);
+        s.ti_time = arena_.alloc<real>(cap);
+        s.ti_energy = arena_.alloc<real>(cap);
+        s.ti_pos = arena_.alloc<real>(size_t(3) * cap);
+        s.ti_dir = arena_.alloc<real>(size_t(3) * cap);
+    }
+    {
+        std::vector<uint32_t> ctr(CTR_SIZE, 0);
+        ctr[CTR_NUM_VACANCIES] = n;
+        s.counters = const_cast<u32*>(arena_.upload(ctr));
+        uint32_t num_blocks = (n + 127) / 128;
+        s.block_scratch = arena_.alloc<u32>(size_t(2) * num_blocks);
+        s.step_counters = arena_.alloc<u64>(4);
+    }
+    // Scoring
+    if (params_->num_detectors() > 0)
+    {
+        s.pre_volume = arena_.alloc_fill<u32>(n, 0xff);
+        s.calo_detector_of_volume = params_->detector_of_volume();
+        s.calo_edep = arena_.alloc<real>(params_->num_detectors());
+    }
+    B2_CUDA_CALL(cudaMallocHost(reinterpret_cast<void**>(&h_counters_), CTR_SIZE * sizeof(uint32_t)));
+    B2_CUDA_CALL(cudaDeviceSynchronize());
+}
+
+CoreState::~CoreState()
+{
+    if (h_counters_)
+        cudaFreeHost(h_counters_);
+    if (stream_)
+        cudaStreamDestroy(stream_);
+}
+
+CoreStateCounters CoreState::sync_counters()
+{
+    B2_CUDA_CALL(cudaMemcpyAsync(h_counters_,
+                                 view_.counters,
+                                 CTR_SIZE * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost,
+                                 stream_));
+    B2_CUDA_CALL(cudaStreamSynchronize(stream_));
+    CoreStateCounters c;
+    c.num_generated = h_counters_[CTR_NUM_GENERATED];
+    c.num_initializers = h_counters_[CTR_NUM_INITIALIZERS];
+    c.num_vacancies = h_counters_[CTR_NUM_VACANCIES];
+    c.num_active = h_counters_[CTR_NUM_ACTIVE];
+    c.num_secondaries = h_counters_[CTR_NUM_SECONDARIES];
+    c.num_alive = h_counters_[CTR_NUM_ALIVE];
+    last_error_ = h_counters_[CTR_ERROR];
+    return c;
+}
+
+void CoreState::get_field(std::string const& f, void* out)
+{
+    StateView const& s = view_;
+    size_t const n = s.num_slots;
+    B2_CUDA_CALL(cudaStreamSynchronize(stream_));
+    auto copy = [&](void const* src, size_t bytes) {
+        B2_CUDA_CALL(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+    };
+    // Fetch status for masking inactive slots in geometry queries
+    std::vector<u8> status(n);
+    B2_CUDA_CALL(cudaMemcpy(status.data(), s.status, n, cudaMemcpyDeviceToHost));
+
+    if (f == "status") copy(s.status, n);
+    else if (f == "track_id") copy(s.track_id, 4 * n);
+    else if (f == "parent_id") copy(s.parent_id, 4 * n);
+    else if (f == "event_id") copy(s.event_id, 4 * n);
+    else if (f == "num_steps") copy(s.num_steps, 4 * n);
+    else if (f == "num_looping_steps") copy(s.num_looping_steps, 4 * n);
+    else if (f == "time") copy(s.time, 8 * n);
+    else if (f == "step_length") copy(s.step_length, 8 * n);
+    else if (f == "post_step_action") copy(s.post_step_action, 4 * n);
+    else if (f == "along_step_action") copy(s.along_step_action, 4 * n);
+    else if (f == "particle_id") copy(s.particle_id, 4 * n);
+    else if (f == "energy") copy(s.energy, 8 * n);
+    else if (f == "material_id") copy(s.material_id, 4 * n);
+    else if (f == "interaction_mfp") copy(s.interaction_mfp, 8 * n);
+    else if (f == "macro_xs") copy(s.macro_xs, 8 * n);
+    else if (f == "energy_deposition") copy(s.energy_deposition, 8 * n);
+    else if (f == "dedx_range") copy(s.dedx_range, 8 * n);
+    else if (f == "geo_level")
+    {
+        copy(s.geo_level, 4 * n);
+        auto* o = static_cast<uint32_t*>(out);
+        for (size_t i = 0; i < n; ++i)
+            if (status[i] == ST_INACTIVE)
+                o[i] = INVALID;
+    }
+    else if (f == "rng")
+    {
+        std::vector<uint32_t> soa(6 * n);
+        B2_CUDA_CALL(cudaMemcpy(soa.data(), s.rng, 24 * n, cudaMemcpyDeviceToHost));
+        auto* o = static_cast<uint32_t*>(out);
+        for (size_t i = 0; i < n; ++i)
+            for (int k = 0; k < 6; ++k)
+                o[6 * i + k] = soa[k * n + i];
+    }
+    else if (f == "pos" || f == "dir")
+    {
+        // level 0 only, as [slot][3]
+        size_t const stride = size_t(s.max_depth) * n;
+        std::vector<double> soa(3 * stride);
+        B2_CUDA_CALL(cudaMemcpy(soa.data(),
+                                f == "pos" ? s.geo_pos : s.geo_dir,
+                                soa.size() * 8,
+                                cudaMemcpyDeviceToHost));
+        auto* o = static_cast<double*>(out);
+        for (size_t i = 0; i < n; ++i)
+            for (int k = 0; k < 3; ++k)
+                o[3 * i + k] = status[i] == ST_INACTIVE ? 0 : soa[k * stride + i];
+    }
+    else if (f == "volume_id" || f == "surface_id")
+    {
+        GeoParams const& g = params_->view().geo;
+        std::vector<uint32_t> level(n), vol(size_t(s.max_depth) * n),
+            univ(size_t(s.max_depth) * n), slevel(n), surf(n);
+        B2_CUDA_CALL(cudaMemcpy(level.data(), s.geo_level, 4 * n, cudaMemcpyDeviceToHost));
+        B2_CUDA_CALL(cudaMemcpy(vol.data(), s.geo_vol, 4 * vol.size(), cudaMemcpyDeviceToHost));
+        B2_CUDA_CALL(cudaMemcpy(univ.data(), s.geo_univ, 4 * univ.size(), cudaMemcpyDeviceToHost));
+        B2_CUDA_CALL(cudaMemcpy(slevel.data(), s.geo_surface_level, 4 * n, cudaMemcpyDeviceToHost));
+        B2_CUDA_CALL(cudaMemcpy(surf.data(), s.geo_surf, 4 * n, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> voff(g.num_universes + 1), soff(g.num_universes + 1);
+        B2_CUDA_CALL(cudaMemcpy(voff.data(), g.universe_volume_offset, 4 * voff.size(), cudaMemcpyDeviceToHost));
+        B2_CUDA_CALL(cudaMemcpy(soff.data(), g.universe_surface_offset, 4 * soff.size(), cudaMemcpyDeviceToHost));
+        auto* o = static_cast<uint32_t*>(out);
+        for (size_t i = 0; i < n; ++i)
+        {
+            if (status[i] == ST_INACTIVE)
+            {
+                o[i] = INVALID;
+            }
+            else if (f == "volume_id")
+            {
+                size_t li = size_t(level[i]) * n + i;
+                o[i] = voff[univ[li]] + vol[li];
+            }
+            else
+            {
+                if (slevel[i] == INVALID)
+                    o[i] = INVALID;
+                else
+                    o[i] = soff[univ[size_t(slevel[i]) * n + i]] + surf[i];
+            }
+        }
+    }
+    else
+    {
+        throw std::runtime_error("unknown state field '" + f + "'");
+    }
+}
+
+void CoreState::calo_get(double* out)
+{
+    if (!view_.calo_edep)
+        throw std::runtime_error("no detectors registered");
+    B2_CUDA_CALL(cudaStreamSynchronize(stream_));
+    B2_CUDA_CALL(cudaMemcpy(
+        out, view_.calo_edep, params_->num_detectors() * sizeof(double), cudaMemcpyDeviceToHost));
+}
+
+void CoreState::calo_clear()
+{
+    if (view_.calo_edep)
+        B2_CUDA_CALL(cudaMemsetAsync(
+            view_.calo_edep, 0, params_->num_detectors() * sizeof(double), stream_));
+}
+}  // namespace celeritas_b200

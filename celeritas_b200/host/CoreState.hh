@@ -1,0 +1,65 @@
+//---------------------------------------------------------------------------//
+// CoreState: all mutable per-stream data, resident in HBM as SoA.
+//
+// Mirrors the reference's CoreState<MemSpace::device>
+// (/root/reference/src/celeritas/global/CoreState.hh:73-182): one per stream,
+// sized by num_track_slots; owns track state, the initializer queue, RNG
+// state and the (here device-resident) CoreStateCounters.
+//---------------------------------------------------------------------------//
+#pragma once
+
+#include <memory>
+
+#include "../csrc/views.cuh"
+#include "CoreParams.hh"
+#include "DeviceMemory.hh"
+
+namespace celeritas_b200
+{
+//! Host copy of the device counters (reference: track/CoreStateCounters.hh:24-47)
+struct CoreStateCounters
+{
+    uint32_t num_generated{0};
+    uint32_t num_initializers{0};
+    uint32_t num_vacancies{0};
+    uint32_t num_active{0};
+    uint32_t num_secondaries{0};
+    uint32_t num_alive{0};
+};
+
+class CoreState
+{
+  public:
+    CoreState(std::shared_ptr<CoreParams const> params, uint32_t stream_id, uint32_t num_track_slots);
+    ~CoreState();
+    CoreState(CoreState const&) = delete;
+    CoreState& operator=(CoreState const&) = delete;
+
+    b200::StateView const& view() const { return view_; }
+    uint32_t size() const { return view_.num_slots; }
+    uint32_t stream_id() const { return stream_id_; }
+    cudaStream_t stream() const { return stream_; }
+    CoreParams const& params() const { return *params_; }
+
+    //! Copy device counters to the host (synchronises the stream)
+    CoreStateCounters sync_counters();
+    //! Nonzero if a kernel flagged an error (B200_ERR_*)
+    uint32_t last_device_error() const { return last_error_; }
+
+    //! Copy a named per-slot field to host memory
+    void get_field(std::string const& name, void* out);
+    void calo_get(double* out);
+    void calo_clear();
+
+    size_t device_bytes() const { return arena_.bytes(); }
+
+  private:
+    std::shared_ptr<CoreParams const> params_;
+    uint32_t stream_id_;
+    cudaStream_t stream_{nullptr};
+    DeviceArena arena_;
+    b200::StateView view_{};
+    uint32_t* h_counters_{nullptr};  // pinned
+    uint32_t last_error_{0};
+};
+}  // namespace celeritas_b200

@@ -1,0 +1,309 @@
+//---------------------------------------------------------------------------//
+// Action sequence construction and the stepping loop.
+//---------------------------------------------------------------------------//
+#include "Stepper.hh"
+
+#include <algorithm>
+#include <map>
+#include <set>
+
+using namespace b200;
+
+namespace celeritas_b200
+{
+namespace
+{
+void check_rc(int rc, char const* what)
+{
+    if (rc != 0)
+        throw std::runtime_error(std::string(what) + " failed with code " + std::to_string(rc));
+}
+
+B200ParamsView const* pv(CoreParams const& p)
+{
+    return reinterpret_cast<B200ParamsView const*>(&p.view());
+}
+B200StateView const* sv(CoreState const& s)
+{
+    return reinterpret_cast<B200StateView const*>(&s.view());
+}
+}  // namespace
+
+//---------------------------------------------------------------------------//
+void KernelAction::step(CoreParams const& params, CoreState& state) const
+{
+    check_rc(launch_(pv(params), sv(state), state.stream()), label_.c_str());
+}
+
+//---------------------------------------------------------------------------//
+// Primaries action: stages host primaries and launches the generate kernels
+class ExtendFromPrimariesAction final : public StepActionInterface
+{
+  public:
+    ExtendFromPrimariesAction(uint32_t id, std::string label) : id_(id), label_(std::move(label)) {}
+    uint32_t action_id() const override { return id_; }
+    std::string const& label() const override { return label_; }
+    StepActionOrder order() const override { return StepActionOrder::generate; }
+    void step(CoreParams const&, CoreState&) const override {}
+
+  private:
+    uint32_t id_;
+    std::string label_;
+};
+
+struct Stepper::Staging
+{
+    uint32_t capacity{0};
+    uint32_t count{0};
+    uint32_t num_events{0};
+    B200Primary* h_primaries{nullptr};  // pinned
+    uint32_t* h_aux{nullptr};           // pinned: rank[cap], event_ids[cap], event_counts[cap]
+    B200Primary* d_primaries{nullptr};
+    uint32_t* d_aux{nullptr};
+
+    void reserve(uint32_t n)
+    {
+        if (n <= capacity)
+            return;
+        release();
+        capacity = std::max<uint32_t>(n, 1024);
+        B2_CUDA_CALL(cudaMallocHost(reinterpret_cast<void**>(&h_primaries),
+                                    capacity * sizeof(B200Primary)));
+        B2_CUDA_CALL(cudaMallocHost(reinterpret_cast<void**>(&h_aux), 3 * capacity * sizeof(uint32_t)));
+        B2_CUDA_CALL(cudaMalloc(reinterpret_cast<void**>(&d_primaries), capacity * sizeof(B200Primary)));
+        B2_CUDA_CALL(cudaMalloc(reinterpret_cast<void**>(&d_aux), 3 * capacity * sizeof(uint32_t)));
+    }
+    void release()
+    {
+        if (h_primaries) cudaFreeHost(h_primaries);
+        if (h_aux) cudaFreeHost(h_aux);
+        if (d_primaries) cudaFree(d_primaries);
+        if (d_aux) cudaFree(d_aux);
+        h_primaries = nullptr;
+        h_aux = nullptr;
+        d_primaries = nullptr;
+        d_aux = nullptr;
+        capacity = 0;
+    }
+    ~Staging() { release(); }
+};
+
+//---------------------------------------------------------------------------//
+ActionSequence::ActionSequence(CoreParams const& params)
+{
+    using Order = StepActionOrder;
+    auto const& view = params.view();
+    uint32_t const model_begin = view.phys.model_to_action;
+    uint32_t const model_end = model_begin + view.phys.num_models;
+    bool have_interact = false;
+    bool have_tally = false;
+
+    for (ActionRecord const& a : params.actions())
+    {
+        if (a.order == INVALID)
+            continue;  // implicit action: no kernel
+        Order order = static_cast<Order>(a.order);
+        SPAction act;
+        if (a.label == "extend-from-primaries")
+        {
+            act = std::make_shared<ExtendFromPrimariesAction>(a.id, a.label);
+        }
+        else if (a.label == "initialize-tracks")
+        {
+            act = std::make_shared<KernelAction>(a.id, a.label, order, &b200_step_initialize_tracks);
+        }
+        else if (a.label == "pre-step")
+        {
+            act = std::make_shared<KernelAction>(a.id, a.label, order, &b200_step_pre_step);
+        }
+        else if (a.label.rfind("along-step-", 0) == 0)
+        {
+            // Neutral and charged along-step are one launch: register once,
+            // under the user (charged) action when present, else the neutral
+            if (a.id == view.scalars.along_step_user_action)
+            {
+                act = std::make_shared<KernelAction>(a.id, a.label, order, &b200_step_along_step);
+            }
+        }
+        else if (a.label == "physics-discrete-select")
+        {
+            act = std::make_shared<KernelAction>(a.id, a.label, order, &b200_step_discrete_select);
+        }
+        else if (a.id >= model_begin && a.id < model_end)
+        {
+            // All discrete models share one launch that dispatches on action id
+            if (!have_interact)
+            {
+                act = std::make_shared<KernelAction>(
+                    a.id, "interact[" + a.label + ",...]", order, &b200_step_interact);
+                have_interact = true;
+            }
+        }
+        else if (a.label == "geo-boundary")
+        {
+            act = std::make_shared<KernelAction>(a.id, a.label, order, &b200_step_boundary);
+        }
+        else if (a.label == "tracking-cut")
+        {
+            act = std::make_shared<KernelAction>(a.id, a.label, order, &b200_step_tracking_cut);
+        }
+        else if (a.label == "extend-from-secondaries")
+        {
+            act = std::make_shared<KernelAction>(
+                a.id, a.label, order, &b200_step_extend_from_secondaries);
+        }
+        else if (a.label.rfind("step-gather-", 0) == 0)
+        {
+            // pre-step gather is folded into pre-step; post-step gather + calo
+            // are one tally launch at user_post
+            if (order == Order::user_post && !have_tally)
+            {
+                act = std::make_shared<KernelAction>(a.id, "tally[" + a.label + "]", order, &b200_step_tally);
+                have_tally = true;
+            }
+        }
+        else
+        {
+            throw std::runtime_error("no B200 kernel for step action '" + a.label + "'");
+        }
+        if (act)
+            actions_.push_back(std::move(act));
+    }
+    std::stable_sort(actions_.begin(), actions_.end(), [](SPAction const& a, SPAction const& b) {
+        if (a->order() != b->order())
+            return a->order() < b->order();
+        return a->action_id() < b->action_id();
+    });
+}
+
+void ActionSequence::step(CoreParams const& params, CoreState& state) const
+{
+    for (auto const& a : actions_)
+        a->step(params, state);
+}
+
+//---------------------------------------------------------------------------//
+Stepper::Stepper(StepperInput input) : params_(std::move(input.params))
+{
+    if (!params_)
+        throw std::runtime_error("Stepper requires params");
+    actions_ = std::make_shared<ActionSequence>(*params_);
+    state_ = std::make_unique<CoreState>(params_, input.stream_id, input.num_track_slots);
+    staging_ = std::make_unique<Staging>();
+}
+
+Stepper::~Stepper() = default;
+
+void Stepper::insert(B200Primary const* primaries, uint32_t n)
+{
+    if (staging_->count != 0)
+        throw std::runtime_error("multiple consecutive primary insertions");
+    if (n == 0)
+        return;
+    staging_->reserve(n);
+    Staging& st = *staging_;
+    std::copy(primaries, primaries + n, st.h_primaries);
+    // Deterministic track ids: rank of each primary among earlier primaries of
+    // the same event, plus per-event totals to advance the device counters
+    uint32_t* rank = st.h_aux;
+    uint32_t* ev_ids = st.h_aux + st.capacity;
+    uint32_t* ev_counts = st.h_aux + 2 * st.capacity;
+    std::map<uint32_t, uint32_t> counts;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        if (primaries[i].event_id >= params_->max_events())
+            throw std::runtime_error("primary event id exceeds max_events");
+        rank[i] = counts[primaries[i].event_id]++;
+    }
+    uint32_t ne = 0;
+    for (auto const& kv : counts)
+    {
+        ev_ids[ne] = kv.first;
+        ev_counts[ne] = kv.second;
+        ++ne;
+    }
+    st.count = n;
+    st.num_events = ne;
+}
+
+void Stepper::step_async()
+{
+    CoreState& state = *state_;
+    cudaStream_t stream = state.stream();
+    check_rc(b200_reset_generated(sv(state), stream), "reset_generated");
+    Staging& st = *staging_;
+    if (st.count > 0)
+    {
+        B2_CUDA_CALL(cudaMemcpyAsync(st.d_primaries,
+                                     st.h_primaries,
+                                     st.count * sizeof(B200Primary),
+                                     cudaMemcpyHostToDevice,
+                                     stream));
+        B2_CUDA_CALL(cudaMemcpyAsync(st.d_aux,
+                                     st.h_aux,
+                                     3 * st.capacity * sizeof(uint32_t),
+                                     cudaMemcpyHostToDevice,
+                                     stream));
+        check_rc(b200_step_extend_from_primaries(sv(state),
+                                                 st.d_primaries,
+                                                 st.d_aux,
+                                                 st.d_aux + st.capacity,
+                                                 st.d_aux + 2 * st.capacity,
+                                                 st.num_events,
+                                                 st.count,
+                                                 stream),
+                 "extend_from_primaries");
+        st.count = 0;
+    }
+    actions_->step(*params_, state);
+}
+
+StepperResult Stepper::operator()()
+{
+    this->step_async();
+    CoreStateCounters c = state_->sync_counters();
+    if (uint32_t err = state_->last_device_error())
+    {
+        if (err == B200_ERR_INITIALIZER_CAPACITY)
+            throw std::runtime_error(
+                "insufficient capacity (" + std::to_string(params_->init_capacity())
+                + ") for track initializers");
+        throw std::runtime_error("device error " + std::to_string(err));
+    }
+    StepperResult r;
+    r.generated = c.num_generated;
+    r.active = c.num_active;
+    r.alive = c.num_alive;
+    r.queued = c.num_initializers;
+    return r;
+}
+
+StepperResult Stepper::operator()(B200Primary const* primaries, uint32_t n)
+{
+    this->insert(primaries, n);
+    return (*this)();
+}
+
+void Stepper::warm_up()
+{
+    CoreStateCounters c = state_->sync_counters();
+    if (c.num_active != 0 && c.num_alive != 0)
+        throw std::runtime_error("cannot warm up when state has active tracks");
+    (*this)();
+}
+
+void Stepper::kill_active()
+{
+    check_rc(b200_kill_active(pv(*params_), sv(*state_), state_->stream()), "kill_active");
+}
+
+void Stepper::reseed(uint64_t event_id)
+{
+    check_rc(b200_reseed(pv(*params_), sv(*state_), event_id, state_->stream()), "reseed");
+    // reference: Stepper::reseed also zeroes the track-id counters (Stepper.cc:193-201)
+    B2_CUDA_CALL(cudaMemsetAsync(state_->view().track_counters,
+                                 0,
+                                 params_->max_events() * sizeof(uint32_t),
+                                 state_->stream()));
+}
+}  // namespace celeritas_b200

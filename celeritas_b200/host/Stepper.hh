@@ -1,0 +1,119 @@
+//---------------------------------------------------------------------------//
+// Step actions, the ordered action sequence and the Stepper.
+//
+// Same shape as the reference's plugin surface:
+//   StepActionInterface::step(CoreParams const&, CoreState&)
+//     (/root/reference/src/corecel/sys/ActionInterface.hh:175-186)
+//   ActionSequence::step, actions sorted by (order, action id)
+//     (/root/reference/src/celeritas/global/ActionSequence.cc:37-138,
+//      /root/reference/src/corecel/sys/ActionGroups.t.hh:23-54)
+//   Stepper::operator()(primaries) / operator()() / warm_up / reseed / kill_active
+//     (/root/reference/src/celeritas/global/Stepper.cc:66-201)
+// Each concrete action is a thin adapter over one C-ABI launcher
+// (include/celeritas_b200.h); there is no host implementation of any action.
+//---------------------------------------------------------------------------//
+#pragma once
+
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/celeritas_b200.h"
+#include "CoreParams.hh"
+#include "CoreState.hh"
+
+namespace celeritas_b200
+{
+class StepActionInterface
+{
+  public:
+    virtual ~StepActionInterface() = default;
+    virtual uint32_t action_id() const = 0;
+    virtual std::string const& label() const = 0;
+    virtual StepActionOrder order() const = 0;
+    //! Launch on the state's stream (asynchronous)
+    virtual void step(CoreParams const&, CoreState&) const = 0;
+};
+
+//! Adapter over a `int f(params view, state view, stream)` launcher
+class KernelAction final : public StepActionInterface
+{
+  public:
+    using Launcher = int (*)(B200ParamsView const*, B200StateView const*, cudaStream_t);
+    KernelAction(uint32_t id, std::string label, StepActionOrder order, Launcher f)
+        : id_(id), label_(std::move(label)), order_(order), launch_(f)
+    {
+    }
+    uint32_t action_id() const override { return id_; }
+    std::string const& label() const override { return label_; }
+    StepActionOrder order() const override { return order_; }
+    void step(CoreParams const& params, CoreState& state) const override;
+
+  private:
+    uint32_t id_;
+    std::string label_;
+    StepActionOrder order_;
+    Launcher launch_;
+};
+
+class ActionSequence
+{
+  public:
+    using SPAction = std::shared_ptr<StepActionInterface const>;
+    //! Build the B200 adapters for every step action in the problem's table
+    explicit ActionSequence(CoreParams const& params);
+    void step(CoreParams const& params, CoreState& state) const;
+    std::vector<SPAction> const& actions() const { return actions_; }
+
+  private:
+    std::vector<SPAction> actions_;
+};
+
+struct StepperResult
+{
+    uint32_t generated{};
+    uint32_t queued{};
+    uint32_t active{};
+    uint32_t alive{};
+    explicit operator bool() const { return queued > 0 || alive > 0; }
+};
+
+struct StepperInput
+{
+    std::shared_ptr<CoreParams const> params;
+    uint32_t stream_id{0};
+    uint32_t num_track_slots{0};
+};
+
+class Stepper
+{
+  public:
+    explicit Stepper(StepperInput input);
+    ~Stepper();
+
+    void warm_up();
+    StepperResult operator()();
+    StepperResult operator()(B200Primary const* primaries, uint32_t n);
+    void kill_active();
+    void reseed(uint64_t event_id);
+
+    ActionSequence const& actions() const { return *actions_; }
+    CoreState& state() { return *state_; }
+    CoreParams const& params() const { return *params_; }
+
+    //! Enqueue one iteration without reading anything back
+    void step_async();
+    //! Stage primaries for the next iteration (host buffers)
+    void insert(B200Primary const* primaries, uint32_t n);
+
+  private:
+    std::shared_ptr<CoreParams const> params_;
+    std::shared_ptr<ActionSequence> actions_;
+    std::unique_ptr<CoreState> state_;
+
+    // staging for primaries (pinned host + device)
+    struct Staging;
+    std::unique_ptr<Staging> staging_;
+};
+}  // namespace celeritas_b200

@@ -1,0 +1,320 @@
+//---------------------------------------------------------------------------//
+// C-ABI (include/celeritas_b200.h) over the host-side objects.
+//---------------------------------------------------------------------------//
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "../../include/celeritas_b200.h"
+#include "CoreParams.hh"
+#include "CoreState.hh"
+#include "Stepper.hh"
+
+using namespace celeritas_b200;
+
+struct B200Params
+{
+    std::shared_ptr<CoreParams> params;
+};
+struct B200State
+{
+    std::unique_ptr<CoreState> owned;
+    CoreState* state;
+};
+struct B200Stepper
+{
+    std::unique_ptr<Stepper> stepper;
+    B200State state_handle;
+    uint64_t launches_at_create;
+};
+
+namespace
+{
+thread_local std::string g_error;
+
+template<class F>
+int guarded(F&& f)
+{
+    try
+    {
+        f();
+        return B200_OK;
+    }
+    catch (CudaError const& e)
+    {
+        g_error = e.what();
+        return e.code;
+    }
+    catch (std::exception const& e)
+    {
+        g_error = e.what();
+        return B200_ERR_RUNTIME;
+    }
+}
+}  // namespace
+
+extern "C" {
+char const* b200_last_error(void)
+{
+    return g_error.c_str();
+}
+
+int b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+        return 0;
+    return n;
+}
+
+//---------------------------------------------------------------------------//
+int b200_params_create_from_image(char const* image_path, B200Params** out)
+{
+    if (!image_path || !out)
+        return B200_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (b200_device_count() == 0)
+    {
+        g_error = "no CUDA device available (this library has no CPU path)";
+        return B200_ERR_NO_DEVICE;
+    }
+    return guarded([&] {
+        auto p = std::make_unique<B200Params>();
+        p->params = CoreParams::from_image(image_path);
+        *out = p.release();
+    });
+}
+
+void b200_params_destroy(B200Params* params)
+{
+    delete params;
+}
+
+B200ParamsView const* b200_params_view(B200Params const* params)
+{
+    return reinterpret_cast<B200ParamsView const*>(&params->params->view());
+}
+
+uint32_t b200_params_num_actions(B200Params const* params)
+{
+    return params->params->actions().size();
+}
+
+char const* b200_params_action_label(B200Params const* params, uint32_t action_id)
+{
+    auto const& a = params->params->actions();
+    return action_id < a.size() ? a[action_id].label.c_str() : "";
+}
+
+uint32_t b200_params_num_volumes(B200Params const* params)
+{
+    return params->params->volume_labels().size();
+}
+
+char const* b200_params_volume_label(B200Params const* params, uint32_t volume_id)
+{
+    auto const& v = params->params->volume_labels();
+    return volume_id < v.size() ? v[volume_id].c_str() : "";
+}
+
+uint32_t b200_params_num_detectors(B200Params const* params)
+{
+    return params->params->num_detectors();
+}
+
+uint32_t b200_params_find_particle(B200Params const* params, int pdg)
+{
+    return params->params->find_particle(pdg);
+}
+
+//---------------------------------------------------------------------------//
+int b200_state_create(B200Params const* params,
+                      uint32_t stream_id,
+                      uint32_t num_track_slots,
+                      B200State** out)
+{
+    if (!params || !out)
+        return B200_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    return guarded([&] {
+        auto s = std::make_unique<B200State>();
+        s->owned = std::make_unique<CoreState>(params->params, stream_id, num_track_slots);
+        s->state = s->owned.get();
+        *out = s.release();
+    });
+}
+
+void b200_state_destroy(B200State* state)
+{
+    delete state;
+}
+
+B200StateView const* b200_state_view(B200State const* state)
+{
+    return reinterpret_cast<B200StateView const*>(&state->state->view());
+}
+
+int b200_state_get(B200State* state, char const* field, void* out)
+{
+    return guarded([&] { state->state->get_field(field, out); });
+}
+
+int b200_state_calo_get(B200State* state, double* out)
+{
+    return guarded([&] { state->state->calo_get(out); });
+}
+
+int b200_state_calo_clear(B200State* state)
+{
+    return guarded([&] { state->state->calo_clear(); });
+}
+
+//---------------------------------------------------------------------------//
+int b200_stepper_create(B200Params const* params,
+                        uint32_t stream_id,
+                        uint32_t num_track_slots,
+                        B200Stepper** out)
+{
+    if (!params || !out)
+        return B200_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    return guarded([&] {
+        auto s = std::make_unique<B200Stepper>();
+        StepperInput inp;
+        inp.params = params->params;
+        inp.stream_id = stream_id;
+        inp.num_track_slots = num_track_slots;
+        s->stepper = std::make_unique<Stepper>(std::move(inp));
+        s->state_handle.state = &s->stepper->state();
+        s->launches_at_create = b200_launch_count();
+        *out = s.release();
+    });
+}
+
+void b200_stepper_destroy(B200Stepper* stepper)
+{
+    delete stepper;
+}
+
+B200State* b200_stepper_state(B200Stepper* stepper)
+{
+    return &stepper->state_handle;
+}
+
+int b200_stepper_step(B200Stepper* stepper,
+                      B200Primary const* primaries,
+                      uint32_t num_primaries,
+                      B200StepperResult* result)
+{
+    return guarded([&] {
+        StepperResult r = num_primaries ? (*stepper->stepper)(primaries, num_primaries)
+                                        : (*stepper->stepper)();
+        if (result)
+        {
+            result->generated = r.generated;
+            result->queued = r.queued;
+            result->active = r.active;
+            result->alive = r.alive;
+        }
+    });
+}
+
+int b200_stepper_warm_up(B200Stepper* stepper)
+{
+    return guarded([&] { stepper->stepper->warm_up(); });
+}
+
+int b200_stepper_reseed(B200Stepper* stepper, uint64_t event_id)
+{
+    return guarded([&] { stepper->stepper->reseed(event_id); });
+}
+
+int b200_stepper_kill_active(B200Stepper* stepper)
+{
+    return guarded([&] { stepper->stepper->kill_active(); });
+}
+
+uint32_t b200_stepper_num_step_actions(B200Stepper const* stepper)
+{
+    return stepper->stepper->actions().actions().size();
+}
+
+char const* b200_stepper_step_action_label(B200Stepper const* stepper, uint32_t i)
+{
+    auto const& a = stepper->stepper->actions().actions();
+    return i < a.size() ? a[i]->label().c_str() : "";
+}
+
+uint64_t b200_stepper_launch_count(B200Stepper const* stepper)
+{
+    return b200_launch_count() - stepper->launches_at_create;
+}
+
+//---------------------------------------------------------------------------//
+// Transport whole events (reference: app/celer-sim/Transporter.cc:84-179)
+int b200_run_events(B200Stepper* handle,
+                    B200Primary const* primaries,
+                    uint32_t const* offsets,
+                    uint32_t num_events,
+                    int merge_events,
+                    uint64_t max_steps,
+                    B200RunResult* result)
+{
+    return guarded([&] {
+        Stepper& step = *handle->stepper;
+        cudaStream_t stream = step.state().stream();
+        cudaEvent_t ev0, ev1;
+        B2_CUDA_CALL(cudaEventCreate(&ev0));
+        B2_CUDA_CALL(cudaEventCreate(&ev1));
+        B200RunResult r{};
+        B2_CUDA_CALL(cudaEventRecord(ev0, stream));
+        auto transport = [&](B200Primary const* p, uint32_t n) {
+            r.num_primaries += n;
+            StepperResult counts = step(p, n);
+            uint64_t local_steps = 0;
+            while (true)
+            {
+                r.num_steps += counts.active;
+                local_steps += counts.active;
+                ++r.num_step_iterations;
+                r.max_queued = std::max<uint64_t>(r.max_queued, counts.queued);
+                if (!counts)
+                    break;
+                if (max_steps && local_steps >= max_steps)
+                {
+                    step.kill_active();
+                    step();
+                    break;
+                }
+                counts = step();
+            }
+        };
+        if (merge_events)
+        {
+            step.reseed(primaries[0].event_id);
+            transport(primaries, offsets[num_events]);
+        }
+        else
+        {
+            for (uint32_t e = 0; e < num_events; ++e)
+            {
+                uint32_t n = offsets[e + 1] - offsets[e];
+                if (n == 0)
+                    continue;
+                step.reseed(primaries[offsets[e]].event_id);
+                transport(primaries + offsets[e], n);
+            }
+        }
+        B2_CUDA_CALL(cudaEventRecord(ev1, stream));
+        B2_CUDA_CALL(cudaEventSynchronize(ev1));
+        float ms = 0;
+        B2_CUDA_CALL(cudaEventElapsedTime(&ms, ev0, ev1));
+        r.seconds = ms * 1e-3;
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+        if (result)
+            *result = r;
+    });
+}
+}  // extern "C"

@@ -1,0 +1,265 @@
+"""ctypes binding of include/celeritas_b200.h."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class Primary(C.Structure):
+    _fields_ = [('particle_id', C.c_uint32), ('event_id', C.c_uint32),
+                ('energy', C.c_double), ('pos', C.c_double * 3),
+                ('dir', C.c_double * 3), ('time', C.c_double)]
+
+
+PRIMARY_DTYPE = np.dtype([('particle_id', '<u4'), ('event_id', '<u4'), ('energy', '<f8'),
+                          ('pos', '<f8', 3), ('dir', '<f8', 3), ('time', '<f8')])
+assert PRIMARY_DTYPE.itemsize == C.sizeof(Primary)
+
+
+class StepperResult(C.Structure):
+    _fields_ = [('generated', C.c_uint32), ('queued', C.c_uint32), ('active', C.c_uint32),
+                ('alive', C.c_uint32)]
+
+
+class RunResult(C.Structure):
+    _fields_ = [('num_steps', C.c_uint64), ('num_step_iterations', C.c_uint64),
+                ('num_primaries', C.c_uint64), ('max_queued', C.c_uint64),
+                ('seconds', C.c_double)]
+
+
+# Every symbol declared in include/celeritas_b200.h
+EXPORTS = [
+    'b200_last_error', 'b200_device_count', 'b200_params_create_from_image',
+    'b200_params_destroy', 'b200_params_view', 'b200_params_num_actions',
+    'b200_params_action_label', 'b200_params_num_volumes', 'b200_params_volume_label',
+    'b200_params_num_detectors', 'b200_params_find_particle', 'b200_state_create',
+    'b200_state_destroy', 'b200_state_view', 'b200_state_get', 'b200_state_calo_get',
+    'b200_state_calo_clear', 'b200_step_extend_from_primaries', 'b200_step_initialize_tracks',
+    'b200_step_pre_step', 'b200_step_along_step', 'b200_step_discrete_select',
+    'b200_step_interact', 'b200_step_boundary', 'b200_step_tracking_cut', 'b200_step_tally',
+    'b200_step_extend_from_secondaries', 'b200_reseed', 'b200_reset_generated',
+    'b200_kill_active', 'b200_launch_count', 'b200_stepper_create', 'b200_stepper_destroy',
+    'b200_stepper_state', 'b200_stepper_step', 'b200_stepper_warm_up', 'b200_stepper_reseed',
+    'b200_stepper_kill_active', 'b200_stepper_num_step_actions',
+    'b200_stepper_step_action_label', 'b200_stepper_launch_count', 'b200_run_events',
+]
+
+_lib = None
+
+
+def library_path():
+    return os.path.join(HERE, 'libceleritas_b200.so')
+
+
+def load_library():
+    """Load the CUDA extension; raise (never fall back) if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise B200Error('%s is missing: run `make -C celeritas_b200` (or '
+                        '__graft_entry__.build()); there is no fallback path' % path)
+    L = C.CDLL(path)
+    vp = C.c_void_p
+    L.b200_last_error.restype = C.c_char_p
+    L.b200_device_count.restype = C.c_int
+    L.b200_params_create_from_image.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.b200_params_destroy.argtypes = [vp]
+    L.b200_params_view.restype = vp
+    L.b200_params_view.argtypes = [vp]
+    L.b200_params_num_actions.argtypes = [vp]
+    L.b200_params_num_actions.restype = C.c_uint32
+    L.b200_params_action_label.argtypes = [vp, C.c_uint32]
+    L.b200_params_action_label.restype = C.c_char_p
+    L.b200_params_num_volumes.argtypes = [vp]
+    L.b200_params_num_volumes.restype = C.c_uint32
+    L.b200_params_volume_label.argtypes = [vp, C.c_uint32]
+    L.b200_params_volume_label.restype = C.c_char_p
+    L.b200_params_num_detectors.argtypes = [vp]
+    L.b200_params_num_detectors.restype = C.c_uint32
+    L.b200_params_find_particle.argtypes = [vp, C.c_int]
+    L.b200_params_find_particle.restype = C.c_uint32
+    L.b200_state_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+    L.b200_state_destroy.argtypes = [vp]
+    L.b200_state_view.argtypes = [vp]
+    L.b200_state_view.restype = vp
+    L.b200_state_get.argtypes = [vp, C.c_char_p, vp]
+    L.b200_state_calo_get.argtypes = [vp, vp]
+    L.b200_state_calo_clear.argtypes = [vp]
+    L.b200_launch_count.restype = C.c_uint64
+    L.b200_stepper_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+    L.b200_stepper_destroy.argtypes = [vp]
+    L.b200_stepper_state.argtypes = [vp]
+    L.b200_stepper_state.restype = vp
+    L.b200_stepper_step.argtypes = [vp, vp, C.c_uint32, C.POINTER(StepperResult)]
+    L.b200_stepper_warm_up.argtypes = [vp]
+    L.b200_stepper_reseed.argtypes = [vp, C.c_uint64]
+    L.b200_stepper_kill_active.argtypes = [vp]
+    L.b200_stepper_num_step_actions.argtypes = [vp]
+    L.b200_stepper_num_step_actions.restype = C.c_uint32
+    L.b200_stepper_step_action_label.argtypes = [vp, C.c_uint32]
+    L.b200_stepper_step_action_label.restype = C.c_char_p
+    L.b200_stepper_launch_count.argtypes = [vp]
+    L.b200_stepper_launch_count.restype = C.c_uint64
+    L.b200_run_events.argtypes = [vp, vp, vp, C.c_uint32, C.c_int, C.c_uint64,
+                                  C.POINTER(RunResult)]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise B200Error('celeritas_b200 error %d: %s'
+                        % (rc, load_library().b200_last_error().decode()))
+
+
+def device_count():
+    return load_library().b200_device_count()
+
+
+def launch_count():
+    return int(load_library().b200_launch_count())
+
+
+FIELDS = {
+    'status': ('u1', 1), 'track_id': ('<u4', 1), 'parent_id': ('<u4', 1), 'event_id': ('<u4', 1),
+    'num_steps': ('<u4', 1), 'num_looping_steps': ('<u4', 1), 'time': ('<f8', 1),
+    'step_length': ('<f8', 1), 'post_step_action': ('<u4', 1), 'along_step_action': ('<u4', 1),
+    'particle_id': ('<u4', 1), 'energy': ('<f8', 1), 'material_id': ('<u4', 1),
+    'interaction_mfp': ('<f8', 1), 'macro_xs': ('<f8', 1), 'energy_deposition': ('<f8', 1),
+    'dedx_range': ('<f8', 1), 'rng': ('<u4', 6), 'pos': ('<f8', 3), 'dir': ('<f8', 3),
+    'volume_id': ('<u4', 1), 'surface_id': ('<u4', 1), 'geo_level': ('<u4', 1),
+}
+
+
+class Params:
+    """Problem parameters in HBM (reference: CoreParams)."""
+
+    def __init__(self, image_path):
+        L = load_library()
+        h = C.c_void_p()
+        _check(L.b200_params_create_from_image(os.fspath(image_path).encode(), C.byref(h)))
+        self.h = h
+        self.image_path = image_path
+
+    def __del__(self):
+        try:
+            if getattr(self, 'h', None):
+                load_library().b200_params_destroy(self.h)
+        except Exception:
+            pass
+
+    @property
+    def action_labels(self):
+        L = load_library()
+        return [L.b200_params_action_label(self.h, i).decode()
+                for i in range(L.b200_params_num_actions(self.h))]
+
+    @property
+    def volume_labels(self):
+        L = load_library()
+        return [L.b200_params_volume_label(self.h, i).decode()
+                for i in range(L.b200_params_num_volumes(self.h))]
+
+    @property
+    def num_detectors(self):
+        return load_library().b200_params_num_detectors(self.h)
+
+    def find_particle(self, pdg):
+        r = load_library().b200_params_find_particle(self.h, pdg)
+        return None if r == 0xffffffff else r
+
+
+class Stepper:
+    """One stream's stepping loop (reference: Stepper<MemSpace::device>)."""
+
+    def __init__(self, params, num_track_slots, stream_id=0):
+        L = load_library()
+        self.params = params
+        self.n = num_track_slots
+        h = C.c_void_p()
+        _check(L.b200_stepper_create(params.h, stream_id, num_track_slots, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, 'h', None):
+                load_library().b200_stepper_destroy(self.h)
+        except Exception:
+            pass
+
+    def step(self, primaries=None):
+        L = load_library()
+        r = StepperResult()
+        if primaries is not None and len(primaries):
+            primaries = np.ascontiguousarray(primaries, dtype=PRIMARY_DTYPE)
+            _check(L.b200_stepper_step(self.h, primaries.ctypes.data, len(primaries), C.byref(r)))
+        else:
+            _check(L.b200_stepper_step(self.h, None, 0, C.byref(r)))
+        return dict(generated=r.generated, queued=r.queued, active=r.active, alive=r.alive)
+
+    def warm_up(self):
+        _check(load_library().b200_stepper_warm_up(self.h))
+
+    def reseed(self, event_id):
+        _check(load_library().b200_stepper_reseed(self.h, event_id))
+
+    def kill_active(self):
+        _check(load_library().b200_stepper_kill_active(self.h))
+
+    @property
+    def step_action_labels(self):
+        L = load_library()
+        return [L.b200_stepper_step_action_label(self.h, i).decode()
+                for i in range(L.b200_stepper_num_step_actions(self.h))]
+
+    @property
+    def launch_count(self):
+        return int(load_library().b200_stepper_launch_count(self.h))
+
+    def get(self, field):
+        L = load_library()
+        dt, w = FIELDS[field]
+        out = np.zeros((self.n, w) if w > 1 else self.n, dtype=dt)
+        _check(L.b200_state_get(L.b200_stepper_state(self.h), field.encode(), out.ctypes.data))
+        return out
+
+    def calo(self):
+        L = load_library()
+        out = np.zeros(self.params.num_detectors)
+        _check(L.b200_state_calo_get(L.b200_stepper_state(self.h), out.ctypes.data))
+        return out
+
+    def calo_clear(self):
+        L = load_library()
+        _check(L.b200_state_calo_clear(L.b200_stepper_state(self.h)))
+
+    def run_events(self, primaries, offsets, merge_events=False, max_steps=0):
+        """Transport whole events from HOST buffers (celer-sim Transporter loop)."""
+        L = load_library()
+        primaries = np.ascontiguousarray(primaries, dtype=PRIMARY_DTYPE)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        r = RunResult()
+        _check(L.b200_run_events(self.h, primaries.ctypes.data, offsets.ctypes.data,
+                                 len(offsets) - 1, int(merge_events), max_steps, C.byref(r)))
+        return dict(num_steps=int(r.num_steps), num_step_iterations=int(r.num_step_iterations),
+                    num_primaries=int(r.num_primaries), max_queued=int(r.max_queued),
+                    seconds=r.seconds)
+
+
+def make_primaries(n, particle_id=0, energy=100.0, pos=(0, 0, 0), direction=(1, 0, 0),
+                   event_of=lambda i: 0):
+    p = np.zeros(n, dtype=PRIMARY_DTYPE)
+    p['particle_id'] = particle_id
+    p['energy'] = energy
+    p['pos'] = pos
+    p['dir'] = direction
+    p['event_id'] = [event_of(i) for i in range(n)]
+    return p

@@ -1,0 +1,184 @@
+/*---------------------------------------------------------------------------*
+ * celeritas_b200: C-ABI of the B200-native per-step track loop.
+ *
+ * Plain C, pointers and sizes only. Everything the reference's step loop does
+ * on the device is reachable from here; there is no CPU fallback behind any
+ * entry point (they fail with a CUDA error code when no device is present).
+ *
+ * The entry points mirror the reference's plugin surface for the hot path:
+ *
+ *   reference (file:line under /root/reference/src)               | here
+ *   ---------------------------------------------------------------+---------------------------
+ *   CoreParams (celeritas/global/CoreParams.hh:42-146)             | b200_params_*
+ *   CoreState<device> (celeritas/global/CoreState.hh:73-182)       | b200_state_*
+ *   StepActionInterface::step(params, state)                       | b200_step_<action>
+ *     (corecel/sys/ActionInterface.hh:175-186), one per action:    |
+ *     ExtendFromPrimariesAction (track/ExtendFromPrimariesAction.cc:183-231)   | b200_step_extend_from_primaries
+ *     InitializeTracksAction (track/InitializeTracksAction.cc:55-97)           | b200_step_initialize_tracks
+ *     PreStepAction (phys/detail/PreStepExecutor.hh:45-115)                    | b200_step_pre_step
+ *     AlongStep{Neutral,GeneralLinear,UniformMsc}Action                        | b200_step_along_step
+ *       (global/alongstep/AlongStep.hh:50-58)                                  |
+ *     DiscreteSelectAction (phys/detail/DiscreteSelectExecutor.hh:37-63)       | b200_step_discrete_select
+ *     *Model::step (em/model/*Model.cu via InteractionApplier)                 | b200_step_interact
+ *     BoundaryAction (geo/detail/BoundaryExecutor.hh:41-84)                    | b200_step_boundary
+ *     TrackingCutAction (phys/detail/TrackingCutExecutor.hh:48-83)             | b200_step_tracking_cut
+ *     StepGather/SimpleCalo (user/detail/SimpleCaloExecutor.hh:48-67)          | b200_step_tally
+ *     ExtendFromSecondariesAction (track/ExtendFromSecondariesAction.cc:55-100)| b200_step_extend_from_secondaries
+ *   Stepper<device> (celeritas/global/Stepper.hh:82-190)           | b200_stepper_*
+ *   reseed_rng (celeritas/random/RngReseed.cu:29-74)               | b200_reseed
+ *   celer-sim Runner/Transporter (app/celer-sim/Transporter.cc:84-179) | b200_run_events
+ *
+ * Return convention: 0 on success; a positive cudaError_t value for CUDA
+ * failures; B200_ERR_* (>= 10000) for library errors. b200_last_error() gives
+ * a message for the calling thread.
+ *---------------------------------------------------------------------------*/
+#ifndef CELERITAS_B200_H
+#define CELERITAS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+enum
+{
+    B200_OK = 0,
+    B200_ERR_INVALID_ARGUMENT = 10001,
+    B200_ERR_IMAGE = 10002,
+    B200_ERR_INITIALIZER_CAPACITY = 10003, /* reference: CELER_VALIDATE in ExtendFromSecondariesAction.cc:89-95 */
+    B200_ERR_GEOMETRY_LIMITS = 10004,
+    B200_ERR_NO_DEVICE = 10005,
+    B200_ERR_RUNTIME = 10006
+};
+
+/* One primary particle (reference: celeritas::Primary, phys/Primary.hh). */
+typedef struct B200Primary
+{
+    uint32_t particle_id;
+    uint32_t event_id;
+    double energy; /* MeV */
+    double pos[3]; /* cm */
+    double dir[3];
+    double time; /* s */
+} B200Primary;
+
+/* Result of one step iteration (reference: StepperResult, Stepper.hh:57-70). */
+typedef struct B200StepperResult
+{
+    uint32_t generated;
+    uint32_t queued;
+    uint32_t active;
+    uint32_t alive;
+} B200StepperResult;
+
+/* Whole-run tallies (reference: TransporterResult, app/celer-sim/Transporter.hh). */
+typedef struct B200RunResult
+{
+    uint64_t num_steps;           /* sum over iterations of active tracks */
+    uint64_t num_step_iterations;
+    uint64_t num_primaries;
+    uint64_t max_queued;
+    double seconds;               /* device time of the transport loop */
+} B200RunResult;
+
+/* Opaque views holding device pointers (layout: celeritas_b200/csrc/views.cuh). */
+typedef struct B200ParamsView B200ParamsView;
+typedef struct B200StateView B200StateView;
+/* Opaque host-side objects. */
+typedef struct B200Params B200Params;
+typedef struct B200State B200State;
+typedef struct B200Stepper B200Stepper;
+
+char const* b200_last_error(void);
+int b200_device_count(void);
+
+/*--- problem parameters ---------------------------------------------------*/
+/* Load a flattened problem image (celeritas_b200/host/Image.hh) into HBM. */
+int b200_params_create_from_image(char const* image_path, B200Params** out);
+void b200_params_destroy(B200Params* params);
+B200ParamsView const* b200_params_view(B200Params const* params);
+/* Problem metadata */
+uint32_t b200_params_num_actions(B200Params const* params);
+char const* b200_params_action_label(B200Params const* params, uint32_t action_id);
+uint32_t b200_params_num_volumes(B200Params const* params);
+char const* b200_params_volume_label(B200Params const* params, uint32_t volume_id);
+uint32_t b200_params_num_detectors(B200Params const* params);
+uint32_t b200_params_find_particle(B200Params const* params, int pdg); /* 0xffffffff if absent */
+
+/*--- per-stream state -------------------------------------------------------*/
+int b200_state_create(B200Params const* params,
+                      uint32_t stream_id,
+                      uint32_t num_track_slots,
+                      B200State** out);
+void b200_state_destroy(B200State* state);
+B200StateView const* b200_state_view(B200State const* state);
+/* Copy one per-slot field to the host (names as in oracle/celerref.py FIELDS). */
+int b200_state_get(B200State* state, char const* field, void* out);
+/* Per-detector energy deposition [MeV] */
+int b200_state_calo_get(B200State* state, double* out);
+int b200_state_calo_clear(B200State* state);
+
+/*--- step actions (asynchronous on `stream`) --------------------------------*/
+int b200_step_extend_from_primaries(B200StateView const* state,
+                                    B200Primary const* d_primaries,
+                                    uint32_t const* d_rank_in_event,
+                                    uint32_t const* d_event_ids,
+                                    uint32_t const* d_event_counts,
+                                    uint32_t num_events,
+                                    uint32_t n,
+                                    cudaStream_t stream);
+int b200_step_initialize_tracks(B200ParamsView const*, B200StateView const*, cudaStream_t);
+int b200_step_pre_step(B200ParamsView const*, B200StateView const*, cudaStream_t);
+int b200_step_along_step(B200ParamsView const*, B200StateView const*, cudaStream_t);
+int b200_step_discrete_select(B200ParamsView const*, B200StateView const*, cudaStream_t);
+int b200_step_interact(B200ParamsView const*, B200StateView const*, cudaStream_t);
+int b200_step_boundary(B200ParamsView const*, B200StateView const*, cudaStream_t);
+int b200_step_tracking_cut(B200ParamsView const*, B200StateView const*, cudaStream_t);
+int b200_step_tally(B200ParamsView const*, B200StateView const*, cudaStream_t);
+int b200_step_extend_from_secondaries(B200ParamsView const*, B200StateView const*, cudaStream_t);
+int b200_reseed(B200ParamsView const*, B200StateView const*, uint64_t event_id, cudaStream_t);
+int b200_reset_generated(B200StateView const*, cudaStream_t);
+int b200_kill_active(B200ParamsView const*, B200StateView const*, cudaStream_t);
+
+/* Total kernel launches issued by this library in this process */
+uint64_t b200_launch_count(void);
+
+/*--- stepper (owns a state and the ordered action sequence) ------------------*/
+int b200_stepper_create(B200Params const* params,
+                        uint32_t stream_id,
+                        uint32_t num_track_slots,
+                        B200Stepper** out);
+void b200_stepper_destroy(B200Stepper* stepper);
+B200State* b200_stepper_state(B200Stepper* stepper);
+/* One step iteration; host primaries may be NULL/0. Synchronises to read counters. */
+int b200_stepper_step(B200Stepper* stepper,
+                      B200Primary const* primaries,
+                      uint32_t num_primaries,
+                      B200StepperResult* result);
+int b200_stepper_warm_up(B200Stepper* stepper);
+int b200_stepper_reseed(B200Stepper* stepper, uint64_t event_id);
+int b200_stepper_kill_active(B200Stepper* stepper);
+uint32_t b200_stepper_num_step_actions(B200Stepper const* stepper);
+char const* b200_stepper_step_action_label(B200Stepper const* stepper, uint32_t i);
+/* Kernel launches issued by this stepper so far */
+uint64_t b200_stepper_launch_count(B200Stepper const* stepper);
+
+/*--- whole events (celer-sim Transporter loop) -------------------------------*/
+/* Event e owns primaries [offsets[e], offsets[e+1]); host buffers. */
+int b200_run_events(B200Stepper* stepper,
+                    B200Primary const* primaries,
+                    uint32_t const* offsets,
+                    uint32_t num_events,
+                    int merge_events,
+                    uint64_t max_steps,
+                    B200RunResult* result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CELERITAS_B200_H */

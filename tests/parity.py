@@ -1,0 +1,58 @@
+"""Helpers shared by the parity tests: lock-step comparison of the CUDA stepper with the
+reference's host Stepper (oracle/_ref) on identical inputs."""
+import numpy as np
+
+INT_FIELDS = ['status', 'particle_id', 'volume_id', 'surface_id', 'post_step_action',
+              'along_step_action', 'num_steps', 'event_id', 'material_id', 'track_id',
+              'parent_id']
+REAL_FIELDS = ['energy', 'pos', 'dir', 'step_length', 'time', 'energy_deposition',
+               'interaction_mfp']
+
+
+def compare_states(ref, gpu, step, rtol=1e-11, atol=1e-11, check_rng=True, skip=()):
+    """Compare every per-slot field; integers exactly, reals within tolerance.
+
+    rtol/atol: transcendental functions (log/exp/sin/cos) differ between glibc and CUDA
+    libm by a few ulp, which is the only source of real-valued differences.
+    """
+    status = ref.get('status')
+    active = status != 0
+    for f in INT_FIELDS:
+        if f in skip:
+            continue
+        a, b = ref.get(f), gpu.get(f)
+        if f in ('material_id', 'event_id', 'track_id', 'parent_id', 'particle_id', 'num_steps'):
+            a, b = a[active], b[active]  # stale values in inactive slots are unspecified
+        assert np.array_equal(a, b), 'step %d field %s differs: ref=%s gpu=%s' % (
+            step, f, a[a != b][:8], b[a != b][:8])
+    for f in REAL_FIELDS:
+        if f in skip:
+            continue
+        a, b = ref.get(f)[active], gpu.get(f)[active]
+        fin = np.isfinite(a)
+        assert np.array_equal(fin, np.isfinite(b)), 'step %d field %s finiteness' % (step, f)
+        assert np.allclose(a[fin], b[fin], rtol=rtol, atol=atol), \
+            'step %d field %s differs by %g' % (step, f, np.max(np.abs(a[fin] - b[fin])))
+    if check_rng:
+        a, b = ref.get('rng'), gpu.get('rng')
+        assert np.array_equal(a, b), 'step %d: RNG streams diverged in slots %s' % (
+            step, np.nonzero((a != b).any(axis=1))[0][:8])
+
+
+def lockstep(ref, gpu, primaries, max_iters=100000, compare_every=1, **kw):
+    """Step both until done, comparing counters every step and states every k steps."""
+    cr = ref.step(primaries)
+    cg = gpu.step(primaries)
+    it = 0
+    history = []
+    while True:
+        assert cr == cg, 'step %d counters differ: ref=%s gpu=%s' % (it, cr, cg)
+        history.append(cr)
+        if compare_every and it % compare_every == 0:
+            compare_states(ref, gpu, it, **kw)
+        if not (cr['queued'] > 0 or cr['alive'] > 0) or it >= max_iters:
+            break
+        cr = ref.step()
+        cg = gpu.step()
+        it += 1
+    return history
