@@ -410,13 +410,15 @@ __global__ void k_end_pass1(ParamsView const p, StateView s)
 {
     u32 slot = thread_slot();
     SlotEnd e = classify_slot(p, s, slot);
-    u32 tv, ts;
+    u32 tv, ts, ta;
     block_exclusive_scan<BLOCK>(e.is_vacant, &tv);
     block_exclusive_scan<BLOCK>(e.num_sec, &ts);
+    block_exclusive_scan<BLOCK>(e.num_sec + (e.reuse_slot ? 1u : 0u), &ta);
     if (threadIdx.x == 0)
     {
         s.block_scratch[blockIdx.x] = tv;
         s.block_scratch[gridDim.x + blockIdx.x] = ts;
+        s.block_scratch[2 * gridDim.x + blockIdx.x] = ta;
     }
 }
 
@@ -424,17 +426,18 @@ __global__ void k_end_pass2(StateView s, u32 num_blocks)
 {
     // Single block: scan block totals (chunked)
     constexpr int B = 1024;
-    __shared__ u32 carry[2];
+    __shared__ u32 carry[3];
     if (threadIdx.x == 0)
     {
         carry[0] = 0;
         carry[1] = 0;
+        carry[2] = 0;
     }
     __syncthreads();
     for (u32 base = 0; base < num_blocks; base += B)
     {
         u32 i = base + threadIdx.x;
-        for (int a = 0; a < 2; ++a)
+        for (int a = 0; a < 3; ++a)
         {
             u32 v = i < num_blocks ? s.block_scratch[a * num_blocks + i] : 0;
             u32 total;
@@ -458,6 +461,13 @@ __global__ void k_end_pass2(StateView s, u32 num_blocks)
         s.counters[CTR_NUM_ALIVE] = s.num_slots - num_vac;
         if (num_init > s.init_capacity)
             s.counters[CTR_ERROR] = B200_ERR_INITIALIZER_CAPACITY;
+        // Single event in flight: track ids are assigned in slot order from the
+        // scan (what the reference's sequential host loop produces)
+        if (s.single_event != INVALID)
+        {
+            s.counters[CTR_TRACK_ID_BASE] = s.track_counters[s.single_event];
+            s.track_counters[s.single_event] += carry[2];
+        }
     }
 }
 
@@ -465,10 +475,12 @@ __global__ void k_end_pass3(ParamsView const p, StateView s)
 {
     u32 slot = thread_slot();
     SlotEnd e = classify_slot(p, s, slot);
-    u32 tv, ts;
+    u32 tv, ts, ta;
     u32 vac_off = block_exclusive_scan<BLOCK>(e.is_vacant, &tv) + s.block_scratch[blockIdx.x];
     u32 sec_off = block_exclusive_scan<BLOCK>(e.num_sec, &ts)
                   + s.block_scratch[gridDim.x + blockIdx.x];
+    u32 all_off = block_exclusive_scan<BLOCK>(e.num_sec + (e.reuse_slot ? 1u : 0u), &ta)
+                  + s.block_scratch[2 * gridDim.x + blockIdx.x];
     if (slot >= s.num_slots)
         return;
     if (s.counters[CTR_ERROR] != 0)
@@ -494,8 +506,13 @@ __global__ void k_end_pass3(ParamsView const p, StateView s)
     Real3 const pos = geo.pos();
 
     // Track ids: per-event counter (reference: atomic_add, detail/Utils.hh:107-116)
+    // (deterministic slot-order ids when a single event is in flight)
     u32 nsec_here = e.num_sec + (e.reuse_slot ? 1 : 0);
-    u32 id_base = nsec_here ? atomicAdd(&s.track_counters[event], nsec_here) : 0;
+    u32 id_base;
+    if (s.single_event != INVALID)
+        id_base = s.counters[CTR_TRACK_ID_BASE] + all_off;
+    else
+        id_base = nsec_here ? atomicAdd(&s.track_counters[event], nsec_here) : 0;
 
     for (int i = 0; i < MAX_SECONDARIES; ++i)
     {

@@ -253,9 +253,126 @@ struct KleinNishinaParams
     real inv_electron_mass;
 };
 
+struct MollerBhabhaParams
+{
+    u32 action;
+    u32 electron;
+    u32 positron;
+    real electron_mass;
+};
+
+struct EPlusGGParams
+{
+    u32 action;
+    u32 positron;
+    u32 gamma;
+    real electron_mass;
+};
+
+struct BetheHeitlerParams
+{
+    u32 action;
+    u32 electron;
+    u32 positron;
+    u32 gamma;
+    u32 enable_lpm;
+    real electron_mass;
+};
+
+//! Seltzer-Berger scaled differential cross sections: one 2D grid per element
+//! (log E x exiting fraction), see em/data/SeltzerBergerData.hh
+struct SeltzerBergerParams
+{
+    u32 action;
+    u32 electron;
+    u32 positron;
+    u32 gamma;
+    real electron_mass;
+    // per element: 8 u32 {x_begin, x_size, y_begin, y_size, values_begin, argmax_begin, 0, 0}
+    u32 const* elements;
+    u32 const* sizes;   // argmax values (y index of the row maximum)
+    real const* reals;
+};
+
+struct RelativisticBremParams
+{
+    u32 action;
+    u32 electron;
+    u32 positron;
+    u32 gamma;
+    u32 enable_lpm;
+    real electron_mass;
+    // per element: fz, factor1, factor2, gamma_factor, epsilon_factor
+    real const* elem_data;
+};
+
+//! Livermore photoelectric data (em/data/LivermorePEData.hh)
+struct LivermorePEParams
+{
+    u32 action;
+    u32 electron;
+    u32 gamma;
+    real inv_electron_mass;
+    // per element: 8 u32 {xs_lo grid begin, xs_lo size, xs_lo value begin, xs_hi grid begin,
+    //                     xs_hi size, xs_hi value begin, shell begin, shell count}
+    u32 const* elements;
+    real const* element_thresh;  // 2 per element: thresh_lo, thresh_hi
+    // per shell: 4 u32 {grid begin, size, value begin, 0}
+    u32 const* shells;
+    // per shell: 13 reals {binding_energy, param_lo[6], param_hi[6]}
+    real const* shell_reals;
+    real const* reals;
+};
+
+//! Urban multiple scattering (em/data/UrbanMscData.hh)
+struct UrbanMscParams
+{
+    u32 enabled;
+    u32 electron;
+    u32 positron;
+    real electron_mass;
+    real tau_small, tau_big, tau_limit, safety_tol, geom_limit;
+    real low_energy_limit, high_energy_limit;
+    // per material: 8 reals {stepmin_coeff[2], theta_coeff[2], tail_coeff[3], tail_corr}
+    real const* material_data;
+    // per (material, particle in {e-, e+}): 2 reals {scaled_zeff, d_over_r}
+    real const* par_mat_data;
+    // per (material, particle): xs grid {size, prime, value offset} + log grid
+    u32 const* xs_grid_u32;   // 3 per entry: size, prime_index, value_offset
+    real const* xs_grid_f64;  // 3 per entry: log_front, log_back, log_delta
+    real const* reals;
+};
+
+//! Energy-loss fluctuation (em/data/FluctuationData.hh)
+struct FluctuationParams
+{
+    u32 enabled;
+    u32 electron;
+    real electron_mass;
+    // per material: 6 reals {binding_energy[2], log_binding_energy[2], oscillator_strength[2]}
+    real const* urban;
+};
+
+struct PhysConstants
+{
+    real migdal_constant;
+    real lpm_constant;     // MeV / len
+    real r_electron;
+    real alpha_fine_structure;
+};
+
 struct ModelParams
 {
     KleinNishinaParams kn;
+    MollerBhabhaParams mb;
+    EPlusGGParams epgg;
+    BetheHeitlerParams bh;
+    SeltzerBergerParams sb;
+    RelativisticBremParams rb;
+    LivermorePEParams pe;
+    UrbanMscParams msc;
+    FluctuationParams fluct;
+    PhysConstants constants;
 };
 
 //---------------------------------------------------------------------------//
@@ -382,7 +499,8 @@ struct StateView
 
     // device-resident counters (mirrors CoreStateCounters) + scratch
     u32* counters;           // see Counter enum
-    u32* block_scratch;      // [2 * num_blocks] per-block totals for the end-of-step scans
+    u32* block_scratch;      // [3 * num_blocks] per-block totals for the end-of-step scans
+    u32 single_event;        // event id if exactly one event is in flight, else INVALID
 
     // scoring (null when no detectors are registered)
     u32* pre_volume;                     // [slot] global volume id at the pre-step point
@@ -403,6 +521,7 @@ enum Counter : u32
     CTR_NUM_ALIVE,
     CTR_NUM_NEW_TRACKS,
     CTR_ERROR,
+    CTR_TRACK_ID_BASE,
     CTR_SIZE = 16
 };
 

@@ -248,6 +248,109 @@ void CoreParams::load(Image const& img)
             m.kn.inv_electron_mass = img.get_scalar<double>("model.kn.inv_electron_mass");
             m.kn.action = img.get_scalar<uint32_t>("model.kn.action");
         }
+        m.mb.action = INVALID;
+        if (img.has("model.mb.ids"))
+        {
+            auto ids = img.get<uint32_t>("model.mb.ids");
+            m.mb.action = ids.at(0);
+            m.mb.electron = ids.at(1);
+            m.mb.positron = ids.at(2);
+            m.mb.electron_mass = img.get_scalar<double>("model.mb.electron_mass");
+        }
+        m.epgg.action = INVALID;
+        if (img.has("model.epgg.ids"))
+        {
+            auto ids = img.get<uint32_t>("model.epgg.ids");
+            m.epgg.action = ids.at(0);
+            m.epgg.positron = ids.at(1);
+            m.epgg.gamma = ids.at(2);
+            m.epgg.electron_mass = img.get_scalar<double>("model.epgg.electron_mass");
+        }
+        m.bh.action = INVALID;
+        if (img.has("model.bh.ids"))
+        {
+            auto ids = img.get<uint32_t>("model.bh.ids");
+            m.bh.action = ids.at(0);
+            m.bh.electron = ids.at(1);
+            m.bh.positron = ids.at(2);
+            m.bh.gamma = ids.at(3);
+            m.bh.enable_lpm = ids.at(4);
+            m.bh.electron_mass = img.get_scalar<double>("model.bh.electron_mass");
+        }
+        m.sb.action = INVALID;
+        if (img.has("model.sb.ids"))
+        {
+            auto ids = img.get<uint32_t>("model.sb.ids");
+            m.sb.action = ids.at(0);
+            m.sb.electron = ids.at(1);
+            m.sb.positron = ids.at(2);
+            m.sb.gamma = ids.at(3);
+            m.sb.electron_mass = img.get_scalar<double>("model.sb.electron_mass");
+            m.sb.elements = U32("model.sb.elements");
+            m.sb.sizes = U32("model.sb.sizes");
+            m.sb.reals = F64("model.sb.reals");
+        }
+        m.rb.action = INVALID;
+        if (img.has("model.rb.ids"))
+        {
+            auto ids = img.get<uint32_t>("model.rb.ids");
+            m.rb.action = ids.at(0);
+            m.rb.electron = ids.at(1);
+            m.rb.positron = ids.at(2);
+            m.rb.gamma = ids.at(3);
+            m.rb.enable_lpm = ids.at(4);
+            m.rb.electron_mass = img.get_scalar<double>("model.rb.electron_mass");
+            m.rb.elem_data = F64("model.rb.elem_data");
+        }
+        m.pe.action = INVALID;
+        if (img.has("model.pe.ids"))
+        {
+            auto ids = img.get<uint32_t>("model.pe.ids");
+            m.pe.action = ids.at(0);
+            m.pe.electron = ids.at(1);
+            m.pe.gamma = ids.at(2);
+            m.pe.inv_electron_mass = img.get_scalar<double>("model.pe.inv_electron_mass");
+            m.pe.elements = U32("model.pe.elements");
+            m.pe.element_thresh = F64("model.pe.element_thresh");
+            m.pe.shells = U32("model.pe.shells");
+            m.pe.shell_reals = F64("model.pe.shell_reals");
+            m.pe.reals = F64("model.pe.reals");
+        }
+        m.msc.enabled = 0;
+        if (img.has("msc.ids"))
+        {
+            auto ids = img.get<uint32_t>("msc.ids");
+            auto pr = img.get<double>("msc.params");
+            m.msc.enabled = 1;
+            m.msc.electron = ids.at(0);
+            m.msc.positron = ids.at(1);
+            m.msc.electron_mass = pr.at(0);
+            m.msc.tau_small = pr.at(1);
+            m.msc.tau_big = pr.at(2);
+            m.msc.tau_limit = pr.at(3);
+            m.msc.safety_tol = pr.at(4);
+            m.msc.geom_limit = pr.at(5);
+            m.msc.low_energy_limit = pr.at(6);
+            m.msc.high_energy_limit = pr.at(7);
+            m.msc.material_data = F64("msc.material_data");
+            m.msc.par_mat_data = F64("msc.par_mat_data");
+            m.msc.xs_grid_u32 = U32("msc.xs_grid_u32");
+            m.msc.xs_grid_f64 = F64("msc.xs_grid_f64");
+            m.msc.reals = F64("msc.reals");
+        }
+        m.fluct.enabled = 0;
+        if (img.has("fluct.urban"))
+        {
+            m.fluct.enabled = 1;
+            m.fluct.electron = img.get_scalar<uint32_t>("fluct.electron");
+            m.fluct.electron_mass = img.get_scalar<double>("fluct.electron_mass");
+            m.fluct.urban = F64("fluct.urban");
+        }
+        auto c = img.get<double>("constants");
+        m.constants.migdal_constant = c.at(0);
+        m.constants.lpm_constant = c.at(1);
+        m.constants.r_electron = c.at(2);
+        m.constants.alpha_fine_structure = c.at(3);
     }
 
     //// RNG / SIM ////

@@ -115,7 +115,8 @@ CoreState::CoreState(std::shared_ptr<CoreParams const> params,
         ctr[CTR_NUM_VACANCIES] = n;
         s.counters = const_cast<u32*>(arena_.upload(ctr));
         uint32_t num_blocks = (n + 127) / 128;
-        s.block_scratch = arena_.alloc<u32>(size_t(2) * num_blocks);
+        s.block_scratch = arena_.alloc<u32>(size_t(3) * num_blocks);
+        s.single_event = INVALID;
         s.step_counters = arena_.alloc<u64>(4);
     }
     // Scoring

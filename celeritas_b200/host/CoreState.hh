@@ -36,6 +36,8 @@ class CoreState
     CoreState& operator=(CoreState const&) = delete;
 
     b200::StateView const& view() const { return view_; }
+    //! Declare which single event is in flight (INVALID: several / unknown)
+    void single_event(uint32_t event_id) { view_.single_event = event_id; }
     uint32_t size() const { return view_.num_slots; }
     uint32_t stream_id() const { return stream_id_; }
     cudaStream_t stream() const { return stream_; }

@@ -224,6 +224,11 @@ void Stepper::insert(B200Primary const* primaries, uint32_t n)
     }
     st.count = n;
     st.num_events = ne;
+    // Track which events are in flight: with exactly one, secondaries get
+    // deterministic slot-ordered track ids
+    for (auto const& kv : counts)
+        events_in_flight_.insert(kv.first);
+    state_->single_event(events_in_flight_.size() == 1 ? *events_in_flight_.begin() : INVALID);
 }
 
 void Stepper::step_async()
@@ -275,6 +280,11 @@ StepperResult Stepper::operator()()
     r.active = c.num_active;
     r.alive = c.num_alive;
     r.queued = c.num_initializers;
+    if (!r)
+    {
+        events_in_flight_.clear();
+        state_->single_event(INVALID);
+    }
     return r;
 }
 

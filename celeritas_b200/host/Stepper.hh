@@ -16,6 +16,7 @@
 
 #include <functional>
 #include <memory>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -115,5 +116,6 @@ class Stepper
     // staging for primaries (pinned host + device)
     struct Staging;
     std::unique_ptr<Staging> staging_;
+    std::set<uint32_t> events_in_flight_;
 };
 }  // namespace celeritas_b200

@@ -15,6 +15,8 @@
 #include "corecel/sys/ActionRegistry.hh"
 #include "orange/OrangeData.hh"
 #include "orange/OrangeParams.hh"
+#include "celeritas/Quantities.hh"
+#include "celeritas/em/interactor/detail/PhysicsConstants.hh"
 #include "celeritas/em/model/BetheHeitlerModel.hh"
 #include "celeritas/em/model/EPlusGGModel.hh"
 #include "celeritas/em/model/KleinNishinaModel.hh"
@@ -508,8 +510,238 @@ void export_models(Problem const& prob, b200::Image& img)
             img.put_scalar<uint32_t>("model.kn.action",
                                      kn->action_id().unchecked_get());
         }
+        else if (auto* mb = dynamic_cast<MollerBhabhaModel const*>(&model))
+        {
+            auto const& d = mb->host_ref();
+            img.put("model.mb.ids",
+                    U32{mb->action_id().unchecked_get(),
+                        raw(d.ids.electron),
+                        raw(d.ids.positron)});
+            img.put_scalar<double>("model.mb.electron_mass",
+                                   d.electron_mass.value());
+        }
+        else if (auto* ep = dynamic_cast<EPlusGGModel const*>(&model))
+        {
+            auto const& d = ep->host_ref();
+            img.put("model.epgg.ids",
+                    U32{ep->action_id().unchecked_get(),
+                        raw(d.positron),
+                        raw(d.gamma)});
+            img.put_scalar<double>("model.epgg.electron_mass",
+                                   d.electron_mass.value());
+        }
+        else if (auto* bh = dynamic_cast<BetheHeitlerModel const*>(&model))
+        {
+            auto const& d = bh->host_ref();
+            img.put("model.bh.ids",
+                    U32{bh->action_id().unchecked_get(),
+                        raw(d.ids.electron),
+                        raw(d.ids.positron),
+                        raw(d.ids.gamma),
+                        d.enable_lpm ? 1u : 0u});
+            img.put_scalar<double>("model.bh.electron_mass",
+                                   d.electron_mass.value());
+        }
+        else if (auto* sb = dynamic_cast<SeltzerBergerModel const*>(&model))
+        {
+            auto const& d = sb->host_ref();
+            img.put("model.sb.ids",
+                    U32{sb->action_id().unchecked_get(),
+                        raw(d.ids.electron),
+                        raw(d.ids.positron),
+                        raw(d.ids.gamma)});
+            img.put_scalar<double>("model.sb.electron_mass",
+                                   d.electron_mass.value());
+            auto const& t = d.differential_xs;
+            U32 rows;
+            for (auto const& el : all(t.elements))
+            {
+                rows.push_back(el.grid.x.begin()->unchecked_get());
+                rows.push_back(el.grid.x.size());
+                rows.push_back(el.grid.y.begin()->unchecked_get());
+                rows.push_back(el.grid.y.size());
+                rows.push_back(el.grid.values.begin()->unchecked_get());
+                rows.push_back(el.argmax.begin()->unchecked_get());
+                rows.push_back(0);
+                rows.push_back(0);
+            }
+            img.put("model.sb.elements", rows);
+            U32 sizes(all(t.sizes).begin(), all(t.sizes).end());
+            img.put("model.sb.sizes", sizes);
+            F64 reals(all(t.reals).begin(), all(t.reals).end());
+            img.put("model.sb.reals", reals);
+        }
+        else if (auto* rb = dynamic_cast<RelativisticBremModel const*>(&model))
+        {
+            auto const& d = rb->host_ref();
+            img.put("model.rb.ids",
+                    U32{rb->action_id().unchecked_get(),
+                        raw(d.ids.electron),
+                        raw(d.ids.positron),
+                        raw(d.ids.gamma),
+                        d.enable_lpm ? 1u : 0u});
+            img.put_scalar<double>("model.rb.electron_mass",
+                                   d.electron_mass.value());
+            F64 ed;
+            for (auto const& e : all(d.elem_data))
+            {
+                ed.push_back(e.fz);
+                ed.push_back(e.factor1);
+                ed.push_back(e.factor2);
+                ed.push_back(e.gamma_factor);
+                ed.push_back(e.epsilon_factor);
+            }
+            img.put("model.rb.elem_data", ed);
+        }
+        else if (auto* pe = dynamic_cast<LivermorePEModel const*>(&model))
+        {
+            auto const& d = pe->host_ref();
+            img.put("model.pe.ids",
+                    U32{pe->action_id().unchecked_get(),
+                        raw(d.ids.electron),
+                        raw(d.ids.gamma)});
+            img.put_scalar<double>("model.pe.inv_electron_mass",
+                                   d.inv_electron_mass);
+            U32 el_rows, sh_rows;
+            F64 el_thresh, sh_reals;
+            for (auto const& el : all(d.xs.elements))
+            {
+                el_rows.push_back(el.xs_lo.grid.empty()
+                                      ? 0
+                                      : el.xs_lo.grid.begin()->unchecked_get());
+                el_rows.push_back(el.xs_lo.grid.size());
+                el_rows.push_back(el.xs_lo.value.empty()
+                                      ? 0
+                                      : el.xs_lo.value.begin()->unchecked_get());
+                el_rows.push_back(el.xs_hi.grid.begin()->unchecked_get());
+                el_rows.push_back(el.xs_hi.grid.size());
+                el_rows.push_back(el.xs_hi.value.begin()->unchecked_get());
+                el_rows.push_back(el.shells.begin()->unchecked_get());
+                el_rows.push_back(el.shells.size());
+                el_thresh.push_back(el.thresh_lo.value());
+                el_thresh.push_back(el.thresh_hi.value());
+            }
+            for (auto const& sh : all(d.xs.shells))
+            {
+                sh_rows.push_back(sh.xs.grid.begin()->unchecked_get());
+                sh_rows.push_back(sh.xs.grid.size());
+                sh_rows.push_back(sh.xs.value.begin()->unchecked_get());
+                sh_rows.push_back(0);
+                sh_reals.push_back(sh.binding_energy.value());
+                for (int k = 0; k < 2; ++k)
+                    for (int i = 0; i < 6; ++i)
+                        sh_reals.push_back(sh.param[k][i]);
+            }
+            img.put("model.pe.elements", el_rows);
+            img.put("model.pe.element_thresh", el_thresh);
+            img.put("model.pe.shells", sh_rows);
+            img.put("model.pe.shell_reals", sh_reals);
+            F64 reals(all(d.xs.reals).begin(), all(d.xs.reals).end());
+            img.put("model.pe.reals", reals);
+        }
+        else
+        {
+            CELER_VALIDATE(false,
+                           << "model '" << model.label()
+                           << "' has no B200 export");
+        }
     }
     img.put_string("model.labels", labels);
+
+    // Urban MSC
+    if (prob.msc)
+    {
+        auto const& d = prob.msc->host_ref();
+        img.put("msc.ids", U32{raw(d.ids.electron), raw(d.ids.positron)});
+        auto const& pr = d.params;
+        img.put("msc.params",
+                F64{d.electron_mass.value(),
+                    pr.tau_small,
+                    pr.tau_big,
+                    pr.tau_limit,
+                    pr.safety_tol,
+                    pr.geom_limit,
+                    pr.low_energy_limit.value(),
+                    pr.high_energy_limit.value()});
+        F64 md, pm, gf;
+        U32 gu;
+        for (auto const& m : all(d.material_data))
+        {
+            md.push_back(m.stepmin_coeff[0]);
+            md.push_back(m.stepmin_coeff[1]);
+            md.push_back(m.theta_coeff[0]);
+            md.push_back(m.theta_coeff[1]);
+            md.push_back(m.tail_coeff[0]);
+            md.push_back(m.tail_coeff[1]);
+            md.push_back(m.tail_coeff[2]);
+            md.push_back(m.tail_corr);
+        }
+        for (auto const& m : all(d.par_mat_data))
+        {
+            pm.push_back(m.scaled_zeff);
+            pm.push_back(m.d_over_r);
+        }
+        for (auto const& g : all(d.xs))
+        {
+            gu.push_back(g.log_energy.size);
+            gu.push_back(g.prime_index);
+            gu.push_back(g.value.begin()->unchecked_get());
+            gf.push_back(g.log_energy.front);
+            gf.push_back(g.log_energy.back);
+            gf.push_back(g.log_energy.delta);
+        }
+        img.put("msc.material_data", md);
+        img.put("msc.par_mat_data", pm);
+        img.put("msc.xs_grid_u32", gu);
+        img.put("msc.xs_grid_f64", gf);
+        F64 reals(all(d.reals).begin(), all(d.reals).end());
+        img.put("msc.reals", reals);
+    }
+    // Energy loss fluctuations
+    if (prob.fluct)
+    {
+        auto const& d = prob.fluct->host_ref();
+        img.put_scalar<uint32_t>("fluct.electron", raw(d.electron_id));
+        img.put_scalar<double>("fluct.electron_mass", d.electron_mass.value());
+        F64 u;
+        for (auto const& m : all(d.urban))
+        {
+            for (int i = 0; i < 2; ++i)
+                u.push_back(m.binding_energy[i]);
+            for (int i = 0; i < 2; ++i)
+                u.push_back(m.log_binding_energy[i]);
+            for (int i = 0; i < 2; ++i)
+                u.push_back(m.oscillator_strength[i]);
+        }
+        img.put("fluct.urban", u);
+    }
+    // Uniform field
+    if (prob.has_field)
+    {
+        F64 f{prob.field.field[0], prob.field.field[1], prob.field.field[2]};
+        auto const& o = prob.field.options;
+        img.put("field.uniform", f);
+        img.put("field.options",
+                F64{o.minimum_step,
+                    o.delta_chord,
+                    o.delta_intersection,
+                    o.epsilon_step,
+                    o.epsilon_rel_max,
+                    o.errcon,
+                    o.pgrow,
+                    o.pshrink,
+                    o.safety,
+                    o.max_stepping_increase,
+                    o.max_stepping_decrease});
+        img.put("field.options_u32", U32{static_cast<uint32_t>(o.max_nsteps), static_cast<uint32_t>(o.max_substeps)});
+    }
+    // Physical constants as the reference computes them
+    img.put("constants",
+            F64{celeritas::detail::migdal_constant(),
+                value_as<celeritas::detail::MevPerLen>(
+                    celeritas::detail::lpm_constant()),
+                constants::r_electron,
+                constants::alpha_fine_structure});
 }
 
 }  // namespace

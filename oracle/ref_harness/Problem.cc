@@ -15,6 +15,7 @@
 #include "orange/OrangeParams.hh"
 #include "celeritas/Quantities.hh"
 #include "celeritas/Units.hh"
+#include "celeritas/em/params/FluctuationParams.hh"
 #include "celeritas/em/params/UrbanMscParams.hh"
 #include "celeritas/em/params/WentzelOKVIParams.hh"
 #include "celeritas/em/process/ComptonProcess.hh"
@@ -134,7 +135,8 @@ void import_from_json(json const& j, ImportData* out)
     {
         ImportPhysMaterial r;
         r.geo_material_id = e.at("geo_material_id");
-        r.optical_material_id = e.at("optical_material_id");
+        // optical physics is outside the EM track loop: never attach optical data
+        r.optical_material_id = ImportPhysMaterial::unspecified;
         for (auto const& c : e.at("pdg_cutoffs"))
         {
             ImportProductionCut pc;
@@ -477,14 +479,16 @@ void build_imported(Problem& p, CoreParams::Input& params)
     p.has_fluct = eloss;
     std::vector<double> field = cfg.value("field", std::vector<double>{0, 0, 0});
     p.has_field = (field[0] != 0 || field[1] != 0 || field[2] != 0);
+    p.msc = msc;
+    if (eloss)
+    {
+        p.fluct = std::make_shared<FluctuationParams>(*params.particle,
+                                                      *params.material);
+    }
     if (!p.has_field)
     {
-        auto along_step = AlongStepGeneralLinearAction::from_params(
-            params.action_reg->next_id(),
-            *params.material,
-            *params.particle,
-            msc,
-            eloss);
+        auto along_step = std::make_shared<AlongStepGeneralLinearAction>(
+            params.action_reg->next_id(), p.fluct, msc);
         params.action_reg->insert(along_step);
     }
     else
@@ -495,13 +499,9 @@ void build_imported(Problem& p, CoreParams::Input& params)
             field_params.field[i]
                 = native_value_from(units::FieldTesla{field[i]});
         }
-        auto along_step = AlongStepUniformMscAction::from_params(
-            params.action_reg->next_id(),
-            *params.material,
-            *params.particle,
-            field_params,
-            msc,
-            eloss);
+        p.field = field_params;
+        auto along_step = std::make_shared<AlongStepUniformMscAction>(
+            params.action_reg->next_id(), field_params, p.fluct, msc);
         params.action_reg->insert(along_step);
     }
     params.sim = SimParams::from_import(

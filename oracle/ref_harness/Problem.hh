@@ -14,6 +14,9 @@
 #include <vector>
 #include <nlohmann/json.hpp>
 
+#include "celeritas/em/params/FluctuationParams.hh"
+#include "celeritas/em/params/UrbanMscParams.hh"
+#include "celeritas/field/UniformFieldData.hh"
 #include "celeritas/global/CoreParams.hh"
 #include "celeritas/io/ImportData.hh"
 #include "celeritas/user/SimpleCalo.hh"
@@ -29,6 +32,9 @@ struct Problem
     std::shared_ptr<celeritas::SimpleCalo> calo;
     std::shared_ptr<celeritas::StepCollector> collector;
     std::vector<std::string> calo_volumes;
+    std::shared_ptr<celeritas::UrbanMscParams const> msc;
+    std::shared_ptr<celeritas::FluctuationParams const> fluct;
+    celeritas::UniformFieldParams field;
     bool has_msc{false};
     bool has_fluct{false};
     bool has_field{false};

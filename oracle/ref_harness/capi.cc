@@ -361,3 +361,47 @@ double celerref_run_events(void* problem,
     return elapsed;
 }
 }  // extern "C"
+
+//---------------------------------------------------------------------------//
+// Element data readers (build-time helper for tools/make_physics.py): parse the
+// reference's bundled G4EMLOW excerpts (test/celeritas/data/br29, pe-*-19.dat)
+// with the reference's own readers and return them as JSON.
+//---------------------------------------------------------------------------//
+#include "celeritas/io/LivermorePEReader.hh"
+#include "celeritas/io/SeltzerBergerReader.hh"
+
+extern "C" int celerref_element_data_json(char const* dir, int z_sb, int z_pe, char* out, size_t size)
+{
+    return guarded([&] {
+        json j;
+        {
+            SeltzerBergerReader read_sb(dir);
+            auto t = read_sb(AtomicNumber{z_sb});
+            j["sb"] = {{"x", t.x}, {"y", t.y}, {"value", t.value}};
+        }
+        {
+            LivermorePEReader read_pe(dir);
+            auto pe = read_pe(AtomicNumber{z_pe});
+            auto vec = [](ImportPhysicsVector const& v) {
+                return json{{"vector_type", static_cast<int>(v.vector_type)}, {"x", v.x}, {"y", v.y}};
+            };
+            json shells = json::array();
+            for (auto const& s : pe.shells)
+            {
+                shells.push_back({{"binding_energy", s.binding_energy},
+                                  {"param_lo", s.param_lo},
+                                  {"param_hi", s.param_hi},
+                                  {"xs", s.xs},
+                                  {"energy", s.energy}});
+            }
+            j["livermore_pe"] = {{"xs_lo", vec(pe.xs_lo)},
+                                 {"xs_hi", vec(pe.xs_hi)},
+                                 {"thresh_lo", pe.thresh_lo},
+                                 {"thresh_hi", pe.thresh_hi},
+                                 {"shells", shells}};
+        }
+        std::string s = j.dump();
+        CELER_VALIDATE(s.size() + 1 <= size, << "output buffer too small");
+        std::memcpy(out, s.c_str(), s.size() + 1);
+    });
+}

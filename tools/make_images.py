@@ -1,0 +1,55 @@
+"""Export the problem images used by tests and bench (runs where /root/reference was built
+into oracle/_ref; the images are committed so the GPU box needs neither).
+
+Each image is the reference's own host-side CoreParams, flattened by the adapter in
+oracle/ref_harness/ExportImage.cc.
+"""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(REPO, 'oracle'))
+import celerref  # noqa: E402
+
+GAPS = ['gap_%d' % i for i in range(50)]
+ABSORBERS = ['absorber_%d' % i for i in range(50)]
+
+PROBLEMS = {
+    'simple-compton': {'problem': 'simple-compton',
+                       'geometry_file': 'data/geometry/two-boxes.org.json', 'seed': 20220511},
+    # BASELINE config 0: TestEm3, no field, MSC off, no fluctuations
+    'testem3-nomsc': {'geometry_file': 'data/geometry/testem3-flat.org.json',
+                      'physics_file': 'data/physics/testem3-steel-lar.json',
+                      'seed': 20220904, 'initializer_capacity': 1 << 20, 'max_events': 1024,
+                      'disable_msc': True, 'eloss_fluctuation': False,
+                      'simple_calo': GAPS + ABSORBERS},
+    # BASELINE config 1: TestEm3 full EM (Urban MSC + fluctuations)
+    'testem3': {'geometry_file': 'data/geometry/testem3-flat.org.json',
+                'physics_file': 'data/physics/testem3-steel-lar.json',
+                'seed': 20220904, 'initializer_capacity': 1 << 25, 'max_events': 16384,
+                'simple_calo': GAPS + ABSORBERS},
+    # small-capacity variant of the same physics for lock-step tests
+    'testem3-small': {'geometry_file': 'data/geometry/testem3-flat.org.json',
+                      'physics_file': 'data/physics/testem3-steel-lar.json',
+                      'seed': 20220904, 'initializer_capacity': 1 << 18, 'max_events': 64,
+                      'simple_calo': GAPS + ABSORBERS},
+}
+
+
+def main(names):
+    out = os.path.join(REPO, 'data', 'images')
+    os.makedirs(out, exist_ok=True)
+    for name in names or PROBLEMS:
+        cfg = PROBLEMS[name]
+        p = celerref.Problem(cfg)
+        path = os.path.join(out, name + '.b2img')
+        p.export_image(path)
+        with open(os.path.join(out, name + '.json'), 'w') as f:
+            json.dump(cfg, f, indent=1)
+        print(name, os.path.getsize(path))
+
+
+if __name__ == '__main__':
+    main(sys.argv[1:])
