@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Benchmark of the per-step track loop (BASELINE.json: track-steps/sec, TestEm3 full EM).
+
+A bench "step" is one complete transport of one batch of synthetic primaries: the
+workload BASELINE.json's metric is quoted on (configs[1]): TestEm3 full EM (Urban MSC +
+energy-loss fluctuations), 10 000 1 GeV e- primaries per GPU as 100 events x 100 primaries
+merged onto one state, num_track_slots = 2^20. Physics tables are the documented stand-in
+(steel absorber instead of Pb; tools/make_physics.py).
+
+  value        track-steps/s with the primaries already staged on the device
+  e2e          the same through the public C-ABI call b200_run_events with HOST primaries
+               (H2D of primaries, per-iteration D2H of counters, D2H of tallies, all timed)
+  roofline     the dominant kernel (along-step) measured live with CUDA events
+  cpu_baseline the reference's own host Stepper (oracle/_ref) on this box's host cores
+
+    python bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      (reference CPU arm)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+IMAGE = os.path.join(REPO, 'data', 'images', 'testem3.b2img')
+CONFIG = os.path.join(REPO, 'data', 'images', 'testem3.json')
+NUM_EVENTS = 100
+PRIMARIES_PER_EVENT = 100
+ENERGY_MEV = 1000.0
+NUM_TRACK_SLOTS = 1 << 20
+ALG_BYTES_PER_TRACK_STEP = 672  # 2 * S_live, D=1, P=4
+
+
+def make_events(num_events, per_event, first_event, particle_id, dtype):
+    n = num_events * per_event
+    p = np.zeros(n, dtype=dtype)
+    p['particle_id'] = particle_id
+    p['energy'] = ENERGY_MEV
+    p['pos'] = (-22, 0, 0)
+    p['dir'] = (1, 0, 0)
+    p['event_id'] = first_event + np.repeat(np.arange(num_events), per_event)
+    offsets = np.arange(0, n + 1, per_event, dtype=np.uint32)
+    return p, offsets
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.index = index
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                      '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(',')]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:]):
+                    if v.lower().startswith('active'):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thread.join(timeout=5)
+
+    def summary(self):
+        return {'sm_mhz': float(np.median(self.samples)) if self.samples else None,
+                'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return json.load(open(path))['hbm_gbs'], 'measured'
+    return 6650.0, 'fallback'
+
+
+def cpu_reference_run(num_events, per_event, slots_per_stream, threads):
+    """Time the reference's own host Stepper (one Stepper per OpenMP thread)."""
+    sys.path.insert(0, os.path.join(REPO, 'oracle'))
+    import celerref
+    cfg = json.load(open(CONFIG))
+    cfg['max_streams'] = max(threads, 1)
+    cfg['initializer_capacity'] = 1 << 22
+    problem = celerref.Problem(cfg)
+    # particle id of e- is fixed by the physics file order (e+, e-, gamma)
+    prim, offsets = make_events(num_events, per_event, 0, 1, celerref.PRIMARY_DTYPE)
+    r = problem.run_events(prim, offsets, slots_per_stream, threads)
+    return r
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = cores
+    per_event, num_events = 4, max(2 * threads, 8)
+    # warm-up passes are smaller; each timed step is the same bounded sample
+    for _ in range(args.warmup):
+        cpu_reference_run(max(threads, 4), 1, 4096, threads)
+    steps, secs = 0, 0.0
+    iters = 0
+    for _ in range(args.steps):
+        r = cpu_reference_run(num_events, per_event, 4096, threads)
+        steps += r['num_steps']
+        secs += r['seconds']
+        iters += r['num_step_iterations']
+    value = steps / secs
+    sample = ('%d events x %d primaries of 1 GeV e- per step on %d OpenMP threads, one Stepper '
+              'per thread, 4096 track slots each' % (num_events, per_event, threads))
+    line = {'impl': 'reference', 'metric': 'track-steps/sec', 'value': value,
+            'unit': 'track-steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * secs / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': 'TestEm3 full EM (Urban MSC + eloss fluctuations), 1 GeV e-, '
+                                   'steel/lAr stand-in physics', 'sample': sample},
+            'cpu_baseline': {'value': value, 'unit': 'track-steps/s', 'cores': threads,
+                             'kind': 'reference', 'sample': sample},
+            'e2e': {'value': value, 'unit': 'track-steps/s', 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0},
+            'events_per_sec': num_events * args.steps / secs}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--events', type=int, default=NUM_EVENTS)
+    ap.add_argument('--primaries-per-event', type=int, default=PRIMARIES_PER_EVENT)
+    ap.add_argument('--slots', type=int, default=NUM_TRACK_SLOTS)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import celeritas_b200 as cb
+    torch.cuda.set_device(local_rank)
+    cb.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    params = cb.Params(IMAGE)
+    stepper = cb.Stepper(params, args.slots, stream_id=rank)
+    electron = params.find_particle(11)
+    ndet = params.num_detectors
+    # Events are sharded by rank: rank r owns global events [r*E, (r+1)*E)
+    prim, offsets = make_events(args.events, args.primaries_per_event, rank * args.events,
+                                electron, cb.PRIMARY_DTYPE)
+    nprim = len(prim)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_pass():
+        stepper.calo_clear()
+        return stepper.run_events(prim, offsets, merge_events=True)
+
+    def reduce_tallies(r):
+        """End-of-run reduction of tallies and counters over NVLink (NCCL)."""
+        calo = torch.from_numpy(stepper.calo()).cuda()
+        counts = torch.tensor([r['num_steps'], r['num_step_iterations'], r['num_primaries']],
+                              dtype=torch.int64, device='cuda')
+        if dist is not None:
+            dist.all_reduce(calo)
+            dist.all_reduce(counts)
+        return calo.cpu().numpy(), counts.cpu().numpy()
+
+    for _ in range(args.warmup):
+        one_pass()
+
+    # ---- timed region 1: e2e through the public C-ABI with HOST buffers
+    launches0 = cb.launch_count()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        total_steps = total_iters = 0
+        dev_secs = 0.0
+        for _ in range(args.steps):
+            r = one_pass()
+            calo, counts = reduce_tallies(r)
+            total_steps += int(counts[0])
+            total_iters += int(counts[1])
+            dev_secs += r['seconds']
+        ev1.record()
+        barrier()
+    launches = cb.launch_count() - launches0
+    e2e_secs = torch.tensor([ev0.elapsed_time(ev1) * 1e-3], device='cuda', dtype=torch.float64)
+    dsecs = torch.tensor([dev_secs], device='cuda', dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(e2e_secs, op=dist.ReduceOp.MAX)
+        dist.all_reduce(dsecs, op=dist.ReduceOp.MAX)
+    e2e_secs = float(e2e_secs.item())
+    dsecs = float(dsecs.item())
+
+    # ---- timed region 2: per-action CUDA-event timing for the roofline of the top kernel
+    stepper.set_action_times(True)
+    before = stepper.action_times
+    r2 = one_pass()
+    after = stepper.action_times
+    stepper.set_action_times(False)
+    per_action = {k: after[k] - before.get(k, 0.0) for k in after}
+    top = max(per_action, key=per_action.get)
+    top_secs = per_action[top]
+    total_action_secs = sum(per_action.values())
+    peak, peak_kind = measured_peak_gbs()
+    achieved = r2['num_steps'] * ALG_BYTES_PER_TRACK_STEP / top_secs / 1e9
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    value = total_steps / dsecs
+    line = {
+        'metric': 'track-steps/sec', 'value': value, 'unit': 'track-steps/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * dsecs / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'TestEm3 full EM (Urban MSC + eloss fluctuations), %d x %d 1 GeV e- '
+                               'primaries per GPU, merged events, %d track slots; steel/lAr '
+                               'stand-in physics (tools/make_physics.py)'
+                               % (args.events, args.primaries_per_event, args.slots),
+                   'l2': 'working set %.0f MB of SoA state per pass exceeds the 126 MB L2'
+                         % (args.slots * 336 / 1e6),
+                   'parallelism': 'events sharded by rank, NCCL all-reduce of tallies'},
+        'events_per_sec': args.events * args.steps * world / dsecs,
+        'num_step_iterations': total_iters,
+        'e2e': {'value': total_steps / e2e_secs, 'unit': 'track-steps/s',
+                'h2d_bytes_per_step': int(nprim * 72 + 12 * nprim),
+                'd2h_bytes_per_step': int(64 * (total_iters // max(args.steps * world, 1))
+                                          + 8 * ndet)},
+        'gpu_launches': int(launches),
+        'clocks': clocks.summary(),
+        'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': achieved, 'peak': peak,
+                     'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                     'peak_kind': peak_kind,
+                     'kernel_share_of_step': top_secs / total_action_secs,
+                     'per_action_seconds': per_action},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        ne, pe = max(2 * cores, 8), 4
+        rc = cpu_reference_run(ne, pe, 4096, cores)
+        line['cpu_baseline'] = {
+            'value': rc['num_steps'] / rc['seconds'], 'unit': 'track-steps/s', 'cores': cores,
+            'kind': 'reference',
+            'sample': '%d events x %d primaries of 1 GeV e-, reference host Stepper '
+                      '(oracle/_ref), one per OpenMP thread, 4096 slots each' % (ne, pe)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -176,10 +176,60 @@ ActionSequence::ActionSequence(CoreParams const& params)
     });
 }
 
-void ActionSequence::step(CoreParams const& params, CoreState& state) const
+ActionSequence::~ActionSequence()
 {
-    for (auto const& a : actions_)
-        a->step(params, state);
+    for (auto& p : pending_)
+    {
+        cudaEventDestroy(p.start);
+        cudaEventDestroy(p.stop);
+    }
+    for (auto e : pool_)
+        cudaEventDestroy(e);
+}
+
+void ActionSequence::step(CoreParams const& params, CoreState& state)
+{
+    if (!action_times_)
+    {
+        for (auto const& a : actions_)
+            a->step(params, state);
+        return;
+    }
+    auto get_event = [this] {
+        cudaEvent_t e;
+        if (!pool_.empty())
+        {
+            e = pool_.back();
+            pool_.pop_back();
+        }
+        else
+        {
+            B2_CUDA_CALL(cudaEventCreate(&e));
+        }
+        return e;
+    };
+    for (uint32_t i = 0; i < actions_.size(); ++i)
+    {
+        Pending p{i, get_event(), get_event()};
+        B2_CUDA_CALL(cudaEventRecord(p.start, state.stream()));
+        actions_[i]->step(params, state);
+        B2_CUDA_CALL(cudaEventRecord(p.stop, state.stream()));
+        pending_.push_back(p);
+    }
+}
+
+void ActionSequence::collect_times()
+{
+    accum_time_.resize(actions_.size(), 0.0);
+    for (auto& p : pending_)
+    {
+        float ms = 0;
+        B2_CUDA_CALL(cudaEventElapsedTime(&ms, p.start, p.stop));
+        accum_time_[p.action] += ms * 1e-3;
+        pool_.push_back(p.start);
+        pool_.push_back(p.stop);
+    }
+    pending_.clear();
 }
 
 //---------------------------------------------------------------------------//
@@ -267,6 +317,7 @@ StepperResult Stepper::operator()()
 {
     this->step_async();
     CoreStateCounters c = state_->sync_counters();
+    actions_->collect_times();
     if (uint32_t err = state_->last_device_error())
     {
         if (err == B200_ERR_INITIALIZER_CAPACITY)

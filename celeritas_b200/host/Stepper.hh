@@ -64,11 +64,29 @@ class ActionSequence
     using SPAction = std::shared_ptr<StepActionInterface const>;
     //! Build the B200 adapters for every step action in the problem's table
     explicit ActionSequence(CoreParams const& params);
-    void step(CoreParams const& params, CoreState& state) const;
+    ~ActionSequence();
+    void step(CoreParams const& params, CoreState& state);
     std::vector<SPAction> const& actions() const { return actions_; }
+
+    //! Per-action device timing with CUDA events on the state's stream
+    //! (reference option: StepperInput::action_times, ActionSequence.cc:99-121)
+    void action_times(bool enable) { action_times_ = enable; }
+    //! Fold finished event pairs into the accumulators (stream must be idle)
+    void collect_times();
+    //! Accumulated device seconds per action since construction
+    std::vector<double> const& accum_time() const { return accum_time_; }
 
   private:
     std::vector<SPAction> actions_;
+    bool action_times_{false};
+    std::vector<double> accum_time_;
+    struct Pending
+    {
+        uint32_t action;
+        cudaEvent_t start, stop;
+    };
+    std::vector<Pending> pending_;
+    std::vector<cudaEvent_t> pool_;
 };
 
 struct StepperResult
@@ -100,6 +118,7 @@ class Stepper
     void reseed(uint64_t event_id);
 
     ActionSequence const& actions() const { return *actions_; }
+    ActionSequence& action_sequence() { return *actions_; }
     CoreState& state() { return *state_; }
     CoreParams const& params() const { return *params_; }
 

@@ -246,6 +246,22 @@ char const* b200_stepper_step_action_label(B200Stepper const* stepper, uint32_t 
     return i < a.size() ? a[i]->label().c_str() : "";
 }
 
+int b200_set_device(int device)
+{
+    return guarded([&] { B2_CUDA_CALL(cudaSetDevice(device)); });
+}
+
+int b200_stepper_set_action_times(B200Stepper* stepper, int enable)
+{
+    return guarded([&] { stepper->stepper->action_sequence().action_times(enable != 0); });
+}
+
+double b200_stepper_action_time(B200Stepper const* stepper, uint32_t i)
+{
+    auto const& t = stepper->stepper->actions().accum_time();
+    return i < t.size() ? t[i] : 0.0;
+}
+
 uint64_t b200_stepper_launch_count(B200Stepper const* stepper)
 {
     return b200_launch_count() - stepper->launches_at_create;

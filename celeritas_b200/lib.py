@@ -48,6 +48,7 @@ EXPORTS = [
     'b200_stepper_state', 'b200_stepper_step', 'b200_stepper_warm_up', 'b200_stepper_reseed',
     'b200_stepper_kill_active', 'b200_stepper_num_step_actions',
     'b200_stepper_step_action_label', 'b200_stepper_launch_count', 'b200_run_events',
+    'b200_stepper_set_action_times', 'b200_stepper_action_time', 'b200_set_device',
 ]
 
 _lib = None
@@ -108,6 +109,10 @@ def load_library():
     L.b200_stepper_step_action_label.restype = C.c_char_p
     L.b200_stepper_launch_count.argtypes = [vp]
     L.b200_stepper_launch_count.restype = C.c_uint64
+    L.b200_stepper_set_action_times.argtypes = [vp, C.c_int]
+    L.b200_stepper_action_time.argtypes = [vp, C.c_uint32]
+    L.b200_stepper_action_time.restype = C.c_double
+    L.b200_set_device.argtypes = [C.c_int]
     L.b200_run_events.argtypes = [vp, vp, vp, C.c_uint32, C.c_int, C.c_uint64,
                                   C.POINTER(RunResult)]
     _lib = L
@@ -122,6 +127,10 @@ def _check(rc):
 
 def device_count():
     return load_library().b200_device_count()
+
+
+def set_device(device):
+    _check(load_library().b200_set_device(device))
 
 
 def launch_count():
@@ -219,6 +228,16 @@ class Stepper:
         L = load_library()
         return [L.b200_stepper_step_action_label(self.h, i).decode()
                 for i in range(L.b200_stepper_num_step_actions(self.h))]
+
+    def set_action_times(self, enable=True):
+        _check(load_library().b200_stepper_set_action_times(self.h, int(enable)))
+
+    @property
+    def action_times(self):
+        """Accumulated device seconds per step action (label -> seconds)."""
+        L = load_library()
+        return {lab: L.b200_stepper_action_time(self.h, i)
+                for i, lab in enumerate(self.step_action_labels)}
 
     @property
     def launch_count(self):

@@ -19,7 +19,7 @@
  *     AlongStep{Neutral,GeneralLinear,UniformMsc}Action                        | b200_step_along_step
  *       (global/alongstep/AlongStep.hh:50-58)                                  |
  *     DiscreteSelectAction (phys/detail/DiscreteSelectExecutor.hh:37-63)       | b200_step_discrete_select
- *     *Model::step (em/model/*Model.cu via InteractionApplier)                 | b200_step_interact
+ *     every EM model's step() (em/model/XModel.cu via InteractionApplier)      | b200_step_interact
  *     BoundaryAction (geo/detail/BoundaryExecutor.hh:41-84)                    | b200_step_boundary
  *     TrackingCutAction (phys/detail/TrackingCutExecutor.hh:48-83)             | b200_step_tracking_cut
  *     StepGather/SimpleCalo (user/detail/SimpleCaloExecutor.hh:48-67)          | b200_step_tally
@@ -165,6 +165,12 @@ int b200_stepper_reseed(B200Stepper* stepper, uint64_t event_id);
 int b200_stepper_kill_active(B200Stepper* stepper);
 uint32_t b200_stepper_num_step_actions(B200Stepper const* stepper);
 char const* b200_stepper_step_action_label(B200Stepper const* stepper, uint32_t i);
+/* Per-action device timing with CUDA events on the stepper's stream (reference:
+ * StepperInput::action_times, celeritas/global/ActionSequence.cc:99-121). */
+int b200_stepper_set_action_times(B200Stepper* stepper, int enable);
+double b200_stepper_action_time(B200Stepper const* stepper, uint32_t i); /* seconds */
+/* Select the CUDA device for objects created afterwards by this thread. */
+int b200_set_device(int device);
 /* Kernel launches issued by this stepper so far */
 uint64_t b200_stepper_launch_count(B200Stepper const* stepper);
 
