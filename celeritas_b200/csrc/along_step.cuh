@@ -9,6 +9,7 @@
 //---------------------------------------------------------------------------//
 #pragma once
 
+#include "field.cuh"
 #include "interact.cuh"
 #include "orange.cuh"
 #include "physics.cuh"
@@ -936,9 +937,38 @@ B2_D Propagation propagate_linear(GeoTrack& geo, real dist)
 }
 
 //! Apply the propagation result to the step (detail/PropagationApplier.hh:93-192)
-B2_D void apply_propagation(ParamsView const& p, StateView const& s, u32 slot, Propagation const& pr)
+B2_D void apply_propagation(ParamsView const& p,
+                            StateView const& s,
+                            u32 slot,
+                            Propagation const& pr,
+                            bool tracks_can_loop,
+                            Particle const& particle)
 {
-    if (pr.boundary)
+    if (tracks_can_loop)
+    {
+        // SimTrackView::update_looping
+        if (pr.looping)
+            s.num_looping_steps[slot] += 1;
+        else
+            s.num_looping_steps[slot] = 0;
+    }
+    if (tracks_can_loop && pr.looping)
+    {
+        s.step_length[slot] = pr.distance;
+        bool abandon = false;
+        if (p.particle.decay_constant[particle.id] == 0)
+        {
+            // SimTrackView::is_looping
+            u32 nloop = s.num_looping_steps[slot];
+            if (particle.energy < p.sim.looping_energy[particle.id])
+                abandon = nloop >= p.sim.looping_steps[2 * particle.id];
+            else
+                abandon = nloop >= p.sim.looping_steps[2 * particle.id + 1];
+        }
+        s.post_step_action[slot] = abandon ? p.scalars.tracking_cut_action
+                                           : p.scalars.propagation_limit_action;
+    }
+    else if (pr.boundary)
     {
         s.step_length[slot] = pr.distance;
         s.post_step_action[slot] = p.scalars.boundary_action;
@@ -1000,8 +1030,10 @@ B2_D void along_step(ParamsView const& p, StateView const& s, u32 slot)
     // propagation
     if (s.step_length[slot] != 0)
     {
-        Propagation pr = propagate_linear(geo, s.step_length[slot]);
-        apply_propagation(p, s, slot, pr);
+        bool const use_field = charged && p.model.field.enabled;
+        Propagation pr = use_field ? propagate_field(p, particle, geo, s.step_length[slot])
+                                   : propagate_linear(geo, s.step_length[slot]);
+        apply_propagation(p, s, slot, pr, use_field, particle);
     }
     if (charged)
     {

@@ -353,6 +353,27 @@ struct FluctuationParams
     real const* urban;
 };
 
+//! Uniform magnetic field + driver options (field/FieldDriverOptions.hh:26-93)
+struct FieldParams
+{
+    u32 enabled;
+    u32 max_nsteps;
+    u32 max_substeps;
+    real field[3];            // native units (gauss)
+    real coeffi_per_charge;   // e / (MeV/c) in native units: dp/ds = coeffi * q * (p x B) / |p|
+    real minimum_step;
+    real delta_chord;
+    real delta_intersection;
+    real epsilon_step;
+    real epsilon_rel_max;
+    real errcon;
+    real pgrow;
+    real pshrink;
+    real safety;
+    real max_stepping_increase;
+    real max_stepping_decrease;
+};
+
 struct PhysConstants
 {
     real migdal_constant;
@@ -372,6 +393,7 @@ struct ModelParams
     LivermorePEParams pe;
     UrbanMscParams msc;
     FluctuationParams fluct;
+    FieldParams field;
     PhysConstants constants;
 };
 

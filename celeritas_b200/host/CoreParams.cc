@@ -346,6 +346,30 @@ void CoreParams::load(Image const& img)
             m.fluct.electron_mass = img.get_scalar<double>("fluct.electron_mass");
             m.fluct.urban = F64("fluct.urban");
         }
+        m.field.enabled = 0;
+        if (img.has("field.uniform"))
+        {
+            auto f = img.get<double>("field.uniform");
+            auto o = img.get<double>("field.options");
+            auto u = img.get<uint32_t>("field.options_u32");
+            m.field.enabled = 1;
+            for (int i = 0; i < 3; ++i)
+                m.field.field[i] = f.at(i);
+            m.field.minimum_step = o.at(0);
+            m.field.delta_chord = o.at(1);
+            m.field.delta_intersection = o.at(2);
+            m.field.epsilon_step = o.at(3);
+            m.field.epsilon_rel_max = o.at(4);
+            m.field.errcon = o.at(5);
+            m.field.pgrow = o.at(6);
+            m.field.pshrink = o.at(7);
+            m.field.safety = o.at(8);
+            m.field.max_stepping_increase = o.at(9);
+            m.field.max_stepping_decrease = o.at(10);
+            m.field.coeffi_per_charge = o.at(11);
+            m.field.max_nsteps = u.at(0);
+            m.field.max_substeps = u.at(1);
+        }
         auto c = img.get<double>("constants");
         m.constants.migdal_constant = c.at(0);
         m.constants.lpm_constant = c.at(1);

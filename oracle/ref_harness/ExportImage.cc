@@ -732,7 +732,9 @@ void export_models(Problem const& prob, b200::Image& img)
                     o.pshrink,
                     o.safety,
                     o.max_stepping_increase,
-                    o.max_stepping_decrease});
+                    o.max_stepping_decrease,
+                    native_value_from(units::ElementaryCharge{1})
+                        / native_value_from(units::MevMomentum{1})});
         img.put("field.options_u32", U32{static_cast<uint32_t>(o.max_nsteps), static_cast<uint32_t>(o.max_substeps)});
     }
     // Physical constants as the reference computes them

@@ -30,6 +30,24 @@ PROBLEMS = {
                 'physics_file': 'data/physics/testem3-steel-lar.json',
                 'seed': 20220904, 'initializer_capacity': 1 << 25, 'max_events': 16384,
                 'simple_calo': GAPS + ABSORBERS},
+    # BASELINE config 2: simple-CMS nested cylinders in a 1 T uniform field (the reference's
+    # bundled simple-cms export: Compton + e-/e+ ionisation + Urban MSC, no fluctuations)
+    'simple-cms-field': {'geometry_file': 'data/geometry/simple-cms.org.json',
+                         'physics_file': 'data/physics/simple-cms.json',
+                         'seed': 20220904, 'initializer_capacity': 1 << 20, 'max_events': 1024,
+                         'field': [0, 0, 1],
+                         'simple_calo': ['si_tracker', 'em_calorimeter', 'had_calorimeter',
+                                         'sc_solenoid', 'fe_muon_chambers']},
+    'simple-cms': {'geometry_file': 'data/geometry/simple-cms.org.json',
+                   'physics_file': 'data/physics/simple-cms.json',
+                   'seed': 20220904, 'initializer_capacity': 1 << 20, 'max_events': 1024},
+    # same geometry and field with the full-EM stand-in materials (10 GeV showers)
+    'simple-cms-em-field': {'geometry_file': 'data/geometry/simple-cms.org.json',
+                            'physics_file': 'data/physics/simple-cms-steel-lar.json',
+                            'seed': 20220904, 'initializer_capacity': 1 << 25,
+                            'max_events': 16384, 'field': [0, 0, 1],
+                            'simple_calo': ['si_tracker', 'em_calorimeter', 'had_calorimeter',
+                                            'sc_solenoid', 'fe_muon_chambers']},
     # small-capacity variant of the same physics for lock-step tests
     'testem3-small': {'geometry_file': 'data/geometry/testem3-flat.org.json',
                       'physics_file': 'data/physics/testem3-steel-lar.json',

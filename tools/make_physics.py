@@ -197,6 +197,17 @@ def main():
           [e['name'] for e in em3['elements']],
           [(p['particle_pdg'], p['process_class']) for p in em3['processes']])
 
+    # simple-CMS geometry (data/geometry/simple-cms.org.json) with full-EM stand-in materials:
+    # the bundled simple-cms.root has only Compton + ionisation + MSC below 1 GeV, which
+    # cannot stop a 10 GeV shower. Tracker -> lAr, calorimeters/solenoid/muon iron -> steel.
+    cms_vols = [('vacuum_tube', 0), ('si_tracker', 2), ('em_calorimeter', 1),
+                ('had_calorimeter', 1), ('sc_solenoid', 1), ('fe_muon_chambers', 1),
+                ('world', 0)]
+    cms = merge([(steel, 'G4_Galactic'), (steel, 'G4_STAINLESS-STEEL'), (lar, 'lAr')], cms_vols)
+    add_element_data(cms)
+    json.dump(cms, open(os.path.join(PHYS, 'simple-cms-steel-lar.json'), 'w'),
+              separators=(',', ':'))
+
     # lar-sphere as bundled (geometry data/geometry/lar-sphere.org.json): volumes keep names
     lar_full = load('lar-sphere')
     filter_physics(lar_full)
