@@ -1005,13 +1005,15 @@ B2_D void update_track(ParamsView const& p, StateView const& s, u32 slot)
     s.num_steps[slot] += 1;
 }
 
-//! Whole along-step for one alive track
+//! Whole along-step for one alive track. CHARGED is a compile-time property of the
+//! launch (dense per-charge slot lists), so the neutral kernel carries no msc/eloss code.
+template<bool CHARGED>
 B2_D void along_step(ParamsView const& p, StateView const& s, u32 slot)
 {
     Particle particle = load_particle(p, s, slot);
     GeoTrack geo(p, s, slot);
     PhysTrack phys(p, particle.id, s.material_id[slot]);
-    bool const charged = particle.charge != 0;
+    constexpr bool charged = CHARGED;
 
     // msc step limit
     bool use_msc = false;

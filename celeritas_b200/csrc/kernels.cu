@@ -2,9 +2,21 @@
 // Step-action kernels and their C-ABI launchers.
 //
 // One kernel per step action of the reference's loop
-// (/root/reference/src/celeritas/global/ActionSequence.cc:77-138),
-// each over all track slots with per-slot predicates, all counters resident in
-// device memory so that a step iteration needs no host round trip.
+// (/root/reference/src/celeritas/global/ActionSequence.cc:77-138).
+//
+// B200-specific structure:
+//  * All counters (CoreStateCounters) are resident in device memory: kernels size
+//    themselves from them, the host only reads them back once per iteration.
+//  * Per-step kernels do not run over all track slots. The end-of-step pass builds
+//    DENSE lists of active slots, charged tracks from the front of `track_slots`,
+//    neutral tracks from the back; thread i of a kernel works on the i-th active
+//    slot. Warps are therefore fully populated and charge-coherent, which is what
+//    the reference's TrackOrder::init_charge / SortTracksAction aim for
+//    (/root/reference/src/celeritas/track/SortTracksAction.cc:46-131) without a
+//    radix sort: the lists fall out of the block scans that the vacancy compaction
+//    needs anyway.
+//  * Results are per-slot deterministic: thread->slot mapping never changes what a
+//    slot computes (RNG state, physics and geometry are all per slot).
 //---------------------------------------------------------------------------//
 #include <atomic>
 #include <cstdio>
@@ -21,9 +33,21 @@ namespace b200
 {
 constexpr int BLOCK = 128;
 
-B2_D u32 thread_slot()
+B2_D u32 thread_id()
 {
     return blockIdx.x * blockDim.x + threadIdx.x;
+}
+
+//! i-th active slot: charged from the front, neutral from the back
+B2_D u32 active_slot(StateView const& s, u32 tid)
+{
+    u32 const nc = s.counters[CTR_NUM_CHARGED];
+    if (tid < nc)
+        return s.track_slots[tid];
+    tid -= nc;
+    if (tid < s.counters[CTR_NUM_NEUTRAL])
+        return s.track_slots[s.num_slots - 1 - tid];
+    return INVALID;
 }
 
 //---------------------------------------------------------------------------//
@@ -35,7 +59,7 @@ __global__ void k_extend_from_primaries(StateView s,
                                         u32 const* __restrict__ rank_in_event,
                                         u32 n)
 {
-    u32 tid = thread_slot();
+    u32 tid = thread_id();
     if (tid >= n)
         return;
     // counters[NUM_INITIALIZERS] has not yet been incremented
@@ -52,6 +76,7 @@ __global__ void k_extend_from_primaries(StateView s,
     s.ti_time[idx] = pr.time;
     s.ti_particle_id[idx] = pr.particle_id;
     s.ti_energy[idx] = pr.energy;
+    s.ti_level[idx] = INVALID;
     for (int k = 0; k < 3; ++k)
     {
         s.ti_pos[k * s.init_capacity + idx] = pr.pos[k];
@@ -65,7 +90,7 @@ __global__ void k_primaries_finalize(StateView s,
                                      u32 num_events,
                                      u32 n)
 {
-    u32 tid = thread_slot();
+    u32 tid = thread_id();
     if (tid < num_events)
         s.track_counters[event_ids[tid]] += event_counts[tid];
     if (tid == 0)
@@ -79,9 +104,9 @@ __global__ void k_primaries_finalize(StateView s,
 // start: initialize tracks in vacant slots
 // (track/detail/InitTracksExecutor.hh:71-175)
 //---------------------------------------------------------------------------//
-__global__ void k_initialize_tracks(ParamsView const p, StateView s)
+__global__ void __launch_bounds__(BLOCK) k_initialize_tracks(ParamsView const p, StateView s)
 {
-    u32 tid = thread_slot();
+    u32 tid = thread_id();
     u32 const num_init = s.counters[CTR_NUM_INITIALIZERS];
     u32 const num_vac = s.counters[CTR_NUM_VACANCIES];
     u32 const num_new = num_init < num_vac ? num_init : num_vac;
@@ -102,8 +127,20 @@ __global__ void k_initialize_tracks(ParamsView const p, StateView s)
     s.post_step_action[slot] = INVALID;
     s.along_step_action[slot] = INVALID;
     // particle
-    s.particle_id[slot] = s.ti_particle_id[ti];
+    u32 const pid = s.ti_particle_id[ti];
+    s.particle_id[slot] = pid;
     s.energy[slot] = s.ti_energy[ti];
+    // append to the dense active lists
+    if (p.particle.charge[pid] != 0)
+    {
+        u32 pos = atomicAdd(&s.counters[CTR_NUM_CHARGED], 1u);
+        s.track_slots[pos] = slot;
+    }
+    else
+    {
+        u32 pos = atomicAdd(&s.counters[CTR_NUM_NEUTRAL], 1u);
+        s.track_slots[s.num_slots - 1 - pos] = slot;
+    }
     // geometry
     Real3 pos, dir;
     for (int k = 0; k < 3; ++k)
@@ -112,7 +149,16 @@ __global__ void k_initialize_tracks(ParamsView const p, StateView s)
         dir[k] = s.ti_dir[k * s.init_capacity + ti];
     }
     GeoTrack geo(p, s, slot);
-    geo.initialize(pos, dir);
+    u32 const known_level = s.ti_level[ti];
+    if (known_level != INVALID)
+    {
+        geo.initialize_known(
+            pos, dir, known_level, s.ti_vol + ti, s.ti_univ + ti, s.init_capacity);
+    }
+    else
+    {
+        geo.initialize(pos, dir);
+    }
     bool errored = geo.failed || geo.is_outside();
     u32 matid = INVALID;
     if (!errored)
@@ -145,24 +191,20 @@ __global__ void k_initialize_finalize(StateView s)
     s.counters[CTR_NUM_VACANCIES] = num_vac - num_new;
     s.counters[CTR_NUM_ACTIVE] = s.num_slots - (num_vac - num_new);
     s.counters[CTR_NUM_NEW_TRACKS] = num_new;
+    // whole-run tallies kept on the device: track-steps and step iterations
+    s.step_counters[0] += s.num_slots - (num_vac - num_new);
+    s.step_counters[1] += 1;
 }
 
 //---------------------------------------------------------------------------//
 // pre: physics step limits (phys/detail/PreStepExecutor.hh:45-115)
 //---------------------------------------------------------------------------//
-__global__ void k_pre_step(ParamsView const p, StateView s)
+__global__ void __launch_bounds__(BLOCK) k_pre_step(ParamsView const p, StateView s)
 {
-    u32 slot = thread_slot();
-    if (slot >= s.num_slots)
+    u32 slot = active_slot(s, thread_id());
+    if (slot == INVALID)
         return;
     u8 status = s.status[slot];
-    if (status == ST_INACTIVE)
-    {
-        s.step_length[slot] = real_inf();
-        s.post_step_action[slot] = INVALID;
-        s.along_step_action[slot] = INVALID;
-        return;
-    }
     s.energy_deposition[slot] = 0;
     for (int i = 0; i < MAX_SECONDARIES; ++i)
         s.sec_particle[i * s.num_slots + slot] = INVALID;
@@ -194,26 +236,37 @@ __global__ void k_pre_step(ParamsView const p, StateView s)
 }
 
 //---------------------------------------------------------------------------//
-// along-step
+// along-step: one launch per charge class over its dense list
 //---------------------------------------------------------------------------//
-__global__ void k_along_step(ParamsView const p, StateView s)
+__global__ void __launch_bounds__(BLOCK) k_along_step_charged(ParamsView const p, StateView s)
 {
-    u32 slot = thread_slot();
-    if (slot >= s.num_slots)
+    u32 tid = thread_id();
+    if (tid >= s.counters[CTR_NUM_CHARGED])
         return;
+    u32 slot = s.track_slots[tid];
     if (s.status[slot] != ST_ALIVE)
         return;
-    along_step(p, s, slot);
+    along_step<true>(p, s, slot);
+}
+
+__global__ void __launch_bounds__(BLOCK) k_along_step_neutral(ParamsView const p, StateView s)
+{
+    u32 tid = thread_id();
+    if (tid >= s.counters[CTR_NUM_NEUTRAL])
+        return;
+    u32 slot = s.track_slots[s.num_slots - 1 - tid];
+    if (s.status[slot] != ST_ALIVE)
+        return;
+    along_step<false>(p, s, slot);
 }
 
 //---------------------------------------------------------------------------//
 // pre-post: discrete select (phys/detail/DiscreteSelectExecutor.hh:37-63)
-// post: interaction / boundary / tracking cut, fused by post-step action id
 //---------------------------------------------------------------------------//
-__global__ void k_discrete_select(ParamsView const p, StateView s)
+__global__ void __launch_bounds__(BLOCK) k_discrete_select(ParamsView const p, StateView s)
 {
-    u32 slot = thread_slot();
-    if (slot >= s.num_slots)
+    u32 slot = active_slot(s, thread_id());
+    if (slot == INVALID)
         return;
     if (s.status[slot] != ST_ALIVE)
         return;
@@ -229,10 +282,13 @@ __global__ void k_discrete_select(ParamsView const p, StateView s)
     s.post_step_action[slot] = action;
 }
 
-__global__ void k_interact(ParamsView const p, StateView s)
+//---------------------------------------------------------------------------//
+// post: every EM model (dispatch on the selected action id)
+//---------------------------------------------------------------------------//
+__global__ void __launch_bounds__(BLOCK) k_interact(ParamsView const p, StateView s)
 {
-    u32 slot = thread_slot();
-    if (slot >= s.num_slots)
+    u32 slot = active_slot(s, thread_id());
+    if (slot == INVALID)
         return;
     if (s.status[slot] != ST_ALIVE)
         return;
@@ -246,10 +302,10 @@ __global__ void k_interact(ParamsView const p, StateView s)
 }
 
 // (geo/detail/BoundaryExecutor.hh:41-84)
-__global__ void k_boundary(ParamsView const p, StateView s)
+__global__ void __launch_bounds__(BLOCK) k_boundary(ParamsView const p, StateView s)
 {
-    u32 slot = thread_slot();
-    if (slot >= s.num_slots)
+    u32 slot = active_slot(s, thread_id());
+    if (slot == INVALID)
         return;
     if (s.status[slot] != ST_ALIVE || s.post_step_action[slot] != p.scalars.boundary_action)
         return;
@@ -277,10 +333,10 @@ __global__ void k_boundary(ParamsView const p, StateView s)
 }
 
 // (phys/detail/TrackingCutExecutor.hh:48-83)
-__global__ void k_tracking_cut(ParamsView const p, StateView s)
+__global__ void __launch_bounds__(BLOCK) k_tracking_cut(ParamsView const p, StateView s)
 {
-    u32 slot = thread_slot();
-    if (slot >= s.num_slots)
+    u32 slot = active_slot(s, thread_id());
+    if (slot == INVALID)
         return;
     u8 status = s.status[slot];
     if (status == ST_INACTIVE || status == ST_KILLED)
@@ -296,14 +352,11 @@ __global__ void k_tracking_cut(ParamsView const p, StateView s)
     s.status[slot] = ST_KILLED;
 }
 
-//---------------------------------------------------------------------------//
-// user_post: tallies (user/detail/SimpleCaloExecutor.hh:48-67,
-// app/celer-sim/Transporter.cc:109-111)
-//---------------------------------------------------------------------------//
-__global__ void k_tally(ParamsView const p, StateView s)
+// user_post: tallies (user/detail/SimpleCaloExecutor.hh:48-67)
+__global__ void __launch_bounds__(BLOCK) k_tally(ParamsView const p, StateView s)
 {
-    u32 slot = thread_slot();
-    if (slot >= s.num_slots)
+    u32 slot = active_slot(s, thread_id());
+    if (slot == INVALID)
         return;
     if (s.status[slot] == ST_INACTIVE)
         return;
@@ -320,28 +373,29 @@ __global__ void k_tally(ParamsView const p, StateView s)
 }
 
 //---------------------------------------------------------------------------//
-// end: secondaries -> initializers, vacancy compaction
+// end: secondaries -> initializers, vacancy compaction, dense active lists
 // (track/detail/LocateAliveExecutor.hh:60-106,
 //  track/detail/ProcessSecondariesExecutor.hh:69-183,
 //  track/detail/TrackInitAlgorithms.cu:34-78)
 //
-// Pass 1 (per block): alive flags and secondary counts, block-level exclusive
-//   scans, block totals to scratch.
+// Pass 1 (per block): classify each slot, block-level exclusive scans of five
+//   quantities packed into two words, block totals to scratch.
 // Pass 2 (one block): scan of block totals -> block offsets, global counters.
-// Pass 3 (per block): write compacted vacancies and track initializers.
+// Pass 3 (per block): write compacted vacancies, track initializers and the
+//   dense charged/neutral lists of the slots that stay active.
 //---------------------------------------------------------------------------//
-template<int B>
-B2_D u32 block_exclusive_scan(u32 value, u32* total)
+template<int B, class T>
+B2_D T block_exclusive_scan(T value, T* total)
 {
-    __shared__ u32 warp_sums[B / 32];
-    __shared__ u32 block_total;
+    __shared__ T warp_sums[B / 32];
+    __shared__ T block_total;
     u32 lane = threadIdx.x & 31;
     u32 warp = threadIdx.x >> 5;
-    u32 incl = value;
+    T incl = value;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1)
     {
-        u32 n = __shfl_up_sync(0xffffffffu, incl, off);
+        T n = __shfl_up_sync(0xffffffffu, incl, off);
         if (lane >= off)
             incl += n;
     }
@@ -350,12 +404,12 @@ B2_D u32 block_exclusive_scan(u32 value, u32* total)
     __syncthreads();
     if (warp == 0)
     {
-        u32 w = lane < B / 32 ? warp_sums[lane] : 0;
-        u32 wi = w;
+        T w = lane < B / 32 ? warp_sums[lane] : T(0);
+        T wi = w;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1)
         {
-            u32 n = __shfl_up_sync(0xffffffffu, wi, off);
+            T n = __shfl_up_sync(0xffffffffu, wi, off);
             if (lane >= off)
                 wi += n;
         }
@@ -365,7 +419,7 @@ B2_D u32 block_exclusive_scan(u32 value, u32* total)
             block_total = wi;
     }
     __syncthreads();
-    u32 result = warp_sums[warp] + incl - value;
+    T result = warp_sums[warp] + incl - value;
     *total = block_total;
     __syncthreads();
     return result;
@@ -374,51 +428,76 @@ B2_D u32 block_exclusive_scan(u32 value, u32* total)
 struct SlotEnd
 {
     u32 is_vacant;
-    u32 num_sec;
+    u32 num_sec;      // secondaries that become initializers
+    u32 num_sec_all;  // including one that reuses the slot in place
+    u32 charged;      // stays active with a charged particle
+    u32 neutral;      // stays active with a neutral particle
     bool reuse_slot;  // first secondary replaces a dead parent in place
 };
 
 B2_D SlotEnd classify_slot(ParamsView const& p, StateView const& s, u32 slot)
 {
-    SlotEnd r{0, 0, false};
+    SlotEnd r{0, 0, 0, 0, 0, false};
     if (slot >= s.num_slots)
         return r;
     u8 status = s.status[slot];
+    u32 first_sec = INVALID;
     if (status != ST_INACTIVE)
     {
-        for (int i = 0; i < MAX_SECONDARIES; ++i)
-            r.num_sec += (s.sec_particle[i * s.num_slots + slot] != INVALID);
+        for (int i = MAX_SECONDARIES - 1; i >= 0; --i)
+        {
+            u32 sp = s.sec_particle[i * s.num_slots + slot];
+            if (sp != INVALID)
+            {
+                ++r.num_sec;
+                first_sec = sp;
+            }
+        }
     }
+    r.num_sec_all = r.num_sec;
+    u32 active_particle = INVALID;
     if (status == ST_ALIVE)
     {
-        r.is_vacant = 0;
+        active_particle = s.particle_id[slot];
     }
     else if (r.num_sec > 0 && p.scalars.track_order != ORDER_INIT_CHARGE)
     {
         --r.num_sec;
         r.reuse_slot = true;
-        r.is_vacant = 0;
+        active_particle = first_sec;
     }
     else
     {
         r.is_vacant = 1;
     }
+    if (active_particle != INVALID)
+    {
+        bool charged = p.particle.charge[active_particle] != 0;
+        r.charged = charged;
+        r.neutral = !charged;
+    }
     return r;
 }
 
-__global__ void k_end_pass1(ParamsView const p, StateView s)
+// Packed scan words: A = vacant | charged << 10 | neutral << 20 (each <= BLOCK),
+//                    B = num_sec | num_sec_all << 16 (each <= 2 * BLOCK)
+static_assert(BLOCK <= 512 && MAX_SECONDARIES * BLOCK < 65536, "packed scan field widths");
+
+__global__ void __launch_bounds__(BLOCK) k_end_pass1(ParamsView const p, StateView s)
 {
-    u32 slot = thread_slot();
+    u32 slot = thread_id();
     SlotEnd e = classify_slot(p, s, slot);
-    u32 tv, ts, ta;
-    block_exclusive_scan<BLOCK>(e.is_vacant, &tv);
-    block_exclusive_scan<BLOCK>(e.num_sec, &ts);
-    block_exclusive_scan<BLOCK>(e.num_sec + (e.reuse_slot ? 1u : 0u), &ta);
+    u32 ta, tb;
+    block_exclusive_scan<BLOCK, u32>(e.is_vacant | (e.charged << 10) | (e.neutral << 20), &ta);
+    block_exclusive_scan<BLOCK, u32>(e.num_sec | (e.num_sec_all << 16), &tb);
     if (threadIdx.x == 0)
     {
-        s.block_scratch[blockIdx.x] = tv;
-        s.block_scratch[gridDim.x + blockIdx.x] = ts;
-        s.block_scratch[2 * gridDim.x + blockIdx.x] = ta;
+        u32 const nb = gridDim.x;
+        s.block_scratch[blockIdx.x] = ta & 0x3ffu;
+        s.block_scratch[nb + blockIdx.x] = (ta >> 10) & 0x3ffu;
+        s.block_scratch[2 * nb + blockIdx.x] = (ta >> 20) & 0x3ffu;
+        s.block_scratch[3 * nb + blockIdx.x] = tb & 0xffffu;
+        s.block_scratch[4 * nb + blockIdx.x] = tb >> 16;
     }
 }
 
@@ -426,22 +505,18 @@ __global__ void k_end_pass2(StateView s, u32 num_blocks)
 {
     // Single block: scan block totals (chunked)
     constexpr int B = 1024;
-    __shared__ u32 carry[3];
-    if (threadIdx.x == 0)
-    {
-        carry[0] = 0;
-        carry[1] = 0;
-        carry[2] = 0;
-    }
+    __shared__ u32 carry[5];
+    if (threadIdx.x < 5)
+        carry[threadIdx.x] = 0;
     __syncthreads();
     for (u32 base = 0; base < num_blocks; base += B)
     {
         u32 i = base + threadIdx.x;
-        for (int a = 0; a < 3; ++a)
+        for (int a = 0; a < 5; ++a)
         {
             u32 v = i < num_blocks ? s.block_scratch[a * num_blocks + i] : 0;
             u32 total;
-            u32 ex = block_exclusive_scan<B>(v, &total);
+            u32 ex = block_exclusive_scan<B, u32>(v, &total);
             if (i < num_blocks)
                 s.block_scratch[a * num_blocks + i] = ex + carry[a];
             __syncthreads();
@@ -453,8 +528,10 @@ __global__ void k_end_pass2(StateView s, u32 num_blocks)
     if (threadIdx.x == 0)
     {
         u32 num_vac = carry[0];
-        u32 num_sec = carry[1];
+        u32 num_sec = carry[3];
         s.counters[CTR_NUM_VACANCIES] = num_vac;
+        s.counters[CTR_NUM_CHARGED] = carry[1];
+        s.counters[CTR_NUM_NEUTRAL] = carry[2];
         s.counters[CTR_NUM_SECONDARIES] = num_sec;
         u32 num_init = s.counters[CTR_NUM_INITIALIZERS] + num_sec;
         s.counters[CTR_NUM_INITIALIZERS] = num_init;
@@ -466,31 +543,50 @@ __global__ void k_end_pass2(StateView s, u32 num_blocks)
         if (s.single_event != INVALID)
         {
             s.counters[CTR_TRACK_ID_BASE] = s.track_counters[s.single_event];
-            s.track_counters[s.single_event] += carry[2];
+            s.track_counters[s.single_event] += carry[4];
         }
     }
 }
 
-__global__ void k_end_pass3(ParamsView const p, StateView s)
+__global__ void __launch_bounds__(BLOCK) k_end_pass3(ParamsView const p, StateView s)
 {
-    u32 slot = thread_slot();
+    u32 slot = thread_id();
     SlotEnd e = classify_slot(p, s, slot);
-    u32 tv, ts, ta;
-    u32 vac_off = block_exclusive_scan<BLOCK>(e.is_vacant, &tv) + s.block_scratch[blockIdx.x];
-    u32 sec_off = block_exclusive_scan<BLOCK>(e.num_sec, &ts)
-                  + s.block_scratch[gridDim.x + blockIdx.x];
-    u32 all_off = block_exclusive_scan<BLOCK>(e.num_sec + (e.reuse_slot ? 1u : 0u), &ta)
-                  + s.block_scratch[2 * gridDim.x + blockIdx.x];
+    u32 ta, tb;
+    u32 const nb = gridDim.x;
+    u32 sa = block_exclusive_scan<BLOCK, u32>(
+        e.is_vacant | (e.charged << 10) | (e.neutral << 20), &ta);
+    u32 sb = block_exclusive_scan<BLOCK, u32>(e.num_sec | (e.num_sec_all << 16), &tb);
+    u32 vac_off = (sa & 0x3ffu) + s.block_scratch[blockIdx.x];
+    u32 chg_off = ((sa >> 10) & 0x3ffu) + s.block_scratch[nb + blockIdx.x];
+    u32 neu_off = ((sa >> 20) & 0x3ffu) + s.block_scratch[2 * nb + blockIdx.x];
+    u32 sec_off = (sb & 0xffffu) + s.block_scratch[3 * nb + blockIdx.x];
+    u32 all_off = (sb >> 16) + s.block_scratch[4 * nb + blockIdx.x];
     if (slot >= s.num_slots)
         return;
     if (s.counters[CTR_ERROR] != 0)
         return;
     if (e.is_vacant)
         s.vacancies[vac_off] = slot;
+    if (e.charged)
+        s.track_slots[chg_off] = slot;
+    if (e.neutral)
+        s.track_slots[s.num_slots - 1 - neu_off] = slot;
 
     u8 status = s.status[slot];
     if (status == ST_INACTIVE)
+    {
+        // The reference's pre-step resets the step limit of inactive slots
+        // (PreStepExecutor.hh:47-57); inactive slots are never visited by the dense
+        // kernels here, so do it once, when the slot is first seen inactive
+        if (s.post_step_action[slot] != INVALID || s.along_step_action[slot] != INVALID)
+        {
+            s.step_length[slot] = real_inf();
+            s.post_step_action[slot] = INVALID;
+            s.along_step_action[slot] = INVALID;
+        }
         return;
+    }
 
     // Initializers created this step occupy [num_init - num_sec, num_init)
     // in slot order (exclusive scan of the per-slot counts)
@@ -499,73 +595,81 @@ __global__ void k_end_pass3(ParamsView const p, StateView s)
     u32 out = num_init - num_sec_total + sec_off;
     bool initialized = false;
     u32 const n = s.num_slots;
-    u32 const event = s.event_id[slot];
-    u32 const parent_track = s.track_id[slot];
-    real const time = s.time[slot];
-    GeoTrack geo(p, s, slot);
-    Real3 const pos = geo.pos();
+    u32 const cap = s.init_capacity;
 
-    // Track ids: per-event counter (reference: atomic_add, detail/Utils.hh:107-116)
-    // (deterministic slot-order ids when a single event is in flight)
-    u32 nsec_here = e.num_sec + (e.reuse_slot ? 1 : 0);
-    u32 id_base;
-    if (s.single_event != INVALID)
-        id_base = s.counters[CTR_TRACK_ID_BASE] + all_off;
-    else
-        id_base = nsec_here ? atomicAdd(&s.track_counters[event], nsec_here) : 0;
-
-    for (int i = 0; i < MAX_SECONDARIES; ++i)
+    if (e.num_sec_all > 0)
     {
-        u32 spid = s.sec_particle[i * n + slot];
-        if (spid == INVALID)
-            continue;
-        real senergy = s.sec_energy[i * n + slot];
-        Real3 sdir = make_real3(s.sec_dir[(i * 3 + 0) * n + slot],
-                                s.sec_dir[(i * 3 + 1) * n + slot],
-                                s.sec_dir[(i * 3 + 2) * n + slot]);
-        u32 new_id = id_base++;
-        if (!initialized && e.reuse_slot)
-        {
-            // The first secondary takes over the dead parent's slot
-            s.track_id[slot] = new_id;
-            s.parent_id[slot] = parent_track;
-            s.num_steps[slot] = 0;
-            s.num_looping_steps[slot] = 0;
-            s.status[slot] = ST_INITIALIZING;
-            s.step_length[slot] = 0;
-            s.post_step_action[slot] = INVALID;
-            s.along_step_action[slot] = INVALID;
-            geo.initialize_from(slot, sdir);
-            s.particle_id[slot] = spid;
-            s.energy[slot] = senergy;
-            s.interaction_mfp[slot] = 0;
-            s.msc_range[slot] = 0;
-            s.msc_range[n + slot] = 0;
-            s.msc_range[2 * n + slot] = 0;
-            initialized = true;
-        }
+        u32 const event = s.event_id[slot];
+        u32 const parent_track = s.track_id[slot];
+        real const time = s.time[slot];
+        GeoTrack geo(p, s, slot);
+        Real3 const pos = geo.pos();
+        u32 const lev = geo.level();
+
+        // Track ids: per-event counter (reference: atomic_add, detail/Utils.hh:107-116);
+        // deterministic slot-order ids when a single event is in flight
+        u32 id_base;
+        if (s.single_event != INVALID)
+            id_base = s.counters[CTR_TRACK_ID_BASE] + all_off;
         else
+            id_base = atomicAdd(&s.track_counters[event], e.num_sec_all);
+
+        for (int i = 0; i < MAX_SECONDARIES; ++i)
         {
-            s.ti_track_id[out] = new_id;
-            s.ti_parent_id[out] = parent_track;
-            s.ti_event_id[out] = event;
-            s.ti_time[out] = time;
-            s.ti_particle_id[out] = spid;
-            s.ti_energy[out] = senergy;
-            for (int k = 0; k < 3; ++k)
+            u32 spid = s.sec_particle[i * n + slot];
+            if (spid == INVALID)
+                continue;
+            real senergy = s.sec_energy[i * n + slot];
+            Real3 sdir = make_real3(s.sec_dir[(i * 3 + 0) * n + slot],
+                                    s.sec_dir[(i * 3 + 1) * n + slot],
+                                    s.sec_dir[(i * 3 + 2) * n + slot]);
+            u32 new_id = id_base++;
+            if (!initialized && e.reuse_slot)
             {
-                s.ti_pos[k * s.init_capacity + out] = pos[k];
-                s.ti_dir[k * s.init_capacity + out] = sdir[k];
+                // The first secondary takes over the dead parent's slot
+                s.track_id[slot] = new_id;
+                s.parent_id[slot] = parent_track;
+                s.num_steps[slot] = 0;
+                s.num_looping_steps[slot] = 0;
+                s.status[slot] = ST_INITIALIZING;
+                s.step_length[slot] = 0;
+                s.post_step_action[slot] = INVALID;
+                s.along_step_action[slot] = INVALID;
+                geo.initialize_from(slot, sdir);
+                s.particle_id[slot] = spid;
+                s.energy[slot] = senergy;
+                s.interaction_mfp[slot] = 0;
+                s.msc_range[slot] = 0;
+                s.msc_range[n + slot] = 0;
+                s.msc_range[2 * n + slot] = 0;
+                initialized = true;
             }
-            ++out;
+            else
+            {
+                s.ti_track_id[out] = new_id;
+                s.ti_parent_id[out] = parent_track;
+                s.ti_event_id[out] = event;
+                s.ti_time[out] = time;
+                s.ti_particle_id[out] = spid;
+                s.ti_energy[out] = senergy;
+                for (int k = 0; k < 3; ++k)
+                {
+                    s.ti_pos[k * cap + out] = pos[k];
+                    s.ti_dir[k * cap + out] = sdir[k];
+                }
+                // the parent's volume hierarchy at this point
+                s.ti_level[out] = lev;
+                for (u32 l = 0; l <= lev; ++l)
+                {
+                    s.ti_vol[l * cap + out] = s.geo_vol[l * n + slot];
+                    s.ti_univ[l * cap + out] = s.geo_univ[l * n + slot];
+                }
+                ++out;
+            }
         }
     }
     if (!initialized && status == ST_KILLED)
         s.status[slot] = ST_INACTIVE;
-    if (status == ST_ERRORED && !initialized)
-    {
-        // errored tracks were killed by tracking-cut; nothing else to do
-    }
 }
 
 //---------------------------------------------------------------------------//
@@ -573,7 +677,7 @@ __global__ void k_end_pass3(ParamsView const p, StateView s)
 //---------------------------------------------------------------------------//
 __global__ void k_reseed(ParamsView const p, StateView s, u64 event_id)
 {
-    u32 slot = thread_slot();
+    u32 slot = thread_id();
     if (slot >= s.num_slots)
         return;
     Rng rng;
@@ -588,7 +692,7 @@ __global__ void k_reset_generated(StateView s)
 
 __global__ void k_kill_active(ParamsView const p, StateView s)
 {
-    u32 slot = thread_slot();
+    u32 slot = thread_id();
     if (slot >= s.num_slots)
         return;
     if (s.status[slot] == ST_INACTIVE)
@@ -610,7 +714,7 @@ std::atomic<uint64_t> g_launches{0};
 #define B2_COUNT(n) g_launches.fetch_add(n, std::memory_order_relaxed)
 inline unsigned grid_for(u32 n)
 {
-    return (n + BLOCK - 1) / BLOCK;
+    return n == 0 ? 1u : (n + BLOCK - 1) / BLOCK;
 }
 inline int check_launch()
 {
@@ -624,6 +728,11 @@ inline ParamsView const& PV(B200ParamsView const* p)
 inline StateView const& SV(B200StateView const* s)
 {
     return *reinterpret_cast<StateView const*>(s);
+}
+//! Threads needed to cover the active list (host upper bound, capped by slots)
+inline u32 active_hint(StateView const& s)
+{
+    return s.hint_active < s.num_slots ? s.hint_active : s.num_slots;
 }
 }  // namespace
 
@@ -657,16 +766,21 @@ int b200_step_initialize_tracks(B200ParamsView const* params,
                                 cudaStream_t stream)
 {
     StateView const& s = SV(state);
-    k_initialize_tracks<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
+    u32 n = s.hint_new < s.num_slots ? s.hint_new : s.num_slots;
+    if (n > 0)
+    {
+        k_initialize_tracks<<<grid_for(n), BLOCK, 0, stream>>>(PV(params), s);
+        B2_COUNT(1);
+    }
     k_initialize_finalize<<<1, 1, 0, stream>>>(s);
-    B2_COUNT(2);
+    B2_COUNT(1);
     return check_launch();
 }
 
 int b200_step_pre_step(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
 {
     StateView const& s = SV(state);
-    k_pre_step<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
+    k_pre_step<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s);
     B2_COUNT(1);
     return check_launch();
 }
@@ -674,8 +788,18 @@ int b200_step_pre_step(B200ParamsView const* params, B200StateView const* state,
 int b200_step_along_step(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
 {
     StateView const& s = SV(state);
-    k_along_step<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
-    B2_COUNT(1);
+    u32 nc = s.hint_charged < s.num_slots ? s.hint_charged : s.num_slots;
+    u32 nn = s.hint_neutral < s.num_slots ? s.hint_neutral : s.num_slots;
+    if (nc > 0)
+    {
+        k_along_step_charged<<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
+        B2_COUNT(1);
+    }
+    if (nn > 0)
+    {
+        k_along_step_neutral<<<grid_for(nn), BLOCK, 0, stream>>>(PV(params), s);
+        B2_COUNT(1);
+    }
     return check_launch();
 }
 
@@ -684,7 +808,7 @@ int b200_step_discrete_select(B200ParamsView const* params,
                               cudaStream_t stream)
 {
     StateView const& s = SV(state);
-    k_discrete_select<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
+    k_discrete_select<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s);
     B2_COUNT(1);
     return check_launch();
 }
@@ -692,7 +816,7 @@ int b200_step_discrete_select(B200ParamsView const* params,
 int b200_step_interact(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
 {
     StateView const& s = SV(state);
-    k_interact<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
+    k_interact<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s);
     B2_COUNT(1);
     return check_launch();
 }
@@ -700,7 +824,7 @@ int b200_step_interact(B200ParamsView const* params, B200StateView const* state,
 int b200_step_boundary(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
 {
     StateView const& s = SV(state);
-    k_boundary<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
+    k_boundary<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s);
     B2_COUNT(1);
     return check_launch();
 }
@@ -710,7 +834,7 @@ int b200_step_tracking_cut(B200ParamsView const* params,
                            cudaStream_t stream)
 {
     StateView const& s = SV(state);
-    k_tracking_cut<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
+    k_tracking_cut<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s);
     B2_COUNT(1);
     return check_launch();
 }
@@ -718,7 +842,7 @@ int b200_step_tracking_cut(B200ParamsView const* params,
 int b200_step_tally(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
 {
     StateView const& s = SV(state);
-    k_tally<<<grid_for(s.num_slots), BLOCK, 0, stream>>>(PV(params), s);
+    k_tally<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s);
     B2_COUNT(1);
     return check_launch();
 }

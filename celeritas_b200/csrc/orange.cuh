@@ -992,6 +992,37 @@ struct GeoTrack
         clear_next();
     }
 
+    //! Locate a track whose volume hierarchy is already known (it was born at its
+    //! parent's position): identical state to initialize() without the BIH searches
+    B2_D void initialize_known(Real3 const& ipos,
+                               Real3 const& idir,
+                               u32 lev_max,
+                               u32 const* vols,
+                               u32 const* univs,
+                               u32 stride)
+    {
+        failed = false;
+        Real3 lpos = ipos, ldir = idir;
+        for (u32 lev = 0; lev <= lev_max; ++lev)
+        {
+            u32 const v = vols[lev * stride];
+            u32 const uid = univs[lev * stride];
+            s.geo_vol[lidx(lev)] = v;
+            s.geo_univ[lidx(lev)] = uid;
+            set_pos(lev, lpos);
+            set_dir(lev, ldir);
+            if (lev < lev_max)
+            {
+                u32 daughter = daughter_of(uid, v);
+                transform_down(g, g.daughter_transform[daughter], lpos, ldir);
+            }
+        }
+        s.geo_level[slot] = lev_max;
+        s.geo_boundary[slot] = 1;
+        clear_surface();
+        clear_next();
+    }
+
     //! Copy another slot's location with a new direction (DetailedInitializer)
     B2_D void initialize_from(u32 other, Real3 const& newdir)
     {

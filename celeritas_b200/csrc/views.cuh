@@ -518,11 +518,25 @@ struct StateView
     real* ti_energy;
     real* ti_pos;            // [3][capacity]
     real* ti_dir;            // [3][capacity]
+    // volume hierarchy of the parent at the secondary's birth point, so that new
+    // tracks from secondaries skip the point-location search (ti_level INVALID = locate)
+    u32* ti_level;           // [capacity]
+    u32* ti_vol;             // [max_depth][capacity]
+    u32* ti_univ;            // [max_depth][capacity]
+
+    // Dense lists of active slots, rebuilt at the end of every step: charged tracks
+    // are track_slots[0 .. num_charged), neutral tracks track_slots[N-1 .. N-num_neutral]
+    u32* track_slots;        // [slot]
 
     // device-resident counters (mirrors CoreStateCounters) + scratch
     u32* counters;           // see Counter enum
-    u32* block_scratch;      // [3 * num_blocks] per-block totals for the end-of-step scans
+    u32* block_scratch;      // [5 * num_blocks] per-block totals for the end-of-step scans
     u32 single_event;        // event id if exactly one event is in flight, else INVALID
+    // host-side upper bounds used only to size grids (kernels re-check device counters)
+    u32 hint_active;
+    u32 hint_charged;
+    u32 hint_neutral;
+    u32 hint_new;
 
     // scoring (null when no detectors are registered)
     u32* pre_volume;                     // [slot] global volume id at the pre-step point
@@ -544,6 +558,8 @@ enum Counter : u32
     CTR_NUM_NEW_TRACKS,
     CTR_ERROR,
     CTR_TRACK_ID_BASE,
+    CTR_NUM_CHARGED,   // entries at the front of track_slots
+    CTR_NUM_NEUTRAL,   // entries at the back of track_slots
     CTR_SIZE = 16
 };
 

@@ -109,13 +109,17 @@ CoreState::CoreState(std::shared_ptr<CoreParams const> params,
         s.ti_energy = arena_.alloc<real>(cap);
         s.ti_pos = arena_.alloc<real>(size_t(3) * cap);
         s.ti_dir = arena_.alloc<real>(size_t(3) * cap);
+        s.ti_level = arena_.alloc_fill<u32>(cap, 0xff);
+        s.ti_vol = arena_.alloc<u32>(size_t(D) * cap);
+        s.ti_univ = arena_.alloc<u32>(size_t(D) * cap);
+        s.track_slots = arena_.alloc<u32>(n);
     }
     {
         std::vector<uint32_t> ctr(CTR_SIZE, 0);
         ctr[CTR_NUM_VACANCIES] = n;
         s.counters = const_cast<u32*>(arena_.upload(ctr));
         uint32_t num_blocks = (n + 127) / 128;
-        s.block_scratch = arena_.alloc<u32>(size_t(3) * num_blocks);
+        s.block_scratch = arena_.alloc<u32>(size_t(5) * num_blocks);
         s.single_event = INVALID;
         s.step_counters = arena_.alloc<u64>(4);
     }
@@ -153,6 +157,8 @@ CoreStateCounters CoreState::sync_counters()
     c.num_active = h_counters_[CTR_NUM_ACTIVE];
     c.num_secondaries = h_counters_[CTR_NUM_SECONDARIES];
     c.num_alive = h_counters_[CTR_NUM_ALIVE];
+    c.num_charged = h_counters_[CTR_NUM_CHARGED];
+    c.num_neutral = h_counters_[CTR_NUM_NEUTRAL];
     last_error_ = h_counters_[CTR_ERROR];
     return c;
 }

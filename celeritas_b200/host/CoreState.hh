@@ -25,6 +25,8 @@ struct CoreStateCounters
     uint32_t num_active{0};
     uint32_t num_secondaries{0};
     uint32_t num_alive{0};
+    uint32_t num_charged{0};  //!< active charged tracks in the dense list
+    uint32_t num_neutral{0};  //!< active neutral tracks in the dense list
 };
 
 class CoreState
@@ -38,6 +40,14 @@ class CoreState
     b200::StateView const& view() const { return view_; }
     //! Declare which single event is in flight (INVALID: several / unknown)
     void single_event(uint32_t event_id) { view_.single_event = event_id; }
+    //! Upper bounds used to size the next iteration's grids
+    void launch_hints(uint32_t active, uint32_t charged, uint32_t neutral, uint32_t fresh)
+    {
+        view_.hint_active = active;
+        view_.hint_charged = charged;
+        view_.hint_neutral = neutral;
+        view_.hint_new = fresh;
+    }
     uint32_t size() const { return view_.num_slots; }
     uint32_t stream_id() const { return stream_id_; }
     cudaStream_t stream() const { return stream_; }

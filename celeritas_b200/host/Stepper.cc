@@ -240,6 +240,7 @@ Stepper::Stepper(StepperInput input) : params_(std::move(input.params))
     actions_ = std::make_shared<ActionSequence>(*params_);
     state_ = std::make_unique<CoreState>(params_, input.stream_id, input.num_track_slots);
     staging_ = std::make_unique<Staging>();
+    last_.num_vacancies = input.num_track_slots;
 }
 
 Stepper::~Stepper() = default;
@@ -285,8 +286,19 @@ void Stepper::step_async()
 {
     CoreState& state = *state_;
     cudaStream_t stream = state.stream();
-    check_rc(b200_reset_generated(sv(state), stream), "reset_generated");
     Staging& st = *staging_;
+    {
+        // Grid sizing: exact counts from the previous iteration's counters. Every
+        // queued initializer (plus staged primaries) may start if a slot is vacant.
+        uint64_t const n = state.size();
+        uint64_t queued = uint64_t(last_.num_initializers) + st.count;
+        uint64_t fresh = std::min<uint64_t>(queued, last_.num_vacancies);
+        state.launch_hints(std::min<uint64_t>(n, last_.num_alive + fresh),
+                           std::min<uint64_t>(n, last_.num_charged + fresh),
+                           std::min<uint64_t>(n, last_.num_neutral + fresh),
+                           fresh);
+    }
+    check_rc(b200_reset_generated(sv(state), stream), "reset_generated");
     if (st.count > 0)
     {
         B2_CUDA_CALL(cudaMemcpyAsync(st.d_primaries,
@@ -317,6 +329,7 @@ StepperResult Stepper::operator()()
 {
     this->step_async();
     CoreStateCounters c = state_->sync_counters();
+    last_ = c;
     actions_->collect_times();
     if (uint32_t err = state_->last_device_error())
     {

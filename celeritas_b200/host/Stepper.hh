@@ -136,5 +136,6 @@ class Stepper
     struct Staging;
     std::unique_ptr<Staging> staging_;
     std::set<uint32_t> events_in_flight_;
+    CoreStateCounters last_{};  // counters at the end of the previous iteration
 };
 }  // namespace celeritas_b200
