@@ -32,6 +32,10 @@
 namespace b200
 {
 constexpr int BLOCK = 128;
+#ifndef B2_ALONG_MIN_BLOCKS
+#    define B2_ALONG_MIN_BLOCKS 4
+#endif
+constexpr int ALONG_MIN_BLOCKS = B2_ALONG_MIN_BLOCKS;
 
 B2_D u32 thread_id()
 {
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(BLOCK) k_pre_step(ParamsView const p, StateVie
 //---------------------------------------------------------------------------//
 // along-step: one launch per charge class over its dense list
 //---------------------------------------------------------------------------//
-__global__ void __launch_bounds__(BLOCK) k_along_step_charged(ParamsView const p, StateView s)
+__global__ void __launch_bounds__(BLOCK, ALONG_MIN_BLOCKS) k_along_step_charged(ParamsView const p, StateView s)
 {
     u32 tid = thread_id();
     if (tid >= s.counters[CTR_NUM_CHARGED])
@@ -353,21 +357,45 @@ __global__ void __launch_bounds__(BLOCK) k_tracking_cut(ParamsView const p, Stat
 }
 
 // user_post: tallies (user/detail/SimpleCaloExecutor.hh:48-67)
-__global__ void __launch_bounds__(BLOCK) k_tally(ParamsView const p, StateView s)
+// Per-detector sums are first accumulated in shared memory (one copy per block) and
+// flushed with one global atomic per touched bin, instead of one contended global
+// atomic per depositing track.
+constexpr u32 TALLY_SMEM_BINS = 1024;
+
+__global__ void __launch_bounds__(BLOCK) k_tally(ParamsView const p, StateView s, u32 num_det)
 {
+    __shared__ real bins[TALLY_SMEM_BINS];
+    bool const use_smem = num_det <= TALLY_SMEM_BINS;
+    if (use_smem)
+    {
+        for (u32 i = threadIdx.x; i < num_det; i += BLOCK)
+            bins[i] = 0;
+        __syncthreads();
+    }
     u32 slot = active_slot(s, thread_id());
-    if (slot == INVALID)
-        return;
-    if (s.status[slot] == ST_INACTIVE)
-        return;
-    if (s.calo_edep)
+    if (slot != INVALID && s.status[slot] != ST_INACTIVE)
     {
         real edep = s.energy_deposition[slot];
         if (edep != 0)
         {
             u32 det = s.calo_detector_of_volume[s.pre_volume[slot]];
             if (det != INVALID)
-                atomicAdd(&s.calo_edep[det], edep);
+            {
+                if (use_smem)
+                    atomicAdd(&bins[det], edep);
+                else
+                    atomicAdd(&s.calo_edep[det], edep);
+            }
+        }
+    }
+    if (use_smem)
+    {
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < num_det; i += BLOCK)
+        {
+            real v = bins[i];
+            if (v != 0)
+                atomicAdd(&s.calo_edep[i], v);
         }
     }
 }
@@ -501,32 +529,42 @@ __global__ void __launch_bounds__(BLOCK) k_end_pass1(ParamsView const p, StateVi
     }
 }
 
-__global__ void k_end_pass2(StateView s, u32 num_blocks)
+__global__ void __launch_bounds__(1024) k_end_pass2(StateView s, u32 num_blocks)
 {
-    // Single block: scan block totals (chunked)
+    // Five blocks, one per scanned quantity: each thread owns a run of consecutive
+    // block totals; the last block to finish publishes the global counters.
     constexpr int B = 1024;
-    __shared__ u32 carry[5];
-    if (threadIdx.x < 5)
-        carry[threadIdx.x] = 0;
-    __syncthreads();
-    for (u32 base = 0; base < num_blocks; base += B)
+    u32 const a = blockIdx.x;
+    u32 const per = (num_blocks + B - 1) / B;
+    u32 const begin = threadIdx.x * per;
+    u32 const end = begin + per < num_blocks ? begin + per : num_blocks;
+    u32 local = 0;
+    for (u32 i = begin; i < end; ++i)
+        local += s.block_scratch[a * num_blocks + i];
+    u32 total;
+    u32 run = block_exclusive_scan<B, u32>(local, &total);
+    for (u32 i = begin; i < end; ++i)
     {
-        u32 i = base + threadIdx.x;
-        for (int a = 0; a < 5; ++a)
-        {
-            u32 v = i < num_blocks ? s.block_scratch[a * num_blocks + i] : 0;
-            u32 total;
-            u32 ex = block_exclusive_scan<B, u32>(v, &total);
-            if (i < num_blocks)
-                s.block_scratch[a * num_blocks + i] = ex + carry[a];
-            __syncthreads();
-            if (threadIdx.x == 0)
-                carry[a] += total;
-            __syncthreads();
-        }
+        u32 v = s.block_scratch[a * num_blocks + i];
+        s.block_scratch[a * num_blocks + i] = run;
+        run += v;
     }
+    __shared__ bool is_last;
     if (threadIdx.x == 0)
     {
+        s.counters[CTR_SCAN_TOTALS + a] = total;
+        __threadfence();
+        u32 done = atomicAdd(&s.counters[CTR_SCAN_DONE], 1u);
+        is_last = (done == 4);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0)
+    {
+        __threadfence();
+        s.counters[CTR_SCAN_DONE] = 0;
+        u32 carry[5];
+        for (int k = 0; k < 5; ++k)
+            carry[k] = reinterpret_cast<u32 volatile*>(s.counters)[CTR_SCAN_TOTALS + k];
         u32 num_vac = carry[0];
         u32 num_sec = carry[3];
         s.counters[CTR_NUM_VACANCIES] = num_vac;
@@ -842,7 +880,9 @@ int b200_step_tracking_cut(B200ParamsView const* params,
 int b200_step_tally(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
 {
     StateView const& s = SV(state);
-    k_tally<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s);
+    if (!s.calo_edep)
+        return 0;
+    k_tally<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s, s.num_detectors);
     B2_COUNT(1);
     return check_launch();
 }
@@ -854,7 +894,7 @@ int b200_step_extend_from_secondaries(B200ParamsView const* params,
     StateView const& s = SV(state);
     unsigned nb = grid_for(s.num_slots);
     k_end_pass1<<<nb, BLOCK, 0, stream>>>(PV(params), s);
-    k_end_pass2<<<1, 1024, 0, stream>>>(s, nb);
+    k_end_pass2<<<5, 1024, 0, stream>>>(s, nb);
     k_end_pass3<<<nb, BLOCK, 0, stream>>>(PV(params), s);
     B2_COUNT(3);
     return check_launch();

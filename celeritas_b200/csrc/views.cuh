@@ -542,6 +542,7 @@ struct StateView
     u32* pre_volume;                     // [slot] global volume id at the pre-step point
     u32 const* calo_detector_of_volume;  // [volume] detector id or INVALID
     real* calo_edep;                     // [detector] accumulated energy deposition [MeV]
+    u32 num_detectors;
 
     // step counters accumulated on device: {track-steps, step iterations}
     u64* step_counters;
@@ -560,7 +561,9 @@ enum Counter : u32
     CTR_TRACK_ID_BASE,
     CTR_NUM_CHARGED,   // entries at the front of track_slots
     CTR_NUM_NEUTRAL,   // entries at the back of track_slots
-    CTR_SIZE = 16
+    CTR_SCAN_DONE,     // blocks of the end-of-step scan that have finished
+    CTR_SCAN_TOTALS,   // 5 totals
+    CTR_SIZE = 24
 };
 
 }  // namespace b200

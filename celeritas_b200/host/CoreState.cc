@@ -129,6 +129,7 @@ CoreState::CoreState(std::shared_ptr<CoreParams const> params,
         s.pre_volume = arena_.alloc_fill<u32>(n, 0xff);
         s.calo_detector_of_volume = params_->detector_of_volume();
         s.calo_edep = arena_.alloc<real>(params_->num_detectors());
+        s.num_detectors = params_->num_detectors();
     }
     B2_CUDA_CALL(cudaMallocHost(reinterpret_cast<void**>(&h_counters_), CTR_SIZE * sizeof(uint32_t)));
     B2_CUDA_CALL(cudaDeviceSynchronize());
