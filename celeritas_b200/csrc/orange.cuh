@@ -825,6 +825,182 @@ B2_D u32 unit_daughter(GeoParams const& g, SimpleUnit const& u, u32 volid)
 }
 
 //---------------------------------------------------------------------------//
+// RECT ARRAY TRACKER (reference univ/RectArrayTracker.hh:120-360)
+// Record (16 u32): daughter_begin, daughter_count, dims[3], {grid begin, end} x 3,
+// surface indexer offsets[4], pad. Local volume = (ix * ny + iy) * nz + iz; local
+// surfaces are the grid planes, numbered per axis through the ragged offsets.
+//---------------------------------------------------------------------------//
+struct RectArrayRef
+{
+    u32 const* r;
+    real const* reals;
+    B2_D u32 dim(int ax) const { return r[2 + ax]; }
+    B2_D real const* grid(int ax) const { return reals + r[5 + 2 * ax]; }
+    B2_D u32 grid_size(int ax) const { return r[6 + 2 * ax] - r[5 + 2 * ax]; }
+    B2_D u32 surf_offset(int i) const { return r[11 + i]; }
+    B2_D void coords(u32 vol, u32 c[3]) const
+    {
+        c[2] = vol % dim(2);
+        vol = (vol - c[2]) / dim(2);
+        c[1] = vol % dim(1);
+        vol = (vol - c[1]) / dim(1);
+        c[0] = vol;
+    }
+    B2_D u32 index(u32 const c[3]) const { return (c[0] * dim(1) + c[1]) * dim(2) + c[2]; }
+    B2_D u32 surface_axis(u32 surf) const
+    {
+        u32 i = 0;
+        while (surf >= surf_offset(i + 1))
+            ++i;
+        return i;
+    }
+};
+
+B2_D RectArrayRef get_rect_array(GeoParams const& g, u32 index)
+{
+    return RectArrayRef{g.rect_arrays + 16 * index, g.reals};
+}
+
+B2_D Initialization rect_initialize(RectArrayRef const& ra, Real3 const& pos)
+{
+    u32 c[3];
+    for (int ax = 0; ax < 3; ++ax)
+    {
+        real const* grid = ra.grid(ax);
+        u32 const n = ra.grid_size(ax);
+        real const p = pos[ax];
+        if (p < grid[0] || p > grid[n - 1])
+            return Initialization{INVALID, INVALID, 0};
+        // NonuniformGrid::find
+        u32 lo = 0, len = n;
+        while (len > 0)
+        {
+            u32 half = len >> 1;
+            u32 mid = lo + half;
+            if (grid[mid] < p)
+            {
+                lo = mid + 1;
+                len -= half + 1;
+            }
+            else
+                len = half;
+        }
+        if (p != grid[lo])
+            --lo;
+        if (grid[lo] == p)
+            return Initialization{INVALID, INVALID, 0};
+        c[ax] = lo;
+    }
+    return Initialization{ra.index(c), INVALID, 0};
+}
+
+B2_D Initialization rect_cross_boundary(RectArrayRef const& ra, LocalState const& st)
+{
+    u32 c[3];
+    ra.coords(st.volume, c);
+    u32 ax = ra.surface_axis(st.surface);
+    // sense outside (1) = increasing coordinate
+    c[ax] += (st.sense == 1) ? 1u : u32(-1);
+    return Initialization{ra.index(c), st.surface, st.sense};
+}
+
+B2_D Intersection rect_intersect(RectArrayRef const& ra, LocalState const& st, bool limited, real max_dist)
+{
+    u32 c[3];
+    ra.coords(st.volume, c);
+    Intersection result{INVALID, 0, real_inf()};
+    for (int ax = 0; ax < 3; ++ax)
+    {
+        real dir = st.dir[ax];
+        if (dir == 0)
+            continue;
+        u32 target_coord = c[ax] + (dir > 0 ? 1u : 0u);
+        real target_value = ra.grid(ax)[target_coord];
+        real dist = (target_value - st.pos[ax]) / st.dir[ax];
+        bool valid = limited ? (dist <= max_dist) : (dist < real_max());
+        if (dist > 0 && valid && dist < result.distance)
+        {
+            result.distance = dist;
+            result.sense = dir > 0 ? 0 : 1;
+            result.surface = ra.surf_offset(ax) + target_coord;
+        }
+    }
+    if (limited && result.surface == INVALID)
+        result.distance = max_dist;
+    return result;
+}
+
+B2_D real rect_safety(RectArrayRef const& ra, Real3 const& pos, u32 vol)
+{
+    u32 c[3];
+    ra.coords(vol, c);
+    real min_dist = real_inf();
+    for (int ax = 0; ax < 3; ++ax)
+    {
+        real const* grid = ra.grid(ax);
+        for (u32 i = 0; i < 2; ++i)
+        {
+            real d = fabs(pos[ax] - grid[c[ax] + i]);
+            min_dist = d < min_dist ? d : min_dist;
+        }
+    }
+    return min_dist;
+}
+
+//---------------------------------------------------------------------------//
+// UNIVERSE DISPATCH (reference univ/TrackerVisitor.hh:63-79)
+//---------------------------------------------------------------------------//
+B2_D Initialization univ_initialize(GeoParams const& g, u32 uid, Real3 const& pos)
+{
+    u32 idx = g.universe_index[uid];
+    if (g.universe_type[uid] == UNIV_SIMPLE)
+        return unit_initialize(g, g.simple_units[idx], pos);
+    return rect_initialize(get_rect_array(g, idx), pos);
+}
+
+B2_D Initialization univ_cross_boundary(GeoParams const& g, u32 uid, LocalState const& st)
+{
+    u32 idx = g.universe_index[uid];
+    if (g.universe_type[uid] == UNIV_SIMPLE)
+        return unit_cross_boundary(g, g.simple_units[idx], st);
+    return rect_cross_boundary(get_rect_array(g, idx), st);
+}
+
+B2_D Intersection univ_intersect(GeoParams const& g, u32 uid, LocalState const& st, bool limited, real max_dist)
+{
+    u32 idx = g.universe_index[uid];
+    if (g.universe_type[uid] == UNIV_SIMPLE)
+        return unit_intersect(g, g.simple_units[idx], st, limited, max_dist);
+    return rect_intersect(get_rect_array(g, idx), st, limited, max_dist);
+}
+
+B2_D real univ_safety(GeoParams const& g, u32 uid, Real3 const& pos, u32 vol)
+{
+    u32 idx = g.universe_index[uid];
+    if (g.universe_type[uid] == UNIV_SIMPLE)
+        return unit_safety(g, g.simple_units[idx], pos, vol);
+    return rect_safety(get_rect_array(g, idx), pos, vol);
+}
+
+B2_D u32 univ_daughter(GeoParams const& g, u32 uid, u32 vol)
+{
+    u32 idx = g.universe_index[uid];
+    if (g.universe_type[uid] == UNIV_SIMPLE)
+        return unit_daughter(g, g.simple_units[idx], vol);
+    return g.rect_arrays[16 * idx] + vol;
+}
+
+B2_D Real3 univ_normal(GeoParams const& g, u32 uid, Real3 const& pos, u32 surf)
+{
+    u32 idx = g.universe_index[uid];
+    if (g.universe_type[uid] == UNIV_SIMPLE)
+        return surface_normal(get_surface(g, g.simple_units[idx], surf), pos);
+    Real3 n = make_real3(0, 0, 0);
+    n[get_rect_array(g, idx).surface_axis(surf)] = 1;
+    return n;
+}
+
+//---------------------------------------------------------------------------//
 // TRANSFORMS
 //---------------------------------------------------------------------------//
 B2_D void transform_down(GeoParams const& g, u32 transform_id, Real3& pos, Real3& dir)
@@ -954,7 +1130,7 @@ struct GeoTrack
 
     B2_D u32 daughter_of(u32 universe, u32 volume) const
     {
-        return unit_daughter(g, unit_of(universe), volume);
+        return univ_daughter(g, universe, volume);
     }
 
     //! Locate a track from scratch (OrangeTrackView::operator=(Initializer))
@@ -967,8 +1143,7 @@ struct GeoTrack
         u32 daughter;
         do
         {
-            SimpleUnit const& u = unit_of(uid);
-            Initialization tinit = unit_initialize(g, u, lpos);
+            Initialization tinit = univ_initialize(g, uid, lpos);
             if (tinit.volume == INVALID || tinit.surface != INVALID)
             {
                 failed = true;
@@ -978,7 +1153,7 @@ struct GeoTrack
             s.geo_univ[lidx(lev)] = uid;
             set_pos(lev, lpos);
             set_dir(lev, ldir);
-            daughter = unit_daughter(g, u, tinit.volume);
+            daughter = univ_daughter(g, uid, tinit.volume);
             if (daughter != INVALID)
             {
                 transform_down(g, g.daughter_transform[daughter], lpos, ldir);
@@ -1100,7 +1275,7 @@ struct GeoTrack
         for (u32 l = 1; l <= lev; ++l)
         {
             Intersection li
-                = unit_intersect(g, unit_of(univ(l)), local_state(l), true, isect.distance);
+                = univ_intersect(g, univ(l), local_state(l), true, isect.distance);
             if (li.distance < isect.distance)
             {
                 isect = li;
@@ -1180,7 +1355,7 @@ struct GeoTrack
         local.surface = s.geo_surf[slot];
         local.sense = s.geo_sense[slot];
 
-        Initialization ci = unit_cross_boundary(g, unit_of(universe), local);
+        Initialization ci = univ_cross_boundary(g, universe, local);
         u32 volume = ci.volume;
         if (volume == INVALID)
         {
@@ -1194,7 +1369,7 @@ struct GeoTrack
             ++lev;
             transform_down(g, g.daughter_transform[daughter], local.pos, local.dir);
             universe = g.daughter_universe[daughter];
-            Initialization ti = unit_initialize(g, unit_of(universe), local.pos);
+            Initialization ti = univ_initialize(g, universe, local.pos);
             volume = ti.volume;
             if (volume == INVALID)
             {
@@ -1215,8 +1390,7 @@ struct GeoTrack
         if (is_on_boundary())
         {
             u32 sl = s.geo_surface_level[slot];
-            SimpleUnit const& u = unit_of(univ(sl));
-            Real3 normal = surface_normal(get_surface(g, u, s.geo_surf[slot]), pos(sl));
+            Real3 normal = univ_normal(g, univ(sl), pos(sl), s.geo_surf[slot]);
             for (int l = int(level()) - 1; l >= 0; --l)
             {
                 u32 daughter = daughter_of(univ(l), vol(l));
@@ -1235,7 +1409,7 @@ struct GeoTrack
         u32 lev = level();
         for (u32 l = 0; l <= lev; ++l)
         {
-            real sd = unit_safety(g, unit_of(univ(l)), pos(l), vol(l));
+            real sd = univ_safety(g, univ(l), pos(l), vol(l));
             min_safety = sd < min_safety ? sd : min_safety;
         }
         return min_safety;

@@ -51,7 +51,11 @@ void CoreParams::load(Image const& img)
     auto F32 = [&](char const* n) { return arena_.upload(img.get<float>(n)); };
     auto U8 = [&](char const* n) { return arena_.upload(img.get<uint8_t>(n)); };
 
+    // Geometry-only images (navigation tests) carry no physics
+    bool const geo_only = !img.has("phys.dims");
+
     //// CORE ////
+    if (!geo_only)
     {
         auto a = img.get<uint32_t>("core.actions");
         view_.scalars.boundary_action = a.at(0);
@@ -91,8 +95,10 @@ void CoreParams::load(Image const& img)
         auto utype = img.get<uint8_t>("geo.universe_type");
         g.num_universes = utype.size();
         for (auto t : utype)
-            if (t != UNIV_SIMPLE)
-                throw std::runtime_error("only simple-unit universes are supported");
+            if (t != UNIV_SIMPLE && t != UNIV_RECT_ARRAY)
+                throw std::runtime_error("unsupported universe type in image");
+        if (utype.empty() || utype[0] != UNIV_SIMPLE)
+            throw std::runtime_error("the global universe must be a simple unit");
         g.universe_type = U8("geo.universe_type");
         g.universe_index = U32("geo.universe_index");
         g.universe_surface_offset = U32("geo.universe_surface_offset");
@@ -138,9 +144,13 @@ void CoreParams::load(Image const& img)
         g.bih_leaf_parent = U32("geo.bih_leaf_parent");
         g.bih_leaf_vol_begin = U32("geo.bih_leaf_vol_begin");
         g.bih_leaf_vol_end = U32("geo.bih_leaf_vol_end");
-        g.volume_material = U32("geomat.volume_material");
+        if (!geo_only)
+            g.volume_material = U32("geomat.volume_material");
         volume_labels_ = split_lines(img.get_string("geo.volume_labels"));
     }
+
+    if (geo_only)
+        return;
 
     //// MATERIALS ////
     {

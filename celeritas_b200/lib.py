@@ -49,6 +49,7 @@ EXPORTS = [
     'b200_stepper_kill_active', 'b200_stepper_num_step_actions',
     'b200_stepper_step_action_label', 'b200_stepper_launch_count', 'b200_run_events',
     'b200_stepper_set_action_times', 'b200_stepper_action_time', 'b200_set_device',
+    'b200_geo_trace', 'b200_geo_trace_host',
 ]
 
 _lib = None
@@ -113,6 +114,7 @@ def load_library():
     L.b200_stepper_action_time.argtypes = [vp, C.c_uint32]
     L.b200_stepper_action_time.restype = C.c_double
     L.b200_set_device.argtypes = [C.c_int]
+    L.b200_geo_trace_host.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp]
     L.b200_run_events.argtypes = [vp, vp, vp, C.c_uint32, C.c_int, C.c_uint64,
                                   C.POINTER(RunResult)]
     _lib = L
@@ -184,6 +186,25 @@ class Params:
     def find_particle(self, pdg):
         r = load_library().b200_params_find_particle(self.h, pdg)
         return None if r == 0xffffffff else r
+
+    def trace(self, pos, direction, max_segments=64):
+        """Ray-trace through the geometry on the GPU.
+
+        Returns (volume[n, max_segments], surface[n, max_segments], distance[n, max_segments],
+        count[n], safety[n]).
+        """
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        direction = np.ascontiguousarray(direction, dtype=np.float64).reshape(-1, 3)
+        n = len(pos)
+        vol = np.full((n, max_segments), 0xffffffff, dtype=np.uint32)
+        surf = np.full((n, max_segments), 0xffffffff, dtype=np.uint32)
+        dist = np.zeros((n, max_segments))
+        count = np.zeros(n, dtype=np.uint32)
+        safety = np.zeros(n)
+        _check(load_library().b200_geo_trace_host(
+            self.h, pos.ctypes.data, direction.ctypes.data, n, max_segments, vol.ctypes.data,
+            surf.ctypes.data, dist.ctypes.data, count.ctypes.data, safety.ctypes.data))
+        return vol, surf, dist, count, safety
 
 
 class Stepper:

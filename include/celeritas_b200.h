@@ -145,6 +145,36 @@ int b200_reseed(B200ParamsView const*, B200StateView const*, uint64_t event_id, 
 int b200_reset_generated(B200StateView const*, cudaStream_t);
 int b200_kill_active(B200ParamsView const*, B200StateView const*, cudaStream_t);
 
+/*--- ORANGE navigation on fixed ray sets -------------------------------------------*/
+/* Reference: OrangeTrackView::{operator=(Initializer), find_next_step, move_to_boundary,
+ * cross_boundary, find_safety, volume_id, surface_id} (orange/OrangeTrackView.hh:265-842).
+ * Per ray: up to max_segments records {volume id, surface id crossed, distance};
+ * count[i] = number of segments (bit 31 set: a crossing failed; 0xffffffff: could not
+ * locate the origin); safety[i] = safety distance at the origin (-1 if outside).
+ * Device-pointer version (asynchronous) and host-buffer convenience version. */
+int b200_geo_trace(B200ParamsView const* params,
+                   B200StateView const* state,
+                   double const* d_pos,
+                   double const* d_dir,
+                   uint32_t num_rays,
+                   uint32_t max_segments,
+                   uint32_t* d_volume,
+                   uint32_t* d_surface,
+                   double* d_distance,
+                   uint32_t* d_count,
+                   double* d_safety,
+                   cudaStream_t stream);
+int b200_geo_trace_host(B200Params const* params,
+                        double const* pos,
+                        double const* dir,
+                        uint32_t num_rays,
+                        uint32_t max_segments,
+                        uint32_t* volume,
+                        uint32_t* surface,
+                        double* distance,
+                        uint32_t* count,
+                        double* safety);
+
 /* Total kernel launches issued by this library in this process */
 uint64_t b200_launch_count(void);
 

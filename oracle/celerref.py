@@ -48,6 +48,9 @@ def lib():
         L.celerref_state_get.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
         L.celerref_calo_get.argtypes = [C.c_void_p, C.c_void_p]
         L.celerref_calo_clear.argtypes = [C.c_void_p]
+        L.celerref_geo_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                         C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
         L.celerref_run_events.restype = C.c_double
         L.celerref_run_events.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                           C.c_uint32, C.c_int, C.c_void_p]
@@ -93,6 +96,22 @@ class Problem:
 
     def calo_clear(self):
         _check(lib().celerref_calo_clear(self.h))
+
+    def trace(self, pos, direction, max_segments=64):
+        """Ray-trace with the reference's OrangeTrackView (same outputs as Params.trace)."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        direction = np.ascontiguousarray(direction, dtype=np.float64).reshape(-1, 3)
+        n = len(pos)
+        vol = np.full((n, max_segments), 0xffffffff, dtype=np.uint32)
+        surf = np.full((n, max_segments), 0xffffffff, dtype=np.uint32)
+        dist = np.zeros((n, max_segments))
+        count = np.zeros(n, dtype=np.uint32)
+        safety = np.zeros(n)
+        _check(lib().celerref_geo_trace(self.h, pos.ctypes.data, direction.ctypes.data, n,
+                                        max_segments, vol.ctypes.data, surf.ctypes.data,
+                                        dist.ctypes.data, count.ctypes.data,
+                                        safety.ctypes.data))
+        return vol, surf, dist, count, safety
 
     def run_events(self, primaries, offsets, num_track_slots, num_threads=0):
         primaries = np.ascontiguousarray(primaries, dtype=PRIMARY_DTYPE)

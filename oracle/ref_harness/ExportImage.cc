@@ -752,10 +752,22 @@ void export_models(Problem const& prob, b200::Image& img)
 void export_image(Problem const& prob, std::string const& path)
 {
     b200::Image img;
+    img.put_string("config", prob.config.dump());
+    if (!prob.core)
+    {
+        // Geometry-only image
+        CELER_VALIDATE(prob.geo, << "empty problem");
+        export_geometry(prob.geo->host_ref(), img);
+        std::string labels;
+        for (auto v : range(VolumeId{prob.geo->volumes().size()}))
+            labels += prob.geo->volumes().at(v).name + "\n";
+        img.put_string("geo.volume_labels", labels);
+        img.write(path);
+        return;
+    }
     CoreParams const& core = *prob.core;
     auto const& ref = core.host_ref();
 
-    img.put_string("config", prob.config.dump());
 
     // Core scalars and the action table
     {

@@ -516,6 +516,13 @@ std::unique_ptr<Problem> build_problem(json const& config)
     p->config = config;
     json const& cfg = p->config;
 
+    if (cfg.value("problem", std::string("imported")) == "geometry")
+    {
+        // ORANGE only: used by the navigation ray-trace tests
+        p->geo = std::make_shared<OrangeParams>(resolve(cfg, "geometry_file"));
+        return p;
+    }
+
     CoreParams::Input params;
     params.action_reg = std::make_shared<ActionRegistry>();
     params.output_reg = std::make_shared<OutputRegistry>();

@@ -17,6 +17,7 @@
 #include "celeritas/em/params/FluctuationParams.hh"
 #include "celeritas/em/params/UrbanMscParams.hh"
 #include "celeritas/field/UniformFieldData.hh"
+#include "orange/OrangeParams.hh"
 #include "celeritas/global/CoreParams.hh"
 #include "celeritas/io/ImportData.hh"
 #include "celeritas/user/SimpleCalo.hh"
@@ -29,6 +30,8 @@ struct Problem
     nlohmann::json config;
     celeritas::ImportData imported;
     std::shared_ptr<celeritas::CoreParams> core;
+    //! Geometry-only problems ("problem": "geometry"): no physics, core is null
+    std::shared_ptr<celeritas::OrangeParams const> geo;
     std::shared_ptr<celeritas::SimpleCalo> calo;
     std::shared_ptr<celeritas::StepCollector> collector;
     std::vector<std::string> calo_volumes;

@@ -405,3 +405,72 @@ extern "C" int celerref_element_data_json(char const* dir, int z_sb, int z_pe, c
         std::memcpy(out, s.c_str(), s.size() + 1);
     });
 }
+
+//---------------------------------------------------------------------------//
+// Ray tracing with the reference's OrangeTrackView on the host (same protocol as
+// celeritas_b200/csrc/geo_trace.cu): per ray, the sequence of (volume id, surface id
+// crossed, segment length) until the ray leaves the geometry, and the safety at
+// the origin.
+//---------------------------------------------------------------------------//
+#include "corecel/data/CollectionStateStore.hh"
+#include "orange/OrangeParams.hh"
+#include "orange/OrangeTrackView.hh"
+
+extern "C" int celerref_geo_trace(void* problem,
+                                  double const* pos,
+                                  double const* dir,
+                                  uint32_t num_rays,
+                                  uint32_t max_segments,
+                                  uint32_t* volume,
+                                  uint32_t* surface,
+                                  double* distance,
+                                  uint32_t* count,
+                                  double* safety)
+{
+    return guarded([&] {
+        auto* p = static_cast<celerref::Problem*>(problem);
+        std::shared_ptr<OrangeParams const> geo
+            = p->geo ? p->geo : p->core->geometry();
+        auto const& params = geo->host_ref();
+        CollectionStateStore<OrangeStateData, MemSpace::host> store(params, num_rays);
+        for (uint32_t i = 0; i < num_rays; ++i)
+        {
+            OrangeTrackView trk(params, store.ref(), TrackSlotId{i});
+            trk = GeoTrackInitializer{{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]},
+                                      {dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]}};
+            if (trk.failed())
+            {
+                count[i] = 0xffffffffu;
+                safety[i] = -1;
+                continue;
+            }
+            safety[i] = trk.is_outside() ? -1 : trk.find_safety();
+            uint32_t n = 0;
+            while (!trk.is_outside() && n < max_segments)
+            {
+                uint32_t vol = trk.volume_id().unchecked_get();
+                auto prop = trk.find_next_step();
+                if (!prop.boundary)
+                {
+                    volume[i * max_segments + n] = vol;
+                    surface[i * max_segments + n] = 0xffffffffu;
+                    distance[i * max_segments + n] = prop.distance;
+                    ++n;
+                    break;
+                }
+                trk.move_to_boundary();
+                volume[i * max_segments + n] = vol;
+                surface[i * max_segments + n] = trk.surface_id().unchecked_get();
+                distance[i * max_segments + n] = prop.distance;
+                ++n;
+                trk.cross_boundary();
+                if (trk.failed())
+                {
+                    n |= 0x80000000u;
+                    break;
+                }
+            }
+            count[i] = n;
+        }
+    });
+}

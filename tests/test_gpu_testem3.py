@@ -53,3 +53,13 @@ def test_calo_tally_matches_reference():
     assert a.sum() > 3000  # most of 4 GeV is deposited in the calorimeter
     # Same tracks, same order of magnitude of roundoff: per-bin relative tolerance
     assert np.allclose(a, b, rtol=1e-9, atol=1e-9)
+
+
+def test_lockstep_nested_geometry():
+    """Two-level geometry: 50 translated daughters of one gap+absorber universe
+    (test/orange/data/testem3.org.json). Whole 1 GeV showers in lock-step."""
+    from parity import lockstep
+    refp, ref, params, gpu = setup('testem3-nested', 4096)
+    hist = lockstep(ref, gpu, electrons(2, 1000.0, params), compare_every=1)
+    assert not (hist[-1]['alive'] or hist[-1]['queued'])
+    assert np.allclose(refp.calo(2), gpu.calo(), rtol=1e-9, atol=1e-9)

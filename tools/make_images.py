@@ -48,12 +48,26 @@ PROBLEMS = {
                             'max_events': 16384, 'field': [0, 0, 1],
                             'simple_calo': ['si_tracker', 'em_calorimeter', 'had_calorimeter',
                                             'sc_solenoid', 'fe_muon_chambers']},
+    # two-level geometry (daughter universes with translations), same physics
+    'testem3-nested': {'geometry_file': 'data/geometry/testem3.org.json',
+                       'physics_file': 'data/physics/testem3-nested-steel-lar.json',
+                       'seed': 20220904, 'initializer_capacity': 1 << 18, 'max_events': 64,
+                       'simple_calo': ['gap', 'absorber']},
     # small-capacity variant of the same physics for lock-step tests
     'testem3-small': {'geometry_file': 'data/geometry/testem3-flat.org.json',
                       'physics_file': 'data/physics/testem3-steel-lar.json',
                       'seed': 20220904, 'initializer_capacity': 1 << 18, 'max_events': 64,
                       'simple_calo': GAPS + ABSORBERS},
 }
+
+
+# Geometry-only images for the navigation (ray-trace) parity tests: the ORANGE test
+# geometries of the reference (test/orange/data, test/geocel/data)
+for _g in ('two-boxes', 'testem3-flat', 'testem3', 'simple-cms', 'five-volumes', 'universes',
+           'rect-array', 'nested-rect-arrays', 'hex-array', 'three-spheres', 'testem15',
+           'lar-sphere', 'four-steel-slabs', 'one-steel-sphere'):
+    PROBLEMS['geo-' + _g] = {'problem': 'geometry',
+                             'geometry_file': 'data/geometry/%s.org.json' % _g}
 
 
 def main(names):

@@ -197,6 +197,14 @@ def main():
           [e['name'] for e in em3['elements']],
           [(p['particle_pdg'], p['process_class']) for p in em3['processes']])
 
+    # Two-level TestEm3 (data/geometry/testem3.org.json: 50 'pair' daughters of one
+    # gap+absorber universe): same materials, volumes named as in that geometry
+    nested = merge([(steel, 'G4_Galactic'), (steel, 'G4_STAINLESS-STEEL'), (lar, 'lAr')],
+                   [('world', 0), ('gap', 2), ('absorber', 1)])
+    add_element_data(nested)
+    json.dump(nested, open(os.path.join(PHYS, 'testem3-nested-steel-lar.json'), 'w'),
+              separators=(',', ':'))
+
     # simple-CMS geometry (data/geometry/simple-cms.org.json) with full-EM stand-in materials:
     # the bundled simple-cms.root has only Compton + ionisation + MSC below 1 GeV, which
     # cannot stop a 10 GeV shower. Tracker -> lAr, calorimeters/solenoid/muon iron -> steel.
