@@ -6,7 +6,9 @@ step action: importing works anywhere, but creating params/state requires a GPU
 and fails loudly otherwise.
 """
 from .lib import (Params, Stepper, Primary, PRIMARY_DTYPE, make_primaries, library_path,
-                  load_library, launch_count, device_count, set_device, B200Error)
+                  load_library, launch_count, device_count, set_device, B200Error,
+                  celer_sim_run)
 
 __all__ = ['Params', 'Stepper', 'Primary', 'PRIMARY_DTYPE', 'make_primaries', 'library_path',
-           'load_library', 'launch_count', 'device_count', 'set_device', 'B200Error']
+           'load_library', 'launch_count', 'device_count', 'set_device', 'B200Error',
+           'celer_sim_run']

@@ -401,6 +401,59 @@ __global__ void __launch_bounds__(BLOCK) k_tally(ParamsView const p, StateView s
 }
 
 //---------------------------------------------------------------------------//
+// diagnostics
+// post: tally the post-step action of every track that took this step
+//   (user/detail/ActionDiagnosticExecutor.hh:30-65)
+// user_post: tally the number of steps of every track killed this step
+//   (user/detail/StepDiagnosticExecutor.hh:28-60)
+// Counts are first gathered per block in shared memory (a handful of bins are hot).
+//---------------------------------------------------------------------------//
+constexpr u32 DIAG_SMEM_BINS = 1024;
+
+template<bool STEPS>
+__global__ void __launch_bounds__(BLOCK) k_diagnostic(StateView s, u32 num_particles)
+{
+    __shared__ u32 bins[DIAG_SMEM_BINS];
+    u32* const out = STEPS ? s.diag_step_counts : s.diag_action_counts;
+    u32 const nb = STEPS ? s.diag_step_bins : s.diag_action_bins;
+    u32 const total = nb * num_particles;
+    bool const use_smem = total <= DIAG_SMEM_BINS;
+    if (use_smem)
+    {
+        for (u32 i = threadIdx.x; i < total; i += BLOCK)
+            bins[i] = 0;
+        __syncthreads();
+    }
+    u32 slot = active_slot(s, thread_id());
+    if (slot != INVALID)
+    {
+        u8 status = s.status[slot];
+        u32 bin = INVALID;
+        if (!STEPS && status != ST_INACTIVE)
+        {
+            bin = s.particle_id[slot] * nb + s.post_step_action[slot];
+        }
+        if (STEPS && status == ST_KILLED)
+        {
+            u32 n = s.num_steps[slot];
+            bin = s.particle_id[slot] * nb + (n < nb - 1 ? n : nb - 1);
+        }
+        if (bin != INVALID)
+            atomicAdd(use_smem ? &bins[bin] : &out[bin], 1u);
+    }
+    if (use_smem)
+    {
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < total; i += BLOCK)
+        {
+            u32 v = bins[i];
+            if (v != 0)
+                atomicAdd(&out[i], v);
+        }
+    }
+}
+
+//---------------------------------------------------------------------------//
 // end: secondaries -> initializers, vacancy compaction, dense active lists
 // (track/detail/LocateAliveExecutor.hh:60-106,
 //  track/detail/ProcessSecondariesExecutor.hh:69-183,
@@ -883,6 +936,32 @@ int b200_step_tally(B200ParamsView const* params, B200StateView const* state, cu
     if (!s.calo_edep)
         return 0;
     k_tally<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s, s.num_detectors);
+    B2_COUNT(1);
+    return check_launch();
+}
+
+int b200_step_action_diagnostic(B200ParamsView const* params,
+                                B200StateView const* state,
+                                cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    if (!s.diag_action_counts)
+        return B200_ERR_INVALID_ARGUMENT;
+    k_diagnostic<false><<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(
+        s, PV(params).particle.num_particles);
+    B2_COUNT(1);
+    return check_launch();
+}
+
+int b200_step_step_diagnostic(B200ParamsView const* params,
+                              B200StateView const* state,
+                              cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    if (!s.diag_step_counts)
+        return B200_ERR_INVALID_ARGUMENT;
+    k_diagnostic<true><<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(
+        s, PV(params).particle.num_particles);
     B2_COUNT(1);
     return check_launch();
 }

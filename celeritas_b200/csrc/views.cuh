@@ -546,6 +546,12 @@ struct StateView
 
     // step counters accumulated on device: {track-steps, step iterations}
     u64* step_counters;
+
+    // diagnostics (user/ActionDiagnostic.hh, user/StepDiagnostic.hh); null when disabled
+    u32* diag_action_counts;  // [particle][diag_action_bins]: post-step action of every track-step
+    u32 diag_action_bins;     // number of actions
+    u32* diag_step_counts;    // [particle][diag_step_bins]: steps per track at its death
+    u32 diag_step_bins;       // max_step_bin + 2
 };
 
 enum Counter : u32

@@ -427,4 +427,28 @@ void CoreParams::load(Image const& img)
         }
     }
 }
+
+void CoreParams::init_capacity(uint32_t capacity)
+{
+    if (capacity == 0)
+        throw std::runtime_error("nonpositive initializer_capacity=0");
+    init_capacity_ = capacity;
+}
+
+void CoreParams::max_events(uint32_t num_events)
+{
+    if (num_events == 0)
+        throw std::runtime_error("max_events must be positive");
+    max_events_ = num_events;
+}
+
+void CoreParams::uniform_field_tesla(double const (&field)[3])
+{
+    if (!this->has_uniform_field())
+        throw std::runtime_error(
+            "the problem image was exported without a uniform-field along-step action");
+    // native field unit is gauss (reference: units::FieldTesla -> native, Runner.cc:394-398)
+    for (int i = 0; i < 3; ++i)
+        view_.model.field.field[i] = field[i] * 1e4;
+}
 }  // namespace celeritas_b200

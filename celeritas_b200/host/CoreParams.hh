@@ -68,6 +68,17 @@ class CoreParams
     uint32_t find_particle(int pdg) const;
     size_t device_bytes() const { return arena_.bytes(); }
 
+    //!@{
+    //! Run options that celer-sim takes from its input rather than from the problem
+    //! (app/celer-sim/Runner.cc:412-440); set before any state is created
+    void rng_seed(uint32_t seed) { view_.rng.seed = seed; }
+    void init_capacity(uint32_t capacity);
+    void max_events(uint32_t num_events);
+    //! Uniform field [T]; only for problems built with the uniform-field along-step
+    void uniform_field_tesla(double const (&field)[3]);
+    bool has_uniform_field() const { return view_.model.field.enabled != 0; }
+    //!@}
+
   private:
     CoreParams() = default;
     void load(b200::Image const& img);

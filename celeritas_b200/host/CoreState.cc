@@ -279,4 +279,77 @@ void CoreState::calo_clear()
         B2_CUDA_CALL(cudaMemsetAsync(
             view_.calo_edep, 0, params_->num_detectors() * sizeof(double), stream_));
 }
+
+void CoreState::enable_action_diagnostic(uint32_t num_actions)
+{
+    if (view_.diag_action_counts)
+        return;
+    view_.diag_action_bins = num_actions;
+    view_.diag_action_counts
+        = arena_.alloc<u32>(size_t(num_actions) * params_->view().particle.num_particles);
+}
+
+void CoreState::enable_step_diagnostic(uint32_t max_step_bin)
+{
+    if (view_.diag_step_counts)
+        return;
+    if (max_step_bin == 0)
+        throw std::runtime_error("nonpositive step diagnostic 'max' bin");
+    // two extra bins for underflow and overflow (user/StepDiagnostic.cc:65-71)
+    view_.diag_step_bins = max_step_bin + 2;
+    view_.diag_step_counts
+        = arena_.alloc<u32>(size_t(max_step_bin + 2) * params_->view().particle.num_particles);
+}
+
+void CoreState::diagnostic_get(bool steps, uint32_t* out)
+{
+    u32 const* src = steps ? view_.diag_step_counts : view_.diag_action_counts;
+    size_t bins = steps ? view_.diag_step_bins : view_.diag_action_bins;
+    if (!src)
+        throw std::runtime_error("diagnostic is not enabled");
+    B2_CUDA_CALL(cudaStreamSynchronize(stream_));
+    B2_CUDA_CALL(cudaMemcpy(out,
+                            src,
+                            bins * params_->view().particle.num_particles * sizeof(u32),
+                            cudaMemcpyDeviceToHost));
+}
+
+void CoreState::diagnostics_clear()
+{
+    size_t const np = params_->view().particle.num_particles;
+    if (view_.diag_action_counts)
+        B2_CUDA_CALL(cudaMemsetAsync(
+            view_.diag_action_counts, 0, np * view_.diag_action_bins * sizeof(u32), stream_));
+    if (view_.diag_step_counts)
+        B2_CUDA_CALL(cudaMemsetAsync(
+            view_.diag_step_counts, 0, np * view_.diag_step_bins * sizeof(u32), stream_));
+}
+
+uint64_t CoreState::num_tracks()
+{
+    std::vector<uint32_t> counters(params_->max_events());
+    B2_CUDA_CALL(cudaStreamSynchronize(stream_));
+    B2_CUDA_CALL(cudaMemcpy(counters.data(),
+                            view_.track_counters,
+                            counters.size() * sizeof(uint32_t),
+                            cudaMemcpyDeviceToHost));
+    return std::accumulate(counters.begin(), counters.end(), uint64_t(0));
+}
+
+void CoreState::reset()
+{
+    // reference: CoreState::reset (global/CoreState.cc:144-155): no tracks, no
+    // initializers, every slot vacant
+    uint32_t const n = view_.num_slots;
+    B2_CUDA_CALL(cudaStreamSynchronize(stream_));
+    B2_CUDA_CALL(cudaMemset(view_.status, 0, n));
+    std::vector<uint32_t> seq(n);
+    std::iota(seq.begin(), seq.end(), 0u);
+    B2_CUDA_CALL(cudaMemcpy(view_.vacancies, seq.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    std::vector<uint32_t> ctr(CTR_SIZE, 0);
+    ctr[CTR_NUM_VACANCIES] = n;
+    B2_CUDA_CALL(
+        cudaMemcpy(view_.counters, ctr.data(), CTR_SIZE * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    last_error_ = 0;
+}
 }  // namespace celeritas_b200

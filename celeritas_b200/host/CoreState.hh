@@ -63,6 +63,18 @@ class CoreState
     void calo_get(double* out);
     void calo_clear();
 
+    //! Allocate the [particle][action] tally of the action diagnostic
+    void enable_action_diagnostic(uint32_t num_actions);
+    //! Allocate the [particle][max_bin + 2] tally of the step diagnostic
+    void enable_step_diagnostic(uint32_t max_step_bin);
+    //! Copy a diagnostic tally to the host (synchronises the stream)
+    void diagnostic_get(bool steps, uint32_t* out);
+    void diagnostics_clear();
+    //! Sum of the per-event track-id counters: tracks created since the last reseed
+    uint64_t num_tracks();
+    //! Back to the freshly constructed state (reference: CoreState::reset)
+    void reset();
+
     size_t device_bytes() const { return arena_.bytes(); }
 
   private:

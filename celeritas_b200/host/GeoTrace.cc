@@ -9,14 +9,10 @@
 #include "CoreParams.hh"
 #include "CoreState.hh"
 #include "DeviceMemory.hh"
+#include "Handles.hh"
 
 using namespace celeritas_b200;
 
-// Defined in capi.cc
-struct B200Params
-{
-    std::shared_ptr<CoreParams> params;
-};
 
 extern "C" int b200_geo_trace_host(B200Params const* params,
                                    double const* pos,

@@ -89,7 +89,7 @@ struct Stepper::Staging
 };
 
 //---------------------------------------------------------------------------//
-ActionSequence::ActionSequence(CoreParams const& params)
+ActionSequence::ActionSequence(CoreParams const& params, Options options)
 {
     using Order = StepActionOrder;
     auto const& view = params.view();
@@ -98,8 +98,39 @@ ActionSequence::ActionSequence(CoreParams const& params)
     bool have_interact = false;
     bool have_tally = false;
 
-    for (ActionRecord const& a : params.actions())
+    // Full action table: the problem's actions, then the diagnostics in the order
+    // celer-sim registers them (app/celer-sim/Runner.cc:616-633), then user actions
+    std::vector<ActionRecord> records = params.actions();
+    auto has_label = [&records](std::string const& label) {
+        return std::any_of(records.begin(), records.end(), [&](ActionRecord const& r) {
+            return r.label == label;
+        });
+    };
+    if (options.action_diagnostic && !has_label("action-diagnostic"))
     {
+        records.push_back(
+            {uint32_t(records.size()), "action-diagnostic", static_cast<uint32_t>(Order::post)});
+    }
+    if (options.step_diagnostic_bins && !has_label("step-diagnostic"))
+    {
+        records.push_back(
+            {uint32_t(records.size()), "step-diagnostic", static_cast<uint32_t>(Order::user_post)});
+    }
+    step_diagnostic_bins_ = options.step_diagnostic_bins;
+    for (SPAction const& user : options.user_actions)
+    {
+        if (!user || user->action_id() != records.size())
+            throw std::runtime_error("user action ids must continue the action table");
+        records.push_back({user->action_id(), user->label(), static_cast<uint32_t>(user->order())});
+        actions_.push_back(user);
+    }
+    for (ActionRecord const& r : records)
+        labels_.push_back(r.label);
+
+    for (ActionRecord const& a : records)
+    {
+        if (a.id >= records.size() - options.user_actions.size())
+            break;  // user actions are already in the list
         if (a.order == INVALID)
             continue;  // implicit action: no kernel
         Order order = static_cast<Order>(a.order);
@@ -151,6 +182,18 @@ ActionSequence::ActionSequence(CoreParams const& params)
         {
             act = std::make_shared<KernelAction>(
                 a.id, a.label, order, &b200_step_extend_from_secondaries);
+        }
+        else if (a.label == "action-diagnostic")
+        {
+            act = std::make_shared<KernelAction>(a.id, a.label, order, &b200_step_action_diagnostic);
+            action_diagnostic_ = true;
+        }
+        else if (a.label == "step-diagnostic")
+        {
+            if (step_diagnostic_bins_ == 0)
+                throw std::runtime_error(
+                    "the problem has a step diagnostic: set step_diagnostic_bins");
+            act = std::make_shared<KernelAction>(a.id, a.label, order, &b200_step_step_diagnostic);
         }
         else if (a.label.rfind("step-gather-", 0) == 0)
         {
@@ -237,8 +280,13 @@ Stepper::Stepper(StepperInput input) : params_(std::move(input.params))
 {
     if (!params_)
         throw std::runtime_error("Stepper requires params");
-    actions_ = std::make_shared<ActionSequence>(*params_);
+    actions_ = std::make_shared<ActionSequence>(*params_, std::move(input.actions));
+    actions_->action_times(input.action_times);
     state_ = std::make_unique<CoreState>(params_, input.stream_id, input.num_track_slots);
+    if (actions_->action_diagnostic())
+        state_->enable_action_diagnostic(actions_->labels().size());
+    if (actions_->step_diagnostic_bins())
+        state_->enable_step_diagnostic(actions_->step_diagnostic_bins());
     staging_ = std::make_unique<Staging>();
     last_.num_vacancies = input.num_track_slots;
 }
@@ -369,6 +417,16 @@ void Stepper::warm_up()
 void Stepper::kill_active()
 {
     check_rc(b200_kill_active(pv(*params_), sv(*state_), state_->stream()), "kill_active");
+}
+
+void Stepper::reset_state()
+{
+    state_->reset();
+    staging_->count = 0;
+    events_in_flight_.clear();
+    state_->single_event(INVALID);
+    last_ = {};
+    last_.num_vacancies = state_->size();
 }
 
 void Stepper::reseed(uint64_t event_id)

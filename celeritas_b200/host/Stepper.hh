@@ -62,11 +62,24 @@ class ActionSequence
 {
   public:
     using SPAction = std::shared_ptr<StepActionInterface const>;
+    struct Options
+    {
+        bool action_diagnostic{false};
+        uint32_t step_diagnostic_bins{0};
+        //! Extra user step actions; ids continue the action table
+        std::vector<SPAction> user_actions;
+    };
     //! Build the B200 adapters for every step action in the problem's table
-    explicit ActionSequence(CoreParams const& params);
+    explicit ActionSequence(CoreParams const& params) : ActionSequence(params, Options{}) {}
+    ActionSequence(CoreParams const& params, Options options);
     ~ActionSequence();
     void step(CoreParams const& params, CoreState& state);
     std::vector<SPAction> const& actions() const { return actions_; }
+    //! Labels of ALL actions (explicit and implicit) by action id
+    std::vector<std::string> const& labels() const { return labels_; }
+    bool action_diagnostic() const { return action_diagnostic_; }
+    uint32_t step_diagnostic_bins() const { return step_diagnostic_bins_; }
+    bool action_times() const { return action_times_; }
 
     //! Per-action device timing with CUDA events on the state's stream
     //! (reference option: StepperInput::action_times, ActionSequence.cc:99-121)
@@ -78,6 +91,9 @@ class ActionSequence
 
   private:
     std::vector<SPAction> actions_;
+    std::vector<std::string> labels_;
+    bool action_diagnostic_{false};
+    uint32_t step_diagnostic_bins_{0};
     bool action_times_{false};
     std::vector<double> accum_time_;
     struct Pending
@@ -103,6 +119,8 @@ struct StepperInput
     std::shared_ptr<CoreParams const> params;
     uint32_t stream_id{0};
     uint32_t num_track_slots{0};
+    bool action_times{false};
+    ActionSequence::Options actions;
 };
 
 class Stepper
@@ -116,6 +134,8 @@ class Stepper
     StepperResult operator()(B200Primary const* primaries, uint32_t n);
     void kill_active();
     void reseed(uint64_t event_id);
+    //! Drop all tracks and initializers (reference: Stepper::reset_state)
+    void reset_state();
 
     ActionSequence const& actions() const { return *actions_; }
     ActionSequence& action_sequence() { return *actions_; }

@@ -2,6 +2,7 @@
 // C-ABI (include/celeritas_b200.h) over the host-side objects.
 //---------------------------------------------------------------------------//
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -9,25 +10,12 @@
 #include "../../include/celeritas_b200.h"
 #include "CoreParams.hh"
 #include "CoreState.hh"
+#include "Handles.hh"
 #include "Stepper.hh"
+#include "Transporter.hh"
 
 using namespace celeritas_b200;
 
-struct B200Params
-{
-    std::shared_ptr<CoreParams> params;
-};
-struct B200State
-{
-    std::unique_ptr<CoreState> owned;
-    CoreState* state;
-};
-struct B200Stepper
-{
-    std::unique_ptr<Stepper> stepper;
-    B200State state_handle;
-    uint64_t launches_at_create;
-};
 
 namespace
 {
@@ -54,7 +42,17 @@ int guarded(F&& f)
 }
 }  // namespace
 
+void celeritas_b200::set_last_error(std::string const& message)
+{
+    g_error = message;
+}
+
 extern "C" {
+void b200_string_free(char* s)
+{
+    std::free(s);
+}
+
 char const* b200_last_error(void)
 {
     return g_error.c_str();
@@ -123,6 +121,11 @@ uint32_t b200_params_num_detectors(B200Params const* params)
     return params->params->num_detectors();
 }
 
+uint32_t b200_params_num_particles(B200Params const* params)
+{
+    return params->params->particle_names().size();
+}
+
 uint32_t b200_params_find_particle(B200Params const* params, int pdg)
 {
     return params->params->find_particle(pdg);
@@ -171,25 +174,73 @@ int b200_state_calo_clear(B200State* state)
 }
 
 //---------------------------------------------------------------------------//
-int b200_stepper_create(B200Params const* params,
-                        uint32_t stream_id,
-                        uint32_t num_track_slots,
-                        B200Stepper** out)
+int b200_stepper_create_opts(B200Params const* params,
+                             B200StepperOptions const* options,
+                             B200Stepper** out)
 {
-    if (!params || !out)
+    if (!params || !options || !out)
         return B200_ERR_INVALID_ARGUMENT;
     *out = nullptr;
     return guarded([&] {
         auto s = std::make_unique<B200Stepper>();
         StepperInput inp;
         inp.params = params->params;
-        inp.stream_id = stream_id;
-        inp.num_track_slots = num_track_slots;
-        s->stepper = std::make_unique<Stepper>(std::move(inp));
+        inp.stream_id = options->stream_id;
+        inp.num_track_slots = options->num_track_slots;
+        inp.action_times = options->action_times != 0;
+        inp.actions.action_diagnostic = options->action_diagnostic != 0;
+        inp.actions.step_diagnostic_bins = options->step_diagnostic_bins;
+        s->stepper = std::make_shared<Stepper>(std::move(inp));
         s->state_handle.state = &s->stepper->state();
         s->launches_at_create = b200_launch_count();
         *out = s.release();
     });
+}
+
+int b200_stepper_create(B200Params const* params,
+                        uint32_t stream_id,
+                        uint32_t num_track_slots,
+                        B200Stepper** out)
+{
+    B200StepperOptions options{};
+    options.stream_id = stream_id;
+    options.num_track_slots = num_track_slots;
+    return b200_stepper_create_opts(params, &options, out);
+}
+
+uint32_t b200_stepper_num_actions(B200Stepper const* stepper)
+{
+    return stepper->stepper->actions().labels().size();
+}
+
+char const* b200_stepper_action_label(B200Stepper const* stepper, uint32_t action_id)
+{
+    auto const& labels = stepper->stepper->actions().labels();
+    return action_id < labels.size() ? labels[action_id].c_str() : "";
+}
+
+int b200_stepper_action_diagnostic_get(B200Stepper* stepper, uint32_t* counts)
+{
+    if (!stepper->stepper->actions().action_diagnostic())
+        return B200_ERR_INVALID_ARGUMENT;
+    return guarded([&] { stepper->stepper->state().diagnostic_get(false, counts); });
+}
+
+int b200_stepper_step_diagnostic_get(B200Stepper* stepper, uint32_t* counts)
+{
+    if (!stepper->stepper->actions().step_diagnostic_bins())
+        return B200_ERR_INVALID_ARGUMENT;
+    return guarded([&] { stepper->stepper->state().diagnostic_get(true, counts); });
+}
+
+uint32_t b200_stepper_step_diagnostic_bins(B200Stepper const* stepper)
+{
+    return stepper->stepper->actions().step_diagnostic_bins();
+}
+
+int b200_stepper_diagnostics_clear(B200Stepper* stepper)
+{
+    return guarded([&] { stepper->stepper->state().diagnostics_clear(); });
 }
 
 void b200_stepper_destroy(B200Stepper* stepper)
@@ -277,7 +328,12 @@ int b200_run_events(B200Stepper* handle,
                     uint64_t max_steps,
                     B200RunResult* result)
 {
+    if (!handle || !primaries || !offsets)
+        return B200_ERR_INVALID_ARGUMENT;
     return guarded([&] {
+        TransporterInput tinp;
+        tinp.max_steps = max_steps;
+        Transporter transport(handle->stepper, tinp);
         Stepper& step = *handle->stepper;
         cudaStream_t stream = step.state().stream();
         cudaEvent_t ev0, ev1;
@@ -285,41 +341,27 @@ int b200_run_events(B200Stepper* handle,
         B2_CUDA_CALL(cudaEventCreate(&ev1));
         B200RunResult r{};
         B2_CUDA_CALL(cudaEventRecord(ev0, stream));
-        auto transport = [&](B200Primary const* p, uint32_t n) {
+        auto run = [&](B200Primary const* p, uint32_t n) {
+            step.reseed(p[0].event_id);
+            TransporterResult t = transport(p, n);
             r.num_primaries += n;
-            StepperResult counts = step(p, n);
-            uint64_t local_steps = 0;
-            while (true)
-            {
-                r.num_steps += counts.active;
-                local_steps += counts.active;
-                ++r.num_step_iterations;
-                r.max_queued = std::max<uint64_t>(r.max_queued, counts.queued);
-                if (!counts)
-                    break;
-                if (max_steps && local_steps >= max_steps)
-                {
-                    step.kill_active();
-                    step();
-                    break;
-                }
-                counts = step();
-            }
+            r.num_steps += t.num_steps;
+            r.num_step_iterations += t.num_step_iterations;
+            r.num_tracks += t.num_tracks;
+            r.num_aborted += t.num_aborted;
+            r.max_queued = std::max<uint64_t>(r.max_queued, t.max_queued);
         };
         if (merge_events)
         {
-            step.reseed(primaries[0].event_id);
-            transport(primaries, offsets[num_events]);
+            run(primaries, offsets[num_events]);
         }
         else
         {
             for (uint32_t e = 0; e < num_events; ++e)
             {
                 uint32_t n = offsets[e + 1] - offsets[e];
-                if (n == 0)
-                    continue;
-                step.reseed(primaries[offsets[e]].event_id);
-                transport(primaries + offsets[e], n);
+                if (n != 0)
+                    run(primaries + offsets[e], n);
             }
         }
         B2_CUDA_CALL(cudaEventRecord(ev1, stream));

@@ -30,7 +30,14 @@ class StepperResult(C.Structure):
 class RunResult(C.Structure):
     _fields_ = [('num_steps', C.c_uint64), ('num_step_iterations', C.c_uint64),
                 ('num_primaries', C.c_uint64), ('max_queued', C.c_uint64),
-                ('seconds', C.c_double)]
+                ('seconds', C.c_double), ('num_tracks', C.c_uint64),
+                ('num_aborted', C.c_uint64)]
+
+
+class StepperOptions(C.Structure):
+    _fields_ = [('stream_id', C.c_uint32), ('num_track_slots', C.c_uint32),
+                ('action_times', C.c_int), ('action_diagnostic', C.c_int),
+                ('step_diagnostic_bins', C.c_uint32)]
 
 
 # Every symbol declared in include/celeritas_b200.h
@@ -50,6 +57,12 @@ EXPORTS = [
     'b200_stepper_step_action_label', 'b200_stepper_launch_count', 'b200_run_events',
     'b200_stepper_set_action_times', 'b200_stepper_action_time', 'b200_set_device',
     'b200_geo_trace', 'b200_geo_trace_host',
+    'b200_step_action_diagnostic', 'b200_step_step_diagnostic', 'b200_stepper_create_opts',
+    'b200_stepper_num_actions', 'b200_stepper_action_label',
+    'b200_stepper_action_diagnostic_get', 'b200_stepper_step_diagnostic_get',
+    'b200_stepper_step_diagnostic_bins', 'b200_stepper_diagnostics_clear',
+    'b200_primaries_generate', 'b200_celer_sim_run', 'b200_string_free',
+    'b200_params_num_particles',
 ]
 
 _lib = None
@@ -88,6 +101,8 @@ def load_library():
     L.b200_params_num_detectors.restype = C.c_uint32
     L.b200_params_find_particle.argtypes = [vp, C.c_int]
     L.b200_params_find_particle.restype = C.c_uint32
+    L.b200_params_num_particles.argtypes = [vp]
+    L.b200_params_num_particles.restype = C.c_uint32
     L.b200_state_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]
     L.b200_state_destroy.argtypes = [vp]
     L.b200_state_view.argtypes = [vp]
@@ -117,6 +132,20 @@ def load_library():
     L.b200_geo_trace_host.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp]
     L.b200_run_events.argtypes = [vp, vp, vp, C.c_uint32, C.c_int, C.c_uint64,
                                   C.POINTER(RunResult)]
+    L.b200_stepper_create_opts.argtypes = [vp, C.POINTER(StepperOptions), C.POINTER(vp)]
+    L.b200_stepper_num_actions.argtypes = [vp]
+    L.b200_stepper_num_actions.restype = C.c_uint32
+    L.b200_stepper_action_label.argtypes = [vp, C.c_uint32]
+    L.b200_stepper_action_label.restype = C.c_char_p
+    L.b200_stepper_action_diagnostic_get.argtypes = [vp, vp]
+    L.b200_stepper_step_diagnostic_get.argtypes = [vp, vp]
+    L.b200_stepper_step_diagnostic_bins.argtypes = [vp]
+    L.b200_stepper_step_diagnostic_bins.restype = C.c_uint32
+    L.b200_stepper_diagnostics_clear.argtypes = [vp]
+    L.b200_primaries_generate.argtypes = [vp, C.c_char_p, vp, C.c_uint64,
+                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+    L.b200_celer_sim_run.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.b200_string_free.argtypes = [vp]
     _lib = L
     return L
 
@@ -187,6 +216,24 @@ class Params:
         r = load_library().b200_params_find_particle(self.h, pdg)
         return None if r == 0xffffffff else r
 
+    @property
+    def num_particles(self):
+        return load_library().b200_params_num_particles(self.h)
+
+    def generate_primaries(self, primary_options):
+        """Primaries of a celer-sim `primary_options` dict; returns (primaries, offsets)."""
+        import json
+        L = load_library()
+        text = json.dumps(primary_options).encode()
+        count, per_event = C.c_uint64(), C.c_uint32()
+        _check(L.b200_primaries_generate(self.h, text, None, 0, C.byref(count),
+                                         C.byref(per_event)))
+        out = np.zeros(count.value, dtype=PRIMARY_DTYPE)
+        _check(L.b200_primaries_generate(self.h, text, out.ctypes.data, len(out),
+                                         C.byref(count), C.byref(per_event)))
+        offsets = np.arange(0, len(out) + 1, per_event.value, dtype=np.uint32)
+        return out, offsets
+
     def trace(self, pos, direction, max_segments=64):
         """Ray-trace through the geometry on the GPU.
 
@@ -210,13 +257,42 @@ class Params:
 class Stepper:
     """One stream's stepping loop (reference: Stepper<MemSpace::device>)."""
 
-    def __init__(self, params, num_track_slots, stream_id=0):
+    def __init__(self, params, num_track_slots, stream_id=0, action_times=False,
+                 action_diagnostic=False, step_diagnostic_bins=0):
         L = load_library()
         self.params = params
         self.n = num_track_slots
         h = C.c_void_p()
-        _check(L.b200_stepper_create(params.h, stream_id, num_track_slots, C.byref(h)))
+        opts = StepperOptions(stream_id, num_track_slots, int(action_times),
+                              int(action_diagnostic), step_diagnostic_bins)
+        _check(L.b200_stepper_create_opts(params.h, C.byref(opts), C.byref(h)))
         self.h = h
+
+    @property
+    def all_action_labels(self):
+        """Labels of every action (explicit and implicit) by action id."""
+        L = load_library()
+        return [L.b200_stepper_action_label(self.h, i).decode()
+                for i in range(L.b200_stepper_num_actions(self.h))]
+
+    def action_diagnostic(self):
+        """counts[particle][action] of the post-step action of every track-step."""
+        L = load_library()
+        out = np.zeros((self.params.num_particles, L.b200_stepper_num_actions(self.h)),
+                       dtype=np.uint32)
+        _check(L.b200_stepper_action_diagnostic_get(self.h, out.ctypes.data))
+        return out
+
+    def step_diagnostic(self):
+        """counts[particle][num_steps] of the steps every killed track took."""
+        L = load_library()
+        out = np.zeros((self.params.num_particles,
+                        L.b200_stepper_step_diagnostic_bins(self.h) + 2), dtype=np.uint32)
+        _check(L.b200_stepper_step_diagnostic_get(self.h, out.ctypes.data))
+        return out
+
+    def diagnostics_clear(self):
+        _check(load_library().b200_stepper_diagnostics_clear(self.h))
 
     def __del__(self):
         try:
@@ -291,7 +367,21 @@ class Stepper:
                                  len(offsets) - 1, int(merge_events), max_steps, C.byref(r)))
         return dict(num_steps=int(r.num_steps), num_step_iterations=int(r.num_step_iterations),
                     num_primaries=int(r.num_primaries), max_queued=int(r.max_queued),
-                    seconds=r.seconds)
+                    seconds=r.seconds, num_tracks=int(r.num_tracks),
+                    num_aborted=int(r.num_aborted))
+
+
+def celer_sim_run(run_input):
+    """Run a celer-sim input (dict or JSON text) and return the report as a dict."""
+    import json
+    L = load_library()
+    text = run_input if isinstance(run_input, str) else json.dumps(run_input)
+    report = C.c_void_p()
+    _check(L.b200_celer_sim_run(text.encode(), C.byref(report)))
+    try:
+        return json.loads(C.string_at(report).decode())
+    finally:
+        L.b200_string_free(report)
 
 
 def make_primaries(n, particle_id=0, energy=100.0, pos=(0, 0, 0), direction=(1, 0, 0),

@@ -84,7 +84,20 @@ typedef struct B200RunResult
     uint64_t num_primaries;
     uint64_t max_queued;
     double seconds;               /* device time of the transport loop */
+    uint64_t num_tracks;          /* tracks created (sum of the per-event track counters) */
+    uint64_t num_aborted;         /* alive + queued tracks left when max_steps was hit */
 } B200RunResult;
+
+/* Stepper construction options (reference: StepperInput, Stepper.hh:42-54, plus the
+ * celer-sim diagnostics of app/celer-sim/Runner.cc:616-633). */
+typedef struct B200StepperOptions
+{
+    uint32_t stream_id;
+    uint32_t num_track_slots;
+    int action_times;              /* time every action with CUDA events */
+    int action_diagnostic;         /* add an ActionDiagnostic unless the problem has one */
+    uint32_t step_diagnostic_bins; /* >0: add a StepDiagnostic with this 'max' bin */
+} B200StepperOptions;
 
 /* Opaque views holding device pointers (layout: celeritas_b200/csrc/views.cuh). */
 typedef struct B200ParamsView B200ParamsView;
@@ -109,6 +122,7 @@ uint32_t b200_params_num_volumes(B200Params const* params);
 char const* b200_params_volume_label(B200Params const* params, uint32_t volume_id);
 uint32_t b200_params_num_detectors(B200Params const* params);
 uint32_t b200_params_find_particle(B200Params const* params, int pdg); /* 0xffffffff if absent */
+uint32_t b200_params_num_particles(B200Params const* params);
 
 /*--- per-stream state -------------------------------------------------------*/
 int b200_state_create(B200Params const* params,
@@ -141,6 +155,11 @@ int b200_step_boundary(B200ParamsView const*, B200StateView const*, cudaStream_t
 int b200_step_tracking_cut(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_step_tally(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_step_extend_from_secondaries(B200ParamsView const*, B200StateView const*, cudaStream_t);
+/* ActionDiagnostic (user/detail/ActionDiagnosticExecutor.hh:30-65, order post) and
+ * StepDiagnostic (user/detail/StepDiagnosticExecutor.hh:28-60, order user_post); the
+ * state must have been created with the diagnostic enabled (B200StepperOptions). */
+int b200_step_action_diagnostic(B200ParamsView const*, B200StateView const*, cudaStream_t);
+int b200_step_step_diagnostic(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_reseed(B200ParamsView const*, B200StateView const*, uint64_t event_id, cudaStream_t);
 int b200_reset_generated(B200StateView const*, cudaStream_t);
 int b200_kill_active(B200ParamsView const*, B200StateView const*, cudaStream_t);
@@ -183,8 +202,20 @@ int b200_stepper_create(B200Params const* params,
                         uint32_t stream_id,
                         uint32_t num_track_slots,
                         B200Stepper** out);
+int b200_stepper_create_opts(B200Params const* params,
+                             B200StepperOptions const* options,
+                             B200Stepper** out);
 void b200_stepper_destroy(B200Stepper* stepper);
 B200State* b200_stepper_state(B200Stepper* stepper);
+/* Diagnostic tallies: counts[particle][bin]. Action diagnostic: bin = action id, num_bins
+ * = b200_stepper_num_actions(); step diagnostic: num_bins = step_diagnostic_bins + 2.
+ * Returns B200_ERR_INVALID_ARGUMENT if the diagnostic is not enabled. */
+uint32_t b200_stepper_num_actions(B200Stepper const* stepper);
+char const* b200_stepper_action_label(B200Stepper const* stepper, uint32_t action_id);
+int b200_stepper_action_diagnostic_get(B200Stepper* stepper, uint32_t* counts);
+int b200_stepper_step_diagnostic_get(B200Stepper* stepper, uint32_t* counts);
+uint32_t b200_stepper_step_diagnostic_bins(B200Stepper const* stepper);
+int b200_stepper_diagnostics_clear(B200Stepper* stepper);
 /* One step iteration; host primaries may be NULL/0. Synchronises to read counters. */
 int b200_stepper_step(B200Stepper* stepper,
                       B200Primary const* primaries,
@@ -205,7 +236,9 @@ int b200_set_device(int device);
 uint64_t b200_stepper_launch_count(B200Stepper const* stepper);
 
 /*--- whole events (celer-sim Transporter loop) -------------------------------*/
-/* Event e owns primaries [offsets[e], offsets[e+1]); host buffers. */
+/* Event e owns primaries [offsets[e], offsets[e+1]); host buffers. max_steps limits the
+ * step ITERATIONS per transport call as in app/celer-sim/Transporter.cc:133-141
+ * (0: unlimited); tracks left over are counted in num_aborted and the state is reset. */
 int b200_run_events(B200Stepper* stepper,
                     B200Primary const* primaries,
                     uint32_t const* offsets,
@@ -213,6 +246,25 @@ int b200_run_events(B200Stepper* stepper,
                     int merge_events,
                     uint64_t max_steps,
                     B200RunResult* result);
+
+/*--- celer-sim front end ------------------------------------------------------*/
+/* Primaries from a celer-sim "primary_options" JSON object (reference:
+ * celeritas/phys/PrimaryGenerator.cc:30-110, PrimaryGeneratorOptionsIO.json.cc): same
+ * std::mt19937 stream, same sampling order, so the primaries are identical to the
+ * reference's. `out` receives num_events * primaries_per_event records (query the count
+ * with out == NULL). */
+int b200_primaries_generate(B200Params const* params,
+                            char const* primary_options_json,
+                            B200Primary* out,
+                            uint64_t capacity,
+                            uint64_t* count,
+                            uint32_t* primaries_per_event);
+/* Run a celer-sim input (app/celer-sim/RunnerInputIO.json.cc:40-139; the problem comes
+ * from "image_file") and write the celer-sim-style JSON report
+ * (app/celer-sim/RunnerOutput.cc:37-115, plus the diagnostics' and SimpleCalo's output)
+ * into a newly allocated string: release it with b200_string_free(). */
+int b200_celer_sim_run(char const* input_json, char** report);
+void b200_string_free(char* s);
 
 #ifdef __cplusplus
 }

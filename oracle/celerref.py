@@ -51,6 +51,12 @@ def lib():
         L.celerref_geo_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                          C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]
+        L.celerref_diagnostic_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p,
+                                              C.POINTER(C.c_uint32)]
+        L.celerref_num_particles.argtypes = [C.c_void_p]
+        L.celerref_action_labels.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32]
+        L.celerref_generate_primaries.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p,
+                                                  C.c_uint64, C.POINTER(C.c_uint64)]
         L.celerref_run_events.restype = C.c_double
         L.celerref_run_events.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                           C.c_uint32, C.c_int, C.c_void_p]
@@ -112,6 +118,29 @@ class Problem:
                                         dist.ctypes.data, count.ctypes.data,
                                         safety.ctypes.data))
         return vol, surf, dist, count, safety
+
+    def diagnostic(self, steps=False):
+        """ActionDiagnostic (steps=False) or StepDiagnostic tallies: counts[particle][bin]."""
+        nb = C.c_uint32()
+        _check(lib().celerref_diagnostic_get(self.h, int(steps), None, C.byref(nb)))
+        out = np.zeros((lib().celerref_num_particles(self.h), nb.value), dtype=np.uint32)
+        _check(lib().celerref_diagnostic_get(self.h, int(steps), out.ctypes.data, C.byref(nb)))
+        return out
+
+    def action_labels(self):
+        buf = C.create_string_buffer(1 << 16)
+        _check(lib().celerref_action_labels(self.h, buf, len(buf)))
+        return buf.value.decode().split('\n')[:-1]
+
+    def generate_primaries(self, primary_options):
+        """The reference's PrimaryGenerator on celer-sim `primary_options`."""
+        text = json.dumps(primary_options).encode()
+        count = C.c_uint64()
+        _check(lib().celerref_generate_primaries(self.h, text, None, 0, C.byref(count)))
+        out = np.zeros(count.value, dtype=PRIMARY_DTYPE)
+        _check(lib().celerref_generate_primaries(self.h, text, out.ctypes.data, len(out),
+                                                 C.byref(count)))
+        return out
 
     def run_events(self, primaries, offsets, num_track_slots, num_threads=0):
         primaries = np.ascontiguousarray(primaries, dtype=PRIMARY_DTYPE)

@@ -570,6 +570,18 @@ std::unique_ptr<Problem> build_problem(json const& config)
             p->core->aux_reg().get(),
             p->core->action_reg().get());
     }
+    // Diagnostics as celer-sim adds them (app/celer-sim/Runner.cc:616-633); registered
+    // after the step collector so that the other action ids stay those of the
+    // diagnostic-free problem
+    if (cfg.value("action_diagnostic", false))
+    {
+        p->action_diag = ActionDiagnostic::make_and_insert(*p->core);
+    }
+    if (cfg.value("step_diagnostic_bins", 0) > 0)
+    {
+        p->step_diag = StepDiagnostic::make_and_insert(
+            *p->core, cfg.at("step_diagnostic_bins").get<size_type>());
+    }
     return p;
 }
 }  // namespace celerref

@@ -20,7 +20,9 @@
 #include "orange/OrangeParams.hh"
 #include "celeritas/global/CoreParams.hh"
 #include "celeritas/io/ImportData.hh"
+#include "celeritas/user/ActionDiagnostic.hh"
 #include "celeritas/user/SimpleCalo.hh"
+#include "celeritas/user/StepDiagnostic.hh"
 #include "celeritas/user/StepCollector.hh"
 
 namespace celerref
@@ -35,6 +37,9 @@ struct Problem
     std::shared_ptr<celeritas::SimpleCalo> calo;
     std::shared_ptr<celeritas::StepCollector> collector;
     std::vector<std::string> calo_volumes;
+    //! celer-sim diagnostics ("action_diagnostic": true, "step_diagnostic_bins": N)
+    std::shared_ptr<celeritas::ActionDiagnostic> action_diag;
+    std::shared_ptr<celeritas::StepDiagnostic> step_diag;
     std::shared_ptr<celeritas::UrbanMscParams const> msc;
     std::shared_ptr<celeritas::FluctuationParams const> fluct;
     celeritas::UniformFieldParams field;

@@ -20,7 +20,11 @@
 #include "celeritas/geo/GeoTrackView.hh"
 #include "celeritas/global/CoreState.hh"
 #include "celeritas/global/Stepper.hh"
+#include "celeritas/phys/ParticleParams.hh"
 #include "celeritas/phys/Primary.hh"
+#include "celeritas/phys/PrimaryGenerator.hh"
+#include "celeritas/phys/PrimaryGeneratorOptions.hh"
+#include "celeritas/phys/PrimaryGeneratorOptionsIO.json.hh"
 #include "celeritas/random/RngEngine.hh"
 
 #include "Problem.hh"
@@ -294,6 +298,93 @@ int celerref_calo_clear(void* problem)
  * is not tracked by the reference; primaries only), max_queued}; returns wall
  * seconds of the transport loop (setup and one warm-up step excluded).
  */
+// Diagnostic tallies summed over streams: counts[particle][bin]; *num_bins = bins per
+// particle. `out` may be null to query the size.
+int celerref_diagnostic_get(void* problem, int steps, uint32_t* out, uint32_t* num_bins)
+{
+    return guarded([&] {
+        auto* p = static_cast<celerref::Problem*>(problem);
+        std::vector<std::vector<size_type>> counts;
+        if (steps)
+        {
+            CELER_VALIDATE(p->step_diag, << "no step diagnostic");
+            counts = p->step_diag->calc_steps();
+        }
+        else
+        {
+            CELER_VALIDATE(p->action_diag, << "no action diagnostic");
+            counts = p->action_diag->calc_actions();
+        }
+        *num_bins = counts.empty() ? 0 : counts.front().size();
+        if (out)
+        {
+            for (auto const& row : counts)
+                out = std::copy(row.begin(), row.end(), out);
+        }
+    });
+}
+
+int celerref_num_particles(void* problem)
+{
+    auto* p = static_cast<celerref::Problem*>(problem);
+    return p->core->particle()->size();
+}
+
+// Action labels by id, newline separated
+int celerref_action_labels(void* problem, char* out, uint32_t capacity)
+{
+    return guarded([&] {
+        auto* p = static_cast<celerref::Problem*>(problem);
+        std::string text;
+        auto const& reg = *p->core->action_reg();
+        for (auto i : range(ActionId{reg.num_actions()}))
+        {
+            text += reg.id_to_label(i);
+            text += '\n';
+        }
+        CELER_VALIDATE(text.size() < capacity, << "buffer too small");
+        std::copy(text.begin(), text.end(), out);
+        out[text.size()] = 0;
+    });
+}
+
+// Primaries from celer-sim "primary_options" JSON with the reference's PrimaryGenerator
+int celerref_generate_primaries(void* problem,
+                                char const* options_json,
+                                CPrimary* out,
+                                uint64_t capacity,
+                                uint64_t* count)
+{
+    return guarded([&] {
+        auto* p = static_cast<celerref::Problem*>(problem);
+        PrimaryGeneratorOptions opts;
+        nlohmann::json::parse(options_json).get_to(opts);
+        auto generate = PrimaryGenerator::from_options(p->core->particle(), opts);
+        uint64_t n = 0;
+        for (auto event = generate(); !event.empty(); event = generate())
+        {
+            for (Primary const& pr : event)
+            {
+                if (out && n < capacity)
+                {
+                    CPrimary& c = out[n];
+                    c.particle_id = pr.particle_id.unchecked_get();
+                    c.event_id = pr.event_id.unchecked_get();
+                    c.energy = pr.energy.value();
+                    for (int k = 0; k < 3; ++k)
+                    {
+                        c.pos[k] = pr.position[k];
+                        c.dir[k] = pr.direction[k];
+                    }
+                    c.time = pr.time;
+                }
+                ++n;
+            }
+        }
+        *count = n;
+    });
+}
+
 double celerref_run_events(void* problem,
                            CPrimary const* primaries,
                            uint32_t const* offsets,
