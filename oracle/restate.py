@@ -116,6 +116,44 @@ def canonical_std(rng):
     return ret
 
 
+def generate_primaries(options, particle_ids):
+    """PrimaryGenerator::operator() over all events (phys/PrimaryGenerator.cc:84-108,
+    PrimaryGeneratorOptions.cc:74-140): one mt19937(seed); per primary the position (box:
+    x, y, z uniform) and then the direction (isotropic: costheta in [-1, 1), phi in
+    [0, 2pi)) are sampled; particle = pdg[i % len(pdg)]. Returns a list of dicts."""
+    rng = Mt19937(options.get('seed', 0))
+
+    def uniform(a, b):
+        # UniformRealDistribution.hh:71-77: fma(b - a, canonical, a)
+        return _fma_exact(b - a, canonical_std(rng), a)
+
+    def spec(value, scalar=False):
+        if isinstance(value, dict):
+            return value['distribution'], list(value.get('params', []))
+        return 'delta', [value] if scalar else list(value)
+
+    (edist, eparams) = spec(options['energy'], scalar=True)
+    (pdist, pparams) = spec(options['position'])
+    (ddist, dparams) = spec(options['direction'])
+    assert edist == 'delta' and pdist in ('delta', 'box') and ddist in ('delta', 'isotropic')
+    out = []
+    for event in range(options['num_events']):
+        for i in range(options['primaries_per_event']):
+            if pdist == 'delta':
+                pos = list(pparams)
+            else:
+                pos = [uniform(pparams[k], pparams[3 + k]) for k in range(3)]
+            if ddist == 'delta':
+                direction = list(dparams)
+            else:
+                costheta = uniform(-1.0, 1.0)
+                phi = uniform(0.0, 2 * math.pi)
+                direction = from_spherical(costheta, phi)
+            out.append(dict(particle_id=particle_ids[i % len(particle_ids)], event_id=event,
+                            energy=eparams[0], pos=pos, dir=direction, time=0.0))
+    return out
+
+
 def initial_xorwow_states(seed, stream, n):
     """initialize_xorwow: n states of 6 words from mt19937(seed_seq{seed[, stream]})."""
     seeds = [seed] if stream == 0 else [seed, stream]

@@ -121,3 +121,37 @@ def test_two_rank_reduction_gloo(tmp_path):
                         '29531', str(script)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert 'OK [0, 1, 2, 3, 4]' in r.stdout
+
+
+def test_celer_sim_input_validation_without_gpu():
+    """RunnerInput parsing and validation (app/celer-sim/RunnerInputIO.json.cc:40-139)
+    happen before any device work, so the error paths are testable on CPU; a valid input
+    then fails loudly for want of a device rather than falling back."""
+    import celeritas_b200 as cb
+    prim = {'seed': 0, 'pdg': 11, 'num_events': 1, 'primaries_per_event': 1, 'energy': 1.0,
+            'position': [0, 0, 0], 'direction': [1, 0, 0]}
+    base = {'use_device': True, 'image_file': data_path('images', 'testem3-small.b2img'),
+            'geometry_file': 'x', 'primary_options': prim, 'num_track_slots': 64,
+            'initializer_capacity': 1024, 'secondary_stack_factor': 3}
+    cases = [({'primary_options': None}, 'either a event filename or options'),
+             ({'event_file': 'events.hepmc3'}, 'but not both'),
+             ({'secondary_stack_factor': None}, 'secondary_stack_factor'),
+             ({'geometry_file': None}, 'geometry_file'),
+             ({'use_device': False}, 'no host track loop'),
+             ({'max_steps': 0}, 'nonpositive max_steps'),
+             ({'track_order': 'reindex_both_action'}, 'track_order'),
+             ({'mctruth_file': 'out.root'}, 'outside the scope'),
+             ({'_format': 'other'}, 'invalid format')]
+    for change, fragment in cases:
+        inp = dict(base)
+        for k, v in change.items():
+            if v is None:
+                inp.pop(k)
+            else:
+                inp[k] = v
+        with pytest.raises(cb.B200Error) as err:
+            cb.celer_sim_run(inp)
+        assert fragment in str(err.value), (change, str(err.value))
+    if cb.device_count() == 0:
+        with pytest.raises(cb.B200Error):
+            cb.celer_sim_run(base)

@@ -189,3 +189,51 @@ def test_ref_first_mfp_draw_matches_restatement():
         mfp = -math.log(r.canonical())
         # mfp after the first step = mfp - step * xs (TrackUpdater)
         assert mfp0[slot] == pytest.approx(mfp - step_len[slot] * xs[slot], rel=1e-14)
+
+
+PRIMARY_OPTIONS = {
+    '_format': 'primary-generator', 'seed': 12345, 'pdg': [11, 22, -11],
+    'num_events': 5, 'primaries_per_event': 7,
+    'energy': {'distribution': 'delta', 'params': [150.0]},
+    'position': {'distribution': 'box', 'params': [-22, -5, -5, -21, 5, 5]},
+    'direction': {'distribution': 'isotropic'},
+}
+
+
+def test_primary_generator_restatement_properties():
+    """test/celeritas/phys/PrimaryGenerator.test.cc:56-132: particle/event id pattern,
+    box bounds and unit directions."""
+    opts = dict(PRIMARY_OPTIONS, pdg=[22, 11], num_events=2, primaries_per_event=3,
+                energy=10.0, position=[1, 2, 3], seed=0)
+    prim = restate.generate_primaries(opts, [0, 1])
+    assert [p['particle_id'] for p in prim] == [0, 1, 0, 0, 1, 0]
+    assert [p['event_id'] for p in prim] == [0, 0, 0, 1, 1, 1]
+    assert all(p['energy'] == 10 and p['pos'] == [1, 2, 3] and p['time'] == 0 for p in prim)
+    opts = dict(PRIMARY_OPTIONS, pdg=[22], num_events=1, primaries_per_event=10, energy=1.0,
+                position={'distribution': 'box', 'params': [-3, -3, -3, 3, 3, 3]}, seed=0)
+    for p in restate.generate_primaries(opts, [0]):
+        assert all(-3 <= x <= 3 for x in p['pos'])
+        assert abs(sum(x * x for x in p['dir']) - 1) < 1e-14
+
+
+@needs_ref
+def test_ref_primary_generator_matches_restatement():
+    """The reference's PrimaryGenerator (compiled from its sources) vs the restatement:
+    identical doubles (the same mt19937 stream and the same arithmetic)."""
+    import json
+    cfg = json.load(open(data_path('images', 'testem3-small.json')))
+    refp = celerref.Problem(cfg)
+    for opts in (PRIMARY_OPTIONS, dict(PRIMARY_OPTIONS, seed=2**31 + 7, num_events=40)):
+        got = refp.generate_primaries(opts)
+        ids = [{11: 0, 22: 1, -11: 2}[p] for p in opts['pdg']]
+        # particle ids of this problem: e-, gamma, e+ in the order of the image
+        want = restate.generate_primaries(opts, ids)
+        assert len(got) == len(want)
+        pid_of = {}
+        for g, w in zip(got, want):
+            pid_of.setdefault(w['particle_id'], int(g['particle_id']))
+            assert pid_of[w['particle_id']] == int(g['particle_id'])
+            assert int(g['event_id']) == w['event_id']
+            assert float(g['energy']) == w['energy']
+            assert g['pos'].tolist() == w['pos']
+            assert g['dir'].tolist() == w['dir']
