@@ -35,6 +35,7 @@ NUM_EVENTS = 100
 PRIMARIES_PER_EVENT = 100
 ENERGY_MEV = 1000.0
 NUM_TRACK_SLOTS = 1 << 20
+NUM_STREAMS = 1
 ALG_BYTES_PER_TRACK_STEP = 672  # 2 * S_live, D=1, P=4
 
 
@@ -159,6 +160,8 @@ def main():
     ap.add_argument('--primaries-per-event', type=int, default=PRIMARIES_PER_EVENT)
     ap.add_argument('--slots', type=int, default=NUM_TRACK_SLOTS)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--streams', type=int, default=NUM_STREAMS,
+                    help='concurrent steppers (CUDA streams) per GPU; slots are divided among them')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -181,7 +184,12 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
     params = cb.Params(IMAGE)
-    stepper = cb.Stepper(params, args.slots, stream_id=rank)
+    nstreams = max(args.streams, 1)
+    steppers = [cb.Stepper(params, args.slots // nstreams, stream_id=rank * nstreams + k)
+                for k in range(nstreams)]
+    # per-action timing (roofline leg) is taken on one stream holding the whole workload
+    stepper = steppers[0] if nstreams == 1 else cb.Stepper(params, args.slots,
+                                                           stream_id=rank * nstreams)
     electron = params.find_particle(11)
     ndet = params.num_detectors
     # Events are sharded by rank: rank r owns global events [r*E, (r+1)*E)
@@ -195,12 +203,21 @@ def main():
         torch.cuda.synchronize()
 
     def one_pass():
-        stepper.calo_clear()
-        return stepper.run_events(prim, offsets, merge_events=True)
+        for st in steppers:
+            st.calo_clear()
+        if nstreams == 1:
+            return steppers[0].run_events(prim, offsets, merge_events=True)
+        per_stream, seconds = cb.run_events_streams(steppers, prim, offsets, merge_events=True)
+        r = {k: sum(x[k] for x in per_stream)
+             for k in ('num_steps', 'num_primaries', 'num_tracks', 'num_aborted')}
+        # the longest stream sets the number of step iterations of the pass
+        r['num_step_iterations'] = max(x['num_step_iterations'] for x in per_stream)
+        r['seconds'] = seconds
+        return r
 
     def reduce_tallies(r):
         """End-of-run reduction of tallies and counters over NVLink (NCCL)."""
-        calo = torch.from_numpy(stepper.calo()).cuda()
+        calo = torch.from_numpy(sum(st.calo() for st in steppers)).cuda()
         counts = torch.tensor([r['num_steps'], r['num_step_iterations'], r['num_primaries']],
                               dtype=torch.int64, device='cuda')
         if dist is not None:
@@ -239,7 +256,8 @@ def main():
     # ---- timed region 2: per-action CUDA-event timing for the roofline of the top kernel
     stepper.set_action_times(True)
     before = stepper.action_times
-    r2 = one_pass()
+    stepper.calo_clear()
+    r2 = stepper.run_events(prim, offsets, merge_events=True)
     after = stepper.action_times
     stepper.set_action_times(False)
     per_action = {k: after[k] - before.get(k, 0.0) for k in after}
@@ -261,9 +279,10 @@ def main():
         'ms_per_step': 1e3 * dsecs / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': 'TestEm3 full EM (Urban MSC + eloss fluctuations), %d x %d 1 GeV e- '
-                               'primaries per GPU, merged events, %d track slots; steel/lAr '
-                               'stand-in physics (tools/make_physics.py)'
-                               % (args.events, args.primaries_per_event, args.slots),
+                               'primaries per GPU, merged events, %d track slots over %d '
+                               'concurrent stream(s); steel/lAr stand-in physics '
+                               '(tools/make_physics.py)'
+                               % (args.events, args.primaries_per_event, args.slots, nstreams),
                    'l2': 'working set %.0f MB of SoA state per pass exceeds the 126 MB L2'
                          % (args.slots * 336 / 1e6),
                    'parallelism': 'events sharded by rank, NCCL all-reduce of tallies'},

@@ -1005,15 +1005,78 @@ B2_D void update_track(ParamsView const& p, StateView const& s, u32 slot)
     s.num_steps[slot] += 1;
 }
 
+//---------------------------------------------------------------------------//
+// The charged along-step in four phases, one kernel each (the reference's along-step is
+// the same sequence of appliers: global/alongstep/detail/AlongStepImpl / AlongStep.hh:
+// 50-58). Everything passed between phases already lives in the per-slot state
+// (step_length, post_step_action, msc_{true,geom}_path, msc_alpha, msc_is_displaced), so
+// the split changes no result. Smaller kernels need fewer registers (more resident warps
+// to hide the latency-bound chains) and keep warps convergent within a phase.
+//---------------------------------------------------------------------------//
+//! Phase 1: MSC step limit (msc_geom_path = 0 marks "MSC not applied this step")
+B2_D void along_phase_msc_limit(ParamsView const& p, StateView const& s, u32 slot)
+{
+    Particle particle = load_particle(p, s, slot);
+    if (msc_is_applicable(p, s, slot, particle, s.step_length[slot]))
+    {
+        GeoTrack geo(p, s, slot);
+        PhysTrack phys(p, particle.id, s.material_id[slot]);
+        msc_limit_step(p, s, slot, particle, phys, geo);
+    }
+    else
+    {
+        s.msc_geom_path[slot] = 0;
+    }
+}
+
+//! Phase 2: propagation through the geometry. FIELD is a property of the problem (the
+//! along-step action it was built with), so it selects the kernel at launch.
+template<bool FIELD>
+B2_D void along_phase_propagate(ParamsView const& p, StateView const& s, u32 slot)
+{
+    if (s.step_length[slot] == 0)
+        return;
+    Particle particle = load_particle(p, s, slot);
+    GeoTrack geo(p, s, slot);
+    Propagation pr;
+    if constexpr (FIELD)
+        pr = propagate_field(p, particle, geo, s.step_length[slot]);
+    else
+        pr = propagate_linear(geo, s.step_length[slot]);
+    apply_propagation(p, s, slot, pr, FIELD, particle);
+}
+
+//! Phase 3: MSC scattering and displacement
+B2_D void along_phase_msc_apply(ParamsView const& p, StateView const& s, u32 slot)
+{
+    if (!(s.msc_geom_path[slot] > 0))
+        return;
+    Particle particle = load_particle(p, s, slot);
+    GeoTrack geo(p, s, slot);
+    PhysTrack phys(p, particle.id, s.material_id[slot]);
+    msc_apply_step(p, s, slot, particle, phys, geo);
+}
+
+//! Phase 4: time, energy loss, track bookkeeping
+B2_D void along_phase_finish(ParamsView const& p, StateView const& s, u32 slot)
+{
+    Particle particle = load_particle(p, s, slot);
+    PhysTrack phys(p, particle.id, s.material_id[slot]);
+    update_time(s, slot, particle);
+    apply_eloss(p, s, slot, phys);
+    update_track(p, s, slot);
+}
+
 //! Whole along-step for one alive track. CHARGED is a compile-time property of the
 //! launch (dense per-charge slot lists), so the neutral kernel carries no msc/eloss code.
-template<bool CHARGED>
+template<bool CHARGED, bool FIELD>
 B2_D void along_step(ParamsView const& p, StateView const& s, u32 slot)
 {
     Particle particle = load_particle(p, s, slot);
     GeoTrack geo(p, s, slot);
     PhysTrack phys(p, particle.id, s.material_id[slot]);
     constexpr bool charged = CHARGED;
+    constexpr bool use_field = CHARGED && FIELD;
 
     // msc step limit
     bool use_msc = false;
@@ -1032,9 +1095,11 @@ B2_D void along_step(ParamsView const& p, StateView const& s, u32 slot)
     // propagation
     if (s.step_length[slot] != 0)
     {
-        bool const use_field = charged && p.model.field.enabled;
-        Propagation pr = use_field ? propagate_field(p, particle, geo, s.step_length[slot])
-                                   : propagate_linear(geo, s.step_length[slot]);
+        Propagation pr;
+        if constexpr (use_field)
+            pr = propagate_field(p, particle, geo, s.step_length[slot]);
+        else
+            pr = propagate_linear(geo, s.step_length[slot]);
         apply_propagation(p, s, slot, pr, use_field, particle);
     }
     if (charged)

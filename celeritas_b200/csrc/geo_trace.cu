@@ -14,8 +14,8 @@
 
 namespace b200
 {
-__global__ void k_geo_trace(ParamsView const p,
-                            StateView s,
+__global__ void k_geo_trace(B2_GRID_CONSTANT ParamsView const p,
+                            B2_GRID_CONSTANT StateView const s,
                             real const* __restrict__ pos,
                             real const* __restrict__ dir,
                             u32 num_rays,

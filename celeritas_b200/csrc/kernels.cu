@@ -33,7 +33,19 @@ namespace b200
 {
 constexpr int BLOCK = 128;
 #ifndef B2_ALONG_MIN_BLOCKS
-#    define B2_ALONG_MIN_BLOCKS 4
+#    define B2_ALONG_MIN_BLOCKS 8
+#endif
+// Resident blocks per SM asked of the fused whole-step kernel (small iterations)
+#ifndef B2_FUSED_MIN_BLOCKS
+#    define B2_FUSED_MIN_BLOCKS 2
+#endif
+// Resident blocks per SM asked of the phase kernels of the split charged along-step
+#ifndef B2_PHASE_MIN_BLOCKS
+#    define B2_PHASE_MIN_BLOCKS 6
+#endif
+// Charged tracks from which the along-step runs as four phase kernels (0 = never)
+#ifndef B2_ALONG_SPLIT_THRESHOLD
+#    define B2_ALONG_SPLIT_THRESHOLD 8192
 #endif
 constexpr int ALONG_MIN_BLOCKS = B2_ALONG_MIN_BLOCKS;
 
@@ -108,7 +120,7 @@ __global__ void k_primaries_finalize(StateView s,
 // start: initialize tracks in vacant slots
 // (track/detail/InitTracksExecutor.hh:71-175)
 //---------------------------------------------------------------------------//
-__global__ void __launch_bounds__(BLOCK) k_initialize_tracks(ParamsView const p, StateView s)
+__global__ void __launch_bounds__(BLOCK) k_initialize_tracks(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 tid = thread_id();
     u32 const num_init = s.counters[CTR_NUM_INITIALIZERS];
@@ -195,6 +207,8 @@ __global__ void k_initialize_finalize(StateView s)
     s.counters[CTR_NUM_VACANCIES] = num_vac - num_new;
     s.counters[CTR_NUM_ACTIVE] = s.num_slots - (num_vac - num_new);
     s.counters[CTR_NUM_NEW_TRACKS] = num_new;
+    // recomputed by this step's end pass (atomicMin over the blocks that hold tracks)
+    s.counters[CTR_FIRST_BUSY_BLOCK] = INVALID;
     // whole-run tallies kept on the device: track-steps and step iterations
     s.step_counters[0] += s.num_slots - (num_vac - num_new);
     s.step_counters[1] += 1;
@@ -203,11 +217,8 @@ __global__ void k_initialize_finalize(StateView s)
 //---------------------------------------------------------------------------//
 // pre: physics step limits (phys/detail/PreStepExecutor.hh:45-115)
 //---------------------------------------------------------------------------//
-__global__ void __launch_bounds__(BLOCK) k_pre_step(ParamsView const p, StateView s)
+B2_D void do_pre_step(ParamsView const& p, StateView const& s, u32 slot)
 {
-    u32 slot = active_slot(s, thread_id());
-    if (slot == INVALID)
-        return;
     u8 status = s.status[slot];
     s.energy_deposition[slot] = 0;
     for (int i = 0; i < MAX_SECONDARIES; ++i)
@@ -239,10 +250,18 @@ __global__ void __launch_bounds__(BLOCK) k_pre_step(ParamsView const p, StateVie
     }
 }
 
+__global__ void __launch_bounds__(BLOCK) k_pre_step(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
+{
+    u32 slot = active_slot(s, thread_id());
+    if (slot != INVALID)
+        do_pre_step(p, s, slot);
+}
+
 //---------------------------------------------------------------------------//
 // along-step: one launch per charge class over its dense list
 //---------------------------------------------------------------------------//
-__global__ void __launch_bounds__(BLOCK, ALONG_MIN_BLOCKS) k_along_step_charged(ParamsView const p, StateView s)
+template<bool FIELD>
+__global__ void __launch_bounds__(BLOCK, ALONG_MIN_BLOCKS) k_along_step_charged(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 tid = thread_id();
     if (tid >= s.counters[CTR_NUM_CHARGED])
@@ -250,10 +269,31 @@ __global__ void __launch_bounds__(BLOCK, ALONG_MIN_BLOCKS) k_along_step_charged(
     u32 slot = s.track_slots[tid];
     if (s.status[slot] != ST_ALIVE)
         return;
-    along_step<true>(p, s, slot);
+    along_step<true, FIELD>(p, s, slot);
 }
 
-__global__ void __launch_bounds__(BLOCK) k_along_step_neutral(ParamsView const p, StateView s)
+// The same charged along-step as four phase kernels (see along_step.cuh). Used for large
+// iterations; small ones stay fused, where launch latency matters more than occupancy.
+#define B2_ALONG_PHASE_KERNEL(NAME, PHASE, MIN_BLOCKS)                                   \
+    __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)                                 \
+        NAME(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)    \
+    {                                                                                    \
+        u32 tid = thread_id();                                                           \
+        if (tid >= s.counters[CTR_NUM_CHARGED])                                          \
+            return;                                                                      \
+        u32 slot = s.track_slots[tid];                                                   \
+        if (s.status[slot] != ST_ALIVE)                                                  \
+            return;                                                                      \
+        PHASE(p, s, slot);                                                               \
+    }
+B2_ALONG_PHASE_KERNEL(k_along_msc_limit, along_phase_msc_limit, B2_PHASE_MIN_BLOCKS)
+B2_ALONG_PHASE_KERNEL(k_along_propagate_linear, along_phase_propagate<false>, B2_PHASE_MIN_BLOCKS)
+B2_ALONG_PHASE_KERNEL(k_along_propagate_field, along_phase_propagate<true>, ALONG_MIN_BLOCKS)
+B2_ALONG_PHASE_KERNEL(k_along_msc_apply, along_phase_msc_apply, B2_PHASE_MIN_BLOCKS)
+B2_ALONG_PHASE_KERNEL(k_along_finish, along_phase_finish, B2_PHASE_MIN_BLOCKS)
+#undef B2_ALONG_PHASE_KERNEL
+
+__global__ void __launch_bounds__(BLOCK) k_along_step_neutral(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 tid = thread_id();
     if (tid >= s.counters[CTR_NUM_NEUTRAL])
@@ -261,17 +301,14 @@ __global__ void __launch_bounds__(BLOCK) k_along_step_neutral(ParamsView const p
     u32 slot = s.track_slots[s.num_slots - 1 - tid];
     if (s.status[slot] != ST_ALIVE)
         return;
-    along_step<false>(p, s, slot);
+    along_step<false, false>(p, s, slot);
 }
 
 //---------------------------------------------------------------------------//
 // pre-post: discrete select (phys/detail/DiscreteSelectExecutor.hh:37-63)
 //---------------------------------------------------------------------------//
-__global__ void __launch_bounds__(BLOCK) k_discrete_select(ParamsView const p, StateView s)
+B2_D void do_discrete_select(ParamsView const& p, StateView const& s, u32 slot)
 {
-    u32 slot = active_slot(s, thread_id());
-    if (slot == INVALID)
-        return;
     if (s.status[slot] != ST_ALIVE)
         return;
     if (s.post_step_action[slot] != p.phys.model_to_action - 2)
@@ -286,14 +323,18 @@ __global__ void __launch_bounds__(BLOCK) k_discrete_select(ParamsView const p, S
     s.post_step_action[slot] = action;
 }
 
+__global__ void __launch_bounds__(BLOCK) k_discrete_select(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
+{
+    u32 slot = active_slot(s, thread_id());
+    if (slot != INVALID)
+        do_discrete_select(p, s, slot);
+}
+
 //---------------------------------------------------------------------------//
 // post: every EM model (dispatch on the selected action id)
 //---------------------------------------------------------------------------//
-__global__ void __launch_bounds__(BLOCK) k_interact(ParamsView const p, StateView s)
+B2_D void do_interact(ParamsView const& p, StateView const& s, u32 slot)
 {
-    u32 slot = active_slot(s, thread_id());
-    if (slot == INVALID)
-        return;
     if (s.status[slot] != ST_ALIVE)
         return;
     u32 action = s.post_step_action[slot];
@@ -305,12 +346,16 @@ __global__ void __launch_bounds__(BLOCK) k_interact(ParamsView const p, StateVie
     rng.store(s, slot);
 }
 
-// (geo/detail/BoundaryExecutor.hh:41-84)
-__global__ void __launch_bounds__(BLOCK) k_boundary(ParamsView const p, StateView s)
+__global__ void __launch_bounds__(BLOCK) k_interact(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 slot = active_slot(s, thread_id());
-    if (slot == INVALID)
-        return;
+    if (slot != INVALID)
+        do_interact(p, s, slot);
+}
+
+// (geo/detail/BoundaryExecutor.hh:41-84)
+B2_D void do_boundary(ParamsView const& p, StateView const& s, u32 slot)
+{
     if (s.status[slot] != ST_ALIVE || s.post_step_action[slot] != p.scalars.boundary_action)
         return;
     GeoTrack geo(p, s, slot);
@@ -336,12 +381,16 @@ __global__ void __launch_bounds__(BLOCK) k_boundary(ParamsView const p, StateVie
     }
 }
 
-// (phys/detail/TrackingCutExecutor.hh:48-83)
-__global__ void __launch_bounds__(BLOCK) k_tracking_cut(ParamsView const p, StateView s)
+__global__ void __launch_bounds__(BLOCK) k_boundary(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 slot = active_slot(s, thread_id());
-    if (slot == INVALID)
-        return;
+    if (slot != INVALID)
+        do_boundary(p, s, slot);
+}
+
+// (phys/detail/TrackingCutExecutor.hh:48-83)
+B2_D void do_tracking_cut(ParamsView const& p, StateView const& s, u32 slot)
+{
     u8 status = s.status[slot];
     if (status == ST_INACTIVE || status == ST_KILLED)
         return;
@@ -356,13 +405,20 @@ __global__ void __launch_bounds__(BLOCK) k_tracking_cut(ParamsView const p, Stat
     s.status[slot] = ST_KILLED;
 }
 
+__global__ void __launch_bounds__(BLOCK) k_tracking_cut(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
+{
+    u32 slot = active_slot(s, thread_id());
+    if (slot != INVALID)
+        do_tracking_cut(p, s, slot);
+}
+
 // user_post: tallies (user/detail/SimpleCaloExecutor.hh:48-67)
 // Per-detector sums are first accumulated in shared memory (one copy per block) and
 // flushed with one global atomic per touched bin, instead of one contended global
 // atomic per depositing track.
 constexpr u32 TALLY_SMEM_BINS = 1024;
 
-__global__ void __launch_bounds__(BLOCK) k_tally(ParamsView const p, StateView s, u32 num_det)
+__global__ void __launch_bounds__(BLOCK) k_tally(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s, u32 num_det)
 {
     __shared__ real bins[TALLY_SMEM_BINS];
     bool const use_smem = num_det <= TALLY_SMEM_BINS;
@@ -450,6 +506,67 @@ __global__ void __launch_bounds__(BLOCK) k_diagnostic(StateView s, u32 num_parti
             if (v != 0)
                 atomicAdd(&out[i], v);
         }
+    }
+}
+
+//---------------------------------------------------------------------------//
+// Whole step of one track in one launch: pre-step, along-step, discrete select,
+// interaction, boundary, tracking cut, tallies and diagnostics, in action order.
+//
+// Every one of those actions touches only its own slot (plus atomic tallies), so running
+// them back to back per thread gives exactly the per-action results. This is the path for
+// SMALL iterations (shower tails): there the cost of a step is not throughput but the
+// latency of ten dependent launches, each of which starts with cold instruction and data
+// caches -- measured floor 213 us per iteration for a single 1 GeV shower, of which the
+// per-action kernels account for ~165 us (profiles/README_r01.md).
+//---------------------------------------------------------------------------//
+template<bool FIELD>
+__global__ void __launch_bounds__(BLOCK, B2_FUSED_MIN_BLOCKS)
+    k_step_fused(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
+{
+    u32 const tid = thread_id();
+    u32 const slot = active_slot(s, tid);
+    if (slot == INVALID)
+        return;
+    bool const charged = tid < s.counters[CTR_NUM_CHARGED];
+    // pre
+    do_pre_step(p, s, slot);
+    // along
+    if (s.status[slot] == ST_ALIVE)
+    {
+        if (charged)
+            along_step<true, FIELD>(p, s, slot);
+        else
+            along_step<false, false>(p, s, slot);
+    }
+    // pre_post, post
+    do_discrete_select(p, s, slot);
+    do_interact(p, s, slot);
+    do_boundary(p, s, slot);
+    do_tracking_cut(p, s, slot);
+    u8 const status = s.status[slot];
+    if (s.diag_action_counts && status != ST_INACTIVE)
+    {
+        atomicAdd(&s.diag_action_counts[s.particle_id[slot] * s.diag_action_bins
+                                        + s.post_step_action[slot]],
+                  1u);
+    }
+    // user_post
+    if (s.calo_edep && status != ST_INACTIVE)
+    {
+        real edep = s.energy_deposition[slot];
+        if (edep != 0)
+        {
+            u32 det = s.calo_detector_of_volume[s.pre_volume[slot]];
+            if (det != INVALID)
+                atomicAdd(&s.calo_edep[det], edep);
+        }
+    }
+    if (s.diag_step_counts && status == ST_KILLED)
+    {
+        u32 const nb = s.diag_step_bins;
+        u32 const n = s.num_steps[slot];
+        atomicAdd(&s.diag_step_counts[s.particle_id[slot] * nb + (n < nb - 1 ? n : nb - 1)], 1u);
     }
 }
 
@@ -564,15 +681,20 @@ B2_D SlotEnd classify_slot(ParamsView const& p, StateView const& s, u32 slot)
 //                    B = num_sec | num_sec_all << 16 (each <= 2 * BLOCK)
 static_assert(BLOCK <= 512 && MAX_SECONDARIES * BLOCK < 65536, "packed scan field widths");
 
-__global__ void __launch_bounds__(BLOCK) k_end_pass1(ParamsView const p, StateView s)
+__global__ void __launch_bounds__(BLOCK) k_end_pass1(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
-    u32 slot = thread_id();
+    u32 slot = s.slot_begin + thread_id();
     SlotEnd e = classify_slot(p, s, slot);
     u32 ta, tb;
     block_exclusive_scan<BLOCK, u32>(e.is_vacant | (e.charged << 10) | (e.neutral << 20), &ta);
     block_exclusive_scan<BLOCK, u32>(e.num_sec | (e.num_sec_all << 16), &tb);
+    // Lowest block that held a track during this step: next step's passes start there
+    bool const busy = slot < s.num_slots && s.status[slot] != ST_INACTIVE;
+    bool const any_busy = __syncthreads_or(busy);
     if (threadIdx.x == 0)
     {
+        if (any_busy)
+            atomicMin(&s.counters[CTR_FIRST_BUSY_BLOCK], slot / BLOCK);
         u32 const nb = gridDim.x;
         s.block_scratch[blockIdx.x] = ta & 0x3ffu;
         s.block_scratch[nb + blockIdx.x] = (ta >> 10) & 0x3ffu;
@@ -591,16 +713,41 @@ __global__ void __launch_bounds__(1024) k_end_pass2(StateView s, u32 num_blocks)
     u32 const per = (num_blocks + B - 1) / B;
     u32 const begin = threadIdx.x * per;
     u32 const end = begin + per < num_blocks ? begin + per : num_blocks;
+    u32* const scratch = s.block_scratch + a * num_blocks;
     u32 local = 0;
-    for (u32 i = begin; i < end; ++i)
-        local += s.block_scratch[a * num_blocks + i];
     u32 total;
-    u32 run = block_exclusive_scan<B, u32>(local, &total);
-    for (u32 i = begin; i < end; ++i)
+    constexpr u32 MAX_PER = 16;
+    if (per <= MAX_PER)
     {
-        u32 v = s.block_scratch[a * num_blocks + i];
-        s.block_scratch[a * num_blocks + i] = run;
-        run += v;
+        // The thread's run is held in registers: all loads are in flight together
+        // (a load/add/store loop costs one memory round trip per element)
+        u32 v[MAX_PER];
+#pragma unroll
+        for (u32 k = 0; k < MAX_PER; ++k)
+            v[k] = (begin + k < end) ? scratch[begin + k] : 0u;
+#pragma unroll
+        for (u32 k = 0; k < MAX_PER; ++k)
+            local += v[k];
+        u32 run = block_exclusive_scan<B, u32>(local, &total);
+#pragma unroll
+        for (u32 k = 0; k < MAX_PER; ++k)
+        {
+            if (begin + k < end)
+                scratch[begin + k] = run;
+            run += v[k];
+        }
+    }
+    else
+    {
+        for (u32 i = begin; i < end; ++i)
+            local += scratch[i];
+        u32 run = block_exclusive_scan<B, u32>(local, &total);
+        for (u32 i = begin; i < end; ++i)
+        {
+            u32 v = scratch[i];
+            scratch[i] = run;
+            run += v;
+        }
     }
     __shared__ bool is_last;
     if (threadIdx.x == 0)
@@ -618,7 +765,8 @@ __global__ void __launch_bounds__(1024) k_end_pass2(StateView s, u32 num_blocks)
         u32 carry[5];
         for (int k = 0; k < 5; ++k)
             carry[k] = reinterpret_cast<u32 volatile*>(s.counters)[CTR_SCAN_TOTALS + k];
-        u32 num_vac = carry[0];
+        // slots below slot_begin are all vacant
+        u32 num_vac = carry[0] + s.slot_begin;
         u32 num_sec = carry[3];
         s.counters[CTR_NUM_VACANCIES] = num_vac;
         s.counters[CTR_NUM_CHARGED] = carry[1];
@@ -639,16 +787,17 @@ __global__ void __launch_bounds__(1024) k_end_pass2(StateView s, u32 num_blocks)
     }
 }
 
-__global__ void __launch_bounds__(BLOCK) k_end_pass3(ParamsView const p, StateView s)
+__global__ void __launch_bounds__(BLOCK) k_end_pass3(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
-    u32 slot = thread_id();
+    u32 slot = s.slot_begin + thread_id();
     SlotEnd e = classify_slot(p, s, slot);
     u32 ta, tb;
     u32 const nb = gridDim.x;
     u32 sa = block_exclusive_scan<BLOCK, u32>(
         e.is_vacant | (e.charged << 10) | (e.neutral << 20), &ta);
     u32 sb = block_exclusive_scan<BLOCK, u32>(e.num_sec | (e.num_sec_all << 16), &tb);
-    u32 vac_off = (sa & 0x3ffu) + s.block_scratch[blockIdx.x];
+    // vacancies[i] = i for the (all vacant) slots below slot_begin
+    u32 vac_off = s.slot_begin + (sa & 0x3ffu) + s.block_scratch[blockIdx.x];
     u32 chg_off = ((sa >> 10) & 0x3ffu) + s.block_scratch[nb + blockIdx.x];
     u32 neu_off = ((sa >> 20) & 0x3ffu) + s.block_scratch[2 * nb + blockIdx.x];
     u32 sec_off = (sb & 0xffffu) + s.block_scratch[3 * nb + blockIdx.x];
@@ -766,7 +915,7 @@ __global__ void __launch_bounds__(BLOCK) k_end_pass3(ParamsView const p, StateVi
 //---------------------------------------------------------------------------//
 // reseed (random/RngReseed.cu:29-74)
 //---------------------------------------------------------------------------//
-__global__ void k_reseed(ParamsView const p, StateView s, u64 event_id)
+__global__ void k_reseed(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s, u64 event_id)
 {
     u32 slot = thread_id();
     if (slot >= s.num_slots)
@@ -781,7 +930,7 @@ __global__ void k_reset_generated(StateView s)
     s.counters[CTR_NUM_GENERATED] = 0;
 }
 
-__global__ void k_kill_active(ParamsView const p, StateView s)
+__global__ void k_kill_active(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 slot = thread_id();
     if (slot >= s.num_slots)
@@ -881,9 +1030,27 @@ int b200_step_along_step(B200ParamsView const* params, B200StateView const* stat
     StateView const& s = SV(state);
     u32 nc = s.hint_charged < s.num_slots ? s.hint_charged : s.num_slots;
     u32 nn = s.hint_neutral < s.num_slots ? s.hint_neutral : s.num_slots;
-    if (nc > 0)
+    if (B2_ALONG_SPLIT_THRESHOLD != 0 && nc >= B2_ALONG_SPLIT_THRESHOLD)
     {
-        k_along_step_charged<<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
+        ParamsView const& p = PV(params);
+        unsigned const grid = grid_for(nc);
+        if (p.model.msc.enabled)
+            k_along_msc_limit<<<grid, BLOCK, 0, stream>>>(p, s);
+        if (p.model.field.enabled)
+            k_along_propagate_field<<<grid, BLOCK, 0, stream>>>(p, s);
+        else
+            k_along_propagate_linear<<<grid, BLOCK, 0, stream>>>(p, s);
+        if (p.model.msc.enabled)
+            k_along_msc_apply<<<grid, BLOCK, 0, stream>>>(p, s);
+        k_along_finish<<<grid, BLOCK, 0, stream>>>(p, s);
+        B2_COUNT(p.model.msc.enabled ? 4 : 2);
+    }
+    else if (nc > 0)
+    {
+        if (PV(params).model.field.enabled)
+            k_along_step_charged<true><<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
+        else
+            k_along_step_charged<false><<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
         B2_COUNT(1);
     }
     if (nn > 0)
@@ -940,6 +1107,18 @@ int b200_step_tally(B200ParamsView const* params, B200StateView const* state, cu
     return check_launch();
 }
 
+int b200_step_fused(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    unsigned const grid = grid_for(active_hint(s));
+    if (PV(params).model.field.enabled)
+        k_step_fused<true><<<grid, BLOCK, 0, stream>>>(PV(params), s);
+    else
+        k_step_fused<false><<<grid, BLOCK, 0, stream>>>(PV(params), s);
+    B2_COUNT(1);
+    return check_launch();
+}
+
 int b200_step_action_diagnostic(B200ParamsView const* params,
                                 B200StateView const* state,
                                 cudaStream_t stream)
@@ -971,7 +1150,9 @@ int b200_step_extend_from_secondaries(B200ParamsView const* params,
                                       cudaStream_t stream)
 {
     StateView const& s = SV(state);
-    unsigned nb = grid_for(s.num_slots);
+    if (s.slot_begin % BLOCK != 0 || s.slot_begin > s.num_slots)
+        return B200_ERR_INVALID_ARGUMENT;
+    unsigned nb = grid_for(s.num_slots - s.slot_begin);
     k_end_pass1<<<nb, BLOCK, 0, stream>>>(PV(params), s);
     k_end_pass2<<<5, 1024, 0, stream>>>(s, nb);
     k_end_pass3<<<nb, BLOCK, 0, stream>>>(PV(params), s);

@@ -949,8 +949,12 @@ B2_D real rect_safety(RectArrayRef const& ra, Real3 const& pos, u32 vol)
 
 //---------------------------------------------------------------------------//
 // UNIVERSE DISPATCH (reference univ/TrackerVisitor.hh:63-79)
+//
+// These are the out-of-line entry points of the geometry: everything above is
+// inlined into them once, and the (many) call sites in the step kernels share the
+// code. `g` must be addressable: kernels declare their ParamsView __grid_constant__.
 //---------------------------------------------------------------------------//
-B2_D Initialization univ_initialize(GeoParams const& g, u32 uid, Real3 const& pos)
+B2_UNIV_FN Initialization univ_initialize(GeoParams const& g, u32 uid, Real3 const& pos)
 {
     u32 idx = g.universe_index[uid];
     if (g.universe_type[uid] == UNIV_SIMPLE)
@@ -958,7 +962,7 @@ B2_D Initialization univ_initialize(GeoParams const& g, u32 uid, Real3 const& po
     return rect_initialize(get_rect_array(g, idx), pos);
 }
 
-B2_D Initialization univ_cross_boundary(GeoParams const& g, u32 uid, LocalState const& st)
+B2_UNIV_FN Initialization univ_cross_boundary(GeoParams const& g, u32 uid, LocalState const& st)
 {
     u32 idx = g.universe_index[uid];
     if (g.universe_type[uid] == UNIV_SIMPLE)
@@ -966,7 +970,7 @@ B2_D Initialization univ_cross_boundary(GeoParams const& g, u32 uid, LocalState 
     return rect_cross_boundary(get_rect_array(g, idx), st);
 }
 
-B2_D Intersection univ_intersect(GeoParams const& g, u32 uid, LocalState const& st, bool limited, real max_dist)
+B2_UNIV_FN Intersection univ_intersect(GeoParams const& g, u32 uid, LocalState const& st, bool limited, real max_dist)
 {
     u32 idx = g.universe_index[uid];
     if (g.universe_type[uid] == UNIV_SIMPLE)
@@ -974,7 +978,7 @@ B2_D Intersection univ_intersect(GeoParams const& g, u32 uid, LocalState const& 
     return rect_intersect(get_rect_array(g, idx), st, limited, max_dist);
 }
 
-B2_D real univ_safety(GeoParams const& g, u32 uid, Real3 const& pos, u32 vol)
+B2_UNIV_FN real univ_safety(GeoParams const& g, u32 uid, Real3 const& pos, u32 vol)
 {
     u32 idx = g.universe_index[uid];
     if (g.universe_type[uid] == UNIV_SIMPLE)
@@ -990,7 +994,7 @@ B2_D u32 univ_daughter(GeoParams const& g, u32 uid, u32 vol)
     return g.rect_arrays[16 * idx] + vol;
 }
 
-B2_D Real3 univ_normal(GeoParams const& g, u32 uid, Real3 const& pos, u32 surf)
+B2_UNIV_FN Real3 univ_normal(GeoParams const& g, u32 uid, Real3 const& pos, u32 surf)
 {
     u32 idx = g.universe_index[uid];
     if (g.universe_type[uid] == UNIV_SIMPLE)
@@ -1052,6 +1056,25 @@ B2_D Real3 rotate_up(GeoParams const& g, u32 transform_id, Real3 const& dir)
 //---------------------------------------------------------------------------//
 // TRACK VIEW
 //---------------------------------------------------------------------------//
+// Out-of-line entry points of the track-level navigation (defined after GeoTrack).
+// The step kernels call these from many places (MSC safety, linear and field
+// propagation, boundary crossing, scattering); sharing one copy per kernel keeps the
+// kernels within reach of the instruction cache. `g` and `s` are references into the
+// kernels' __grid_constant__ parameters.
+B2_GEO_FN Propagation
+geo_find_next_step(GeoParams const& g, StateView const& s, u32 slot, bool limited, real max_step);
+B2_GEO_FN real geo_find_safety(GeoParams const& g, StateView const& s, u32 slot);
+B2_GEO_FN void
+geo_set_dir(GeoParams const& g, StateView const& s, u32 slot, real dx, real dy, real dz);
+B2_GEO_FN bool geo_cross_boundary(GeoParams const& g, StateView const& s, u32 slot);
+B2_GEO_FN bool geo_initialize(GeoParams const& g,
+                                       StateView const& s,
+                                       u32 slot,
+                                       Real3 const& pos,
+                                       Real3 const& dir);
+B2_GEO_FN void
+geo_move_internal_pos(GeoParams const& g, StateView const& s, u32 slot, real x, real y, real z);
+
 struct GeoTrack
 {
     GeoParams const& g;
@@ -1061,6 +1084,10 @@ struct GeoTrack
 
     B2_D GeoTrack(ParamsView const& p, StateView const& st, u32 sl)
         : g(p.geo), s(st), slot(sl), failed(false)
+    {
+    }
+    B2_D GeoTrack(GeoParams const& gp, StateView const& st, u32 sl)
+        : g(gp), s(st), slot(sl), failed(false)
     {
     }
 
@@ -1135,6 +1162,10 @@ struct GeoTrack
 
     //! Locate a track from scratch (OrangeTrackView::operator=(Initializer))
     B2_D void initialize(Real3 const& ipos, Real3 const& idir)
+    {
+        failed = geo_initialize(g, s, slot, ipos, idir);
+    }
+    B2_D void initialize_impl(Real3 const& ipos, Real3 const& idir)
     {
         failed = false;
         Real3 lpos = ipos, ldir = idir;
@@ -1264,12 +1295,16 @@ struct GeoTrack
     //! Distance to next boundary over all levels (find_next_step[_impl])
     B2_D Propagation find_next_step(bool limited, real max_step)
     {
+        return geo_find_next_step(g, s, slot, limited, max_step);
+    }
+    B2_D Propagation find_next_step_impl(bool limited, real max_step)
+    {
         if (s.geo_boundary[slot] == 0)
         {
             // reentrant: already "at" the next boundary
             return Propagation{0, true, false};
         }
-        Intersection isect = unit_intersect(g, unit_of(0), local_state(0), limited, max_step);
+        Intersection isect = univ_intersect(g, 0, local_state(0), limited, max_step);
         u32 min_level = 0;
         u32 lev = level();
         for (u32 l = 1; l <= lev; ++l)
@@ -1321,6 +1356,10 @@ struct GeoTrack
 
     B2_D void move_internal_pos(Real3 const& newpos)
     {
+        geo_move_internal_pos(g, s, slot, newpos[0], newpos[1], newpos[2]);
+    }
+    B2_D void move_internal_pos_impl(Real3 const& newpos)
+    {
         Real3 lpos = newpos;
         u32 lev = level();
         for (u32 l = 0; l < lev; ++l)
@@ -1337,6 +1376,11 @@ struct GeoTrack
     }
 
     B2_D void cross_boundary()
+    {
+        if (geo_cross_boundary(g, s, slot))
+            failed = true;
+    }
+    B2_D void cross_boundary_impl()
     {
         if (s.geo_boundary[slot] == 0)
         {
@@ -1387,6 +1431,10 @@ struct GeoTrack
 
     B2_D void set_dir(Real3 const& newdir)
     {
+        geo_set_dir(g, s, slot, newdir[0], newdir[1], newdir[2]);
+    }
+    B2_D void set_dir_impl(Real3 const& newdir)
+    {
         if (is_on_boundary())
         {
             u32 sl = s.geo_surface_level[slot];
@@ -1403,7 +1451,8 @@ struct GeoTrack
         clear_next();
     }
 
-    B2_D real find_safety()
+    B2_D real find_safety() { return geo_find_safety(g, s, slot); }
+    B2_D real find_safety_impl()
     {
         real min_safety = real_inf();
         u32 lev = level();
@@ -1415,4 +1464,45 @@ struct GeoTrack
         return min_safety;
     }
 };
+
+B2_GEO_FN Propagation
+geo_find_next_step(GeoParams const& g, StateView const& s, u32 slot, bool limited, real max_step)
+{
+    return GeoTrack(g, s, slot).find_next_step_impl(limited, max_step);
+}
+
+B2_GEO_FN real geo_find_safety(GeoParams const& g, StateView const& s, u32 slot)
+{
+    return GeoTrack(g, s, slot).find_safety_impl();
+}
+
+B2_GEO_FN void
+geo_set_dir(GeoParams const& g, StateView const& s, u32 slot, real dx, real dy, real dz)
+{
+    GeoTrack(g, s, slot).set_dir_impl(make_real3(dx, dy, dz));
+}
+
+B2_GEO_FN bool geo_cross_boundary(GeoParams const& g, StateView const& s, u32 slot)
+{
+    GeoTrack t(g, s, slot);
+    t.cross_boundary_impl();
+    return t.failed;
+}
+
+B2_GEO_FN bool geo_initialize(GeoParams const& g,
+                                       StateView const& s,
+                                       u32 slot,
+                                       Real3 const& pos,
+                                       Real3 const& dir)
+{
+    GeoTrack t(g, s, slot);
+    t.initialize_impl(pos, dir);
+    return t.failed;
+}
+
+B2_GEO_FN void
+geo_move_internal_pos(GeoParams const& g, StateView const& s, u32 slot, real x, real y, real z)
+{
+    GeoTrack(g, s, slot).move_internal_pos_impl(make_real3(x, y, z));
+}
 }  // namespace b200

@@ -25,6 +25,42 @@ constexpr u32 INVALID = 0xffffffffu;
 
 #define B2_HD __host__ __device__ __forceinline__
 #define B2_D __device__ __forceinline__
+#define B2_NOINLINE __device__ __noinline__
+// Outlining level: 0 = transcendentals only, 1 = + universe dispatch (univ_*),
+// 2 = + track-level navigation (geo_*). Levels >= 1 take addresses inside the kernel
+// parameters, which therefore are declared __grid_constant__.
+// Measured on the TestEm3 benchmark (profiles/README_r01.md): level 0 141.7 ms per pass,
+// level 1 146.4 ms, level 2 152.1 ms -- the calls cost more (spills around them, lost
+// cross-call scheduling) than the smaller code gains, so level 0 is the default.
+#ifndef B2_OUTLINE_LEVEL
+#    define B2_OUTLINE_LEVEL 0
+#endif
+#if B2_OUTLINE_LEVEL >= 1
+#    define B2_UNIV_FN B2_NOINLINE inline
+#    define B2_GRID_CONSTANT __grid_constant__
+#else
+#    define B2_UNIV_FN B2_D
+#    define B2_GRID_CONSTANT
+#endif
+#if B2_OUTLINE_LEVEL >= 2
+#    define B2_GEO_FN B2_NOINLINE inline
+#else
+#    define B2_GEO_FN B2_D
+#endif
+
+// Transcendentals are called out of line. Everything else in the track loop is
+// force-inlined into a handful of large kernels; with ~70 call sites the inlined
+// libdevice bodies (40-150 instructions each) made the charged along-step ~600 KB
+// of SASS and a quarter of its stall samples were instruction-fetch misses
+// (profiles/README_r01.md). Unqualified exp/log/sin/cos inside namespace b200
+// resolve to these.
+// (device pass only: in the host pass the names fall through to ::exp etc.)
+#ifdef __CUDA_ARCH__
+B2_NOINLINE inline real exp(real x) { return ::exp(x); }
+B2_NOINLINE inline real log(real x) { return ::log(x); }
+B2_NOINLINE inline real sin(real x) { return ::sin(x); }
+B2_NOINLINE inline real cos(real x) { return ::cos(x); }
+#endif
 
 //! Track status: same numbering as the reference's TrackStatus
 //! (/root/reference/src/celeritas/Types.hh:113-122)

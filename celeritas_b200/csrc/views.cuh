@@ -537,6 +537,10 @@ struct StateView
     u32 hint_charged;
     u32 hint_neutral;
     u32 hint_new;
+    // End-of-step passes cover slots [slot_begin, num_slots) only (multiple of the block
+    // size). Every slot below is inactive, settled, and listed in vacancies[i] = i: new
+    // tracks take the highest vacancies first, so the busy slots cluster at the top.
+    u32 slot_begin;
 
     // scoring (null when no detectors are registered)
     u32* pre_volume;                     // [slot] global volume id at the pre-step point
@@ -569,6 +573,7 @@ enum Counter : u32
     CTR_NUM_NEUTRAL,   // entries at the back of track_slots
     CTR_SCAN_DONE,     // blocks of the end-of-step scan that have finished
     CTR_SCAN_TOTALS,   // 5 totals
+    CTR_FIRST_BUSY_BLOCK = CTR_SCAN_TOTALS + 5,  // first 128-slot block that held a track this step
     CTR_SIZE = 24
 };
 

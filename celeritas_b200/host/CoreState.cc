@@ -160,6 +160,7 @@ CoreStateCounters CoreState::sync_counters()
     c.num_alive = h_counters_[CTR_NUM_ALIVE];
     c.num_charged = h_counters_[CTR_NUM_CHARGED];
     c.num_neutral = h_counters_[CTR_NUM_NEUTRAL];
+    c.first_busy_block = h_counters_[CTR_FIRST_BUSY_BLOCK];
     last_error_ = h_counters_[CTR_ERROR];
     return c;
 }

@@ -27,6 +27,8 @@ struct CoreStateCounters
     uint32_t num_alive{0};
     uint32_t num_charged{0};  //!< active charged tracks in the dense list
     uint32_t num_neutral{0};  //!< active neutral tracks in the dense list
+    //! First 128-slot block that held a track during the last step (INVALID: none)
+    uint32_t first_busy_block{0};
 };
 
 class CoreState
@@ -41,12 +43,17 @@ class CoreState
     //! Declare which single event is in flight (INVALID: several / unknown)
     void single_event(uint32_t event_id) { view_.single_event = event_id; }
     //! Upper bounds used to size the next iteration's grids
-    void launch_hints(uint32_t active, uint32_t charged, uint32_t neutral, uint32_t fresh)
+    void launch_hints(uint32_t active,
+                      uint32_t charged,
+                      uint32_t neutral,
+                      uint32_t fresh,
+                      uint32_t slot_begin = 0)
     {
         view_.hint_active = active;
         view_.hint_charged = charged;
         view_.hint_neutral = neutral;
         view_.hint_new = fresh;
+        view_.slot_begin = slot_begin;
     }
     uint32_t size() const { return view_.num_slots; }
     uint32_t stream_id() const { return stream_id_; }

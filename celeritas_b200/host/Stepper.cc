@@ -4,6 +4,7 @@
 #include "Stepper.hh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <set>
 
@@ -217,6 +218,20 @@ ActionSequence::ActionSequence(CoreParams const& params, Options options)
             return a->order() < b->order();
         return a->action_id() < b->action_id();
     });
+
+    // The fused small-iteration launch covers exactly the built-in actions between
+    // `pre` and `user_post`; any user action in that range turns it off
+    fusable_ = true;
+    for (SPAction const& user : options.user_actions)
+    {
+        if (user->order() >= Order::pre && user->order() <= Order::user_post)
+            fusable_ = false;
+    }
+    fuse_threshold_ = options.fuse_threshold ? options.fuse_threshold : default_fuse_threshold;
+    if (char const* env = std::getenv("B200_FUSE_THRESHOLD"))
+        fuse_threshold_ = static_cast<uint32_t>(std::strtoul(env, nullptr, 10));
+    if (fuse_threshold_ == 0xffffffffu)
+        fusable_ = false;
 }
 
 ActionSequence::~ActionSequence()
@@ -232,6 +247,18 @@ ActionSequence::~ActionSequence()
 
 void ActionSequence::step(CoreParams const& params, CoreState& state)
 {
+    if (fusable_ && !action_times_ && state.view().hint_active <= fuse_threshold_)
+    {
+        // Small iteration: one launch for everything between `pre` and `user_post`
+        for (auto const& a : actions_)
+            if (a->order() < StepActionOrder::pre)
+                a->step(params, state);
+        check_rc(b200_step_fused(pv(params), sv(state), state.stream()), "step_fused");
+        for (auto const& a : actions_)
+            if (a->order() > StepActionOrder::user_post)
+                a->step(params, state);
+        return;
+    }
     if (!action_times_)
     {
         for (auto const& a : actions_)
@@ -341,10 +368,19 @@ void Stepper::step_async()
         uint64_t const n = state.size();
         uint64_t queued = uint64_t(last_.num_initializers) + st.count;
         uint64_t fresh = std::min<uint64_t>(queued, last_.num_vacancies);
+        // The end-of-step passes start at the first block that can hold a track: the
+        // lowest busy block of the last step, lowered by the tracks about to start
+        // (they take the highest vacancies; at worst all of them lie just below it)
+        uint64_t const block = 128;
+        uint64_t busy_begin = last_.first_busy_block == INVALID
+                                  ? n
+                                  : std::min<uint64_t>(n, last_.first_busy_block * block);
+        uint64_t slot_begin = busy_begin > fresh ? (busy_begin - fresh) / block * block : 0;
         state.launch_hints(std::min<uint64_t>(n, last_.num_alive + fresh),
                            std::min<uint64_t>(n, last_.num_charged + fresh),
                            std::min<uint64_t>(n, last_.num_neutral + fresh),
-                           fresh);
+                           fresh,
+                           slot_begin);
     }
     check_rc(b200_reset_generated(sv(state), stream), "reset_generated");
     if (st.count > 0)

@@ -68,7 +68,12 @@ class ActionSequence
         uint32_t step_diagnostic_bins{0};
         //! Extra user step actions; ids continue the action table
         std::vector<SPAction> user_actions;
+        //! Iterations with at most this many active tracks run pre..user_post as one
+        //! fused launch (0: default, 0xffffffff: never)
+        uint32_t fuse_threshold{0};
     };
+    //! Default of Options::fuse_threshold (measured: profiles/README_r01.md)
+    static constexpr uint32_t default_fuse_threshold = 16384;
     //! Build the B200 adapters for every step action in the problem's table
     explicit ActionSequence(CoreParams const& params) : ActionSequence(params, Options{}) {}
     ActionSequence(CoreParams const& params, Options options);
@@ -80,6 +85,9 @@ class ActionSequence
     bool action_diagnostic() const { return action_diagnostic_; }
     uint32_t step_diagnostic_bins() const { return step_diagnostic_bins_; }
     bool action_times() const { return action_times_; }
+    //! Whether small iterations can take the fused path, and up to how many tracks
+    bool fusable() const { return fusable_; }
+    uint32_t fuse_threshold() const { return fuse_threshold_; }
 
     //! Per-action device timing with CUDA events on the state's stream
     //! (reference option: StepperInput::action_times, ActionSequence.cc:99-121)
@@ -95,6 +103,8 @@ class ActionSequence
     bool action_diagnostic_{false};
     uint32_t step_diagnostic_bins_{0};
     bool action_times_{false};
+    bool fusable_{false};
+    uint32_t fuse_threshold_{0};
     std::vector<double> accum_time_;
     struct Pending
     {

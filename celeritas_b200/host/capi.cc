@@ -6,6 +6,8 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/celeritas_b200.h"
 #include "CoreParams.hh"
@@ -190,6 +192,7 @@ int b200_stepper_create_opts(B200Params const* params,
         inp.action_times = options->action_times != 0;
         inp.actions.action_diagnostic = options->action_diagnostic != 0;
         inp.actions.step_diagnostic_bins = options->step_diagnostic_bins;
+        inp.actions.fuse_threshold = options->fuse_threshold;
         s->stepper = std::make_shared<Stepper>(std::move(inp));
         s->state_handle.state = &s->stepper->state();
         s->launches_at_create = b200_launch_count();
@@ -373,6 +376,116 @@ int b200_run_events(B200Stepper* handle,
         cudaEventDestroy(ev1);
         if (result)
             *result = r;
+    });
+}
+
+//---------------------------------------------------------------------------//
+// Several streams at once: one host thread per Stepper, as celer-sim runs one
+// OpenMP thread per stream (app/celer-sim/celer-sim.cc:120-137). On the device the
+// streams overlap: the latency-bound small iterations of one shower tail fill in
+// under the throughput-bound iterations of another.
+int b200_run_events_streams(B200Stepper* const* handles,
+                            uint32_t num_streams,
+                            B200Primary const* primaries,
+                            uint32_t const* offsets,
+                            uint32_t num_events,
+                            int merge_events,
+                            uint64_t max_steps,
+                            B200RunResult* results,
+                            double* seconds)
+{
+    if (!handles || num_streams == 0 || !primaries || !offsets || !results)
+        return B200_ERR_INVALID_ARGUMENT;
+    for (uint32_t k = 0; k < num_streams; ++k)
+        if (!handles[k])
+            return B200_ERR_INVALID_ARGUMENT;
+    return guarded([&] {
+        int device = 0;
+        B2_CUDA_CALL(cudaGetDevice(&device));
+        // Event e belongs to stream e % num_streams (static, so runs are reproducible)
+        std::vector<std::vector<B200Primary>> merged(num_streams);
+        if (merge_events)
+        {
+            for (uint32_t e = 0; e < num_events; ++e)
+            {
+                auto& dst = merged[e % num_streams];
+                dst.insert(dst.end(), primaries + offsets[e], primaries + offsets[e + 1]);
+            }
+        }
+        cudaStream_t stream0 = handles[0]->stepper->state().stream();
+        cudaEvent_t ev0, ev1;
+        B2_CUDA_CALL(cudaEventCreate(&ev0));
+        B2_CUDA_CALL(cudaEventCreate(&ev1));
+        std::vector<std::string> errors(num_streams);
+        std::vector<int> codes(num_streams, 0);
+        B2_CUDA_CALL(cudaEventRecord(ev0, stream0));
+        auto work = [&](uint32_t k) {
+            try
+            {
+                B2_CUDA_CALL(cudaSetDevice(device));
+                TransporterInput tinp;
+                tinp.max_steps = max_steps;
+                Transporter transport(handles[k]->stepper, tinp);
+                Stepper& step = *handles[k]->stepper;
+                B200RunResult r{};
+                auto run = [&](B200Primary const* p, uint32_t n) {
+                    step.reseed(p[0].event_id);
+                    TransporterResult t = transport(p, n);
+                    r.num_primaries += n;
+                    r.num_steps += t.num_steps;
+                    r.num_step_iterations += t.num_step_iterations;
+                    r.num_tracks += t.num_tracks;
+                    r.num_aborted += t.num_aborted;
+                    r.max_queued = std::max<uint64_t>(r.max_queued, t.max_queued);
+                };
+                if (merge_events)
+                {
+                    if (!merged[k].empty())
+                        run(merged[k].data(), merged[k].size());
+                }
+                else
+                {
+                    for (uint32_t e = k; e < num_events; e += num_streams)
+                    {
+                        uint32_t n = offsets[e + 1] - offsets[e];
+                        if (n != 0)
+                            run(primaries + offsets[e], n);
+                    }
+                }
+                results[k] = r;
+            }
+            catch (CudaError const& e)
+            {
+                errors[k] = e.what();
+                codes[k] = e.code;
+            }
+            catch (std::exception const& e)
+            {
+                errors[k] = e.what();
+                codes[k] = B200_ERR_RUNTIME;
+            }
+        };
+        std::vector<std::thread> threads;
+        for (uint32_t k = 1; k < num_streams; ++k)
+            threads.emplace_back(work, k);
+        work(0);
+        for (auto& t : threads)
+            t.join();
+        // Every stream is idle here (each transport ends with a synchronised iteration)
+        B2_CUDA_CALL(cudaEventRecord(ev1, stream0));
+        B2_CUDA_CALL(cudaEventSynchronize(ev1));
+        float ms = 0;
+        B2_CUDA_CALL(cudaEventElapsedTime(&ms, ev0, ev1));
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+        for (uint32_t k = 0; k < num_streams; ++k)
+        {
+            if (codes[k] != 0)
+                throw std::runtime_error("stream " + std::to_string(k) + ": " + errors[k]);
+            results[k].seconds = ms * 1e-3;
+        }
+        if (seconds)
+            *seconds = ms * 1e-3;
     });
 }
 }  // extern "C"

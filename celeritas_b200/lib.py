@@ -37,7 +37,7 @@ class RunResult(C.Structure):
 class StepperOptions(C.Structure):
     _fields_ = [('stream_id', C.c_uint32), ('num_track_slots', C.c_uint32),
                 ('action_times', C.c_int), ('action_diagnostic', C.c_int),
-                ('step_diagnostic_bins', C.c_uint32)]
+                ('step_diagnostic_bins', C.c_uint32), ('fuse_threshold', C.c_uint32)]
 
 
 # Every symbol declared in include/celeritas_b200.h
@@ -62,14 +62,16 @@ EXPORTS = [
     'b200_stepper_action_diagnostic_get', 'b200_stepper_step_diagnostic_get',
     'b200_stepper_step_diagnostic_bins', 'b200_stepper_diagnostics_clear',
     'b200_primaries_generate', 'b200_celer_sim_run', 'b200_string_free',
-    'b200_params_num_particles',
+    'b200_params_num_particles', 'b200_run_events_streams', 'b200_step_fused',
 ]
 
 _lib = None
 
 
 def library_path():
-    return os.path.join(HERE, 'libceleritas_b200.so')
+    # CELERITAS_B200_LIB selects another build of the same CUDA library (kernel tuning
+    # experiments); it is never a fallback implementation
+    return os.environ.get('CELERITAS_B200_LIB') or os.path.join(HERE, 'libceleritas_b200.so')
 
 
 def load_library():
@@ -132,6 +134,8 @@ def load_library():
     L.b200_geo_trace_host.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp]
     L.b200_run_events.argtypes = [vp, vp, vp, C.c_uint32, C.c_int, C.c_uint64,
                                   C.POINTER(RunResult)]
+    L.b200_run_events_streams.argtypes = [vp, C.c_uint32, vp, vp, C.c_uint32, C.c_int,
+                                          C.c_uint64, vp, C.POINTER(C.c_double)]
     L.b200_stepper_create_opts.argtypes = [vp, C.POINTER(StepperOptions), C.POINTER(vp)]
     L.b200_stepper_num_actions.argtypes = [vp]
     L.b200_stepper_num_actions.restype = C.c_uint32
@@ -258,13 +262,13 @@ class Stepper:
     """One stream's stepping loop (reference: Stepper<MemSpace::device>)."""
 
     def __init__(self, params, num_track_slots, stream_id=0, action_times=False,
-                 action_diagnostic=False, step_diagnostic_bins=0):
+                 action_diagnostic=False, step_diagnostic_bins=0, fuse_threshold=0):
         L = load_library()
         self.params = params
         self.n = num_track_slots
         h = C.c_void_p()
         opts = StepperOptions(stream_id, num_track_slots, int(action_times),
-                              int(action_diagnostic), step_diagnostic_bins)
+                              int(action_diagnostic), step_diagnostic_bins, fuse_threshold)
         _check(L.b200_stepper_create_opts(params.h, C.byref(opts), C.byref(h)))
         self.h = h
 
@@ -369,6 +373,26 @@ class Stepper:
                     num_primaries=int(r.num_primaries), max_queued=int(r.max_queued),
                     seconds=r.seconds, num_tracks=int(r.num_tracks),
                     num_aborted=int(r.num_aborted))
+
+
+def run_events_streams(steppers, primaries, offsets, merge_events=False, max_steps=0):
+    """Transport events over several steppers (streams) concurrently; event e goes to
+    steppers[e % len(steppers)]. Returns (per-stream results, device seconds)."""
+    L = load_library()
+    primaries = np.ascontiguousarray(primaries, dtype=PRIMARY_DTYPE)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+    n = len(steppers)
+    handles = (C.c_void_p * n)(*[s.h for s in steppers])
+    results = (RunResult * n)()
+    seconds = C.c_double()
+    _check(L.b200_run_events_streams(handles, n, primaries.ctypes.data, offsets.ctypes.data,
+                                     len(offsets) - 1, int(merge_events), max_steps, results,
+                                     C.byref(seconds)))
+    out = [dict(num_steps=int(r.num_steps), num_step_iterations=int(r.num_step_iterations),
+                num_primaries=int(r.num_primaries), max_queued=int(r.max_queued),
+                seconds=r.seconds, num_tracks=int(r.num_tracks),
+                num_aborted=int(r.num_aborted)) for r in results]
+    return out, seconds.value
 
 
 def celer_sim_run(run_input):

@@ -97,6 +97,9 @@ typedef struct B200StepperOptions
     int action_times;              /* time every action with CUDA events */
     int action_diagnostic;         /* add an ActionDiagnostic unless the problem has one */
     uint32_t step_diagnostic_bins; /* >0: add a StepDiagnostic with this 'max' bin */
+    /* Iterations with at most this many active tracks run pre-step..tally as one fused
+     * launch (b200_step_fused). 0: library default; 0xffffffff: never fuse. */
+    uint32_t fuse_threshold;
 } B200StepperOptions;
 
 /* Opaque views holding device pointers (layout: celeritas_b200/csrc/views.cuh). */
@@ -158,6 +161,10 @@ int b200_step_extend_from_secondaries(B200ParamsView const*, B200StateView const
 /* ActionDiagnostic (user/detail/ActionDiagnosticExecutor.hh:30-65, order post) and
  * StepDiagnostic (user/detail/StepDiagnosticExecutor.hh:28-60, order user_post); the
  * state must have been created with the diagnostic enabled (B200StepperOptions). */
+/* All of pre-step .. tally/diagnostics for every active track in ONE launch (identical
+ * results: those actions only touch their own slot). The stepper uses it for small
+ * iterations, where launch latency dominates; see B200StepperOptions::fuse_threshold. */
+int b200_step_fused(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_step_action_diagnostic(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_step_step_diagnostic(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_reseed(B200ParamsView const*, B200StateView const*, uint64_t event_id, cudaStream_t);
@@ -246,6 +253,20 @@ int b200_run_events(B200Stepper* stepper,
                     int merge_events,
                     uint64_t max_steps,
                     B200RunResult* result);
+
+/* The same over several streams at once, one host thread per stepper (reference: one
+ * OpenMP thread per stream, app/celer-sim/celer-sim.cc:120-137). Event e is transported
+ * by stepper e % num_streams; with merge_events every stepper transports its events as
+ * one batch. results[num_streams]; *seconds = device time of the whole call. */
+int b200_run_events_streams(B200Stepper* const* steppers,
+                            uint32_t num_streams,
+                            B200Primary const* primaries,
+                            uint32_t const* offsets,
+                            uint32_t num_events,
+                            int merge_events,
+                            uint64_t max_steps,
+                            B200RunResult* results,
+                            double* seconds);
 
 /*--- celer-sim front end ------------------------------------------------------*/
 /* Primaries from a celer-sim "primary_options" JSON object (reference:
