@@ -44,10 +44,15 @@ constexpr int BLOCK = 128;
 #    define B2_PHASE_MIN_BLOCKS 6
 #endif
 // Charged tracks from which the along-step runs as four phase kernels (0 = never)
+// Measured (profiles/README_r01.md): the split is NOT faster (56.2 vs 54.3 ms per pass in
+// the along-step), so it is off; the phase kernels stay for profiling single phases.
 #ifndef B2_ALONG_SPLIT_THRESHOLD
-#    define B2_ALONG_SPLIT_THRESHOLD 8192
+#    define B2_ALONG_SPLIT_THRESHOLD 0
 #endif
 constexpr int ALONG_MIN_BLOCKS = B2_ALONG_MIN_BLOCKS;
+
+// Size of StateView::interact_count (CoreState allocates this many counters)
+constexpr u32 MAX_INTERACT_MODELS_RESET = 16;
 
 B2_D u32 thread_id()
 {
@@ -209,6 +214,12 @@ __global__ void k_initialize_finalize(StateView s)
     s.counters[CTR_NUM_NEW_TRACKS] = num_new;
     // recomputed by this step's end pass (atomicMin over the blocks that hold tracks)
     s.counters[CTR_FIRST_BUSY_BLOCK] = INVALID;
+    // per-model interaction lists are rebuilt by this step's discrete select
+    if (s.interact_count)
+    {
+        for (u32 m = 0; m < MAX_INTERACT_MODELS_RESET; ++m)
+            s.interact_count[m] = 0;
+    }
     // whole-run tallies kept on the device: track-steps and step iterations
     s.step_counters[0] += s.num_slots - (num_vac - num_new);
     s.step_counters[1] += 1;
@@ -323,11 +334,46 @@ B2_D void do_discrete_select(ParamsView const& p, StateView const& s, u32 slot)
     s.post_step_action[slot] = action;
 }
 
+// Besides selecting, the launch sorts the interacting tracks BY MODEL into per-model slot
+// lists (block-aggregated appends), so that the interaction kernel runs warps in which
+// every lane executes the same interactor. Launched over all active tracks, only ~4 of
+// 32 lanes were active per instruction (ncu: profiles/README_r01.md).
+constexpr u32 MAX_INTERACT_MODELS = 16;
+
 __global__ void __launch_bounds__(BLOCK) k_discrete_select(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
+    __shared__ u32 count[MAX_INTERACT_MODELS];
+    __shared__ u32 base[MAX_INTERACT_MODELS];
+    bool const build_lists = s.interact_list != nullptr;
+    if (build_lists)
+    {
+        if (threadIdx.x < MAX_INTERACT_MODELS)
+            count[threadIdx.x] = 0;
+        __syncthreads();
+    }
     u32 slot = active_slot(s, thread_id());
+    u32 model = INVALID;
     if (slot != INVALID)
+    {
         do_discrete_select(p, s, slot);
+        if (build_lists && s.status[slot] == ST_ALIVE)
+        {
+            u32 m = s.post_step_action[slot] - p.phys.model_to_action;
+            if (m < p.phys.num_models)
+                model = m;
+        }
+    }
+    if (!build_lists)
+        return;
+    u32 rank = 0;
+    if (model != INVALID)
+        rank = atomicAdd(&count[model], 1u);
+    __syncthreads();
+    if (threadIdx.x < p.phys.num_models && count[threadIdx.x] > 0)
+        base[threadIdx.x] = atomicAdd(&s.interact_count[threadIdx.x], count[threadIdx.x]);
+    __syncthreads();
+    if (model != INVALID)
+        s.interact_list[size_t(model) * s.num_slots + base[model] + rank] = slot;
 }
 
 //---------------------------------------------------------------------------//
@@ -351,6 +397,28 @@ __global__ void __launch_bounds__(BLOCK) k_interact(B2_GRID_CONSTANT ParamsView 
     u32 slot = active_slot(s, thread_id());
     if (slot != INVALID)
         do_interact(p, s, slot);
+}
+
+//! Interactions over the per-model lists built by k_discrete_select: thread t works on
+//! the t-th interacting track in model order
+__global__ void __launch_bounds__(BLOCK) k_interact_lists(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
+{
+    u32 tid = thread_id();
+    u32 const num_models = p.phys.num_models;
+    u32 model = 0;
+    u32 count = 0;
+    for (; model < num_models; ++model)
+    {
+        // every model's segment starts on a warp boundary: no warp mixes interactors
+        count = s.interact_count[model];
+        u32 const padded = (count + 31u) & ~31u;
+        if (tid < padded)
+            break;
+        tid -= padded;
+    }
+    if (model == num_models || tid >= count)
+        return;
+    do_interact(p, s, s.interact_list[size_t(model) * s.num_slots + tid]);
 }
 
 // (geo/detail/BoundaryExecutor.hh:41-84)
@@ -1074,7 +1142,17 @@ int b200_step_discrete_select(B200ParamsView const* params,
 int b200_step_interact(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
 {
     StateView const& s = SV(state);
-    k_interact<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s);
+    if (s.interact_list)
+    {
+        // lists built by this step's b200_step_discrete_select; segments are padded to
+        // whole warps
+        u32 const bound = active_hint(s) + 32 * PV(params).phys.num_models;
+        k_interact_lists<<<grid_for(bound), BLOCK, 0, stream>>>(PV(params), s);
+    }
+    else
+    {
+        k_interact<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s);
+    }
     B2_COUNT(1);
     return check_launch();
 }

@@ -542,6 +542,11 @@ struct StateView
     // tracks take the highest vacancies first, so the busy slots cluster at the top.
     u32 slot_begin;
 
+    // Interacting tracks of the current step sorted by model (null: interactions run
+    // over the whole active list). Filled by the discrete-select launch.
+    u32* interact_list;   // [model][slot]
+    u32* interact_count;  // [16] entries per model
+
     // scoring (null when no detectors are registered)
     u32* pre_volume;                     // [slot] global volume id at the pre-step point
     u32 const* calo_detector_of_volume;  // [volume] detector id or INVALID

@@ -131,6 +131,12 @@ CoreState::CoreState(std::shared_ptr<CoreParams const> params,
         s.calo_edep = arena_.alloc<real>(params_->num_detectors());
         s.num_detectors = params_->num_detectors();
     }
+    // Per-model lists of interacting slots (16 = MAX_INTERACT_MODELS in kernels.cu)
+    if (p.phys.num_models > 0 && p.phys.num_models <= 16)
+    {
+        s.interact_list = arena_.alloc<u32>(size_t(p.phys.num_models) * n);
+        s.interact_count = arena_.alloc<u32>(16);
+    }
     B2_CUDA_CALL(cudaMallocHost(reinterpret_cast<void**>(&h_counters_), CTR_SIZE * sizeof(uint32_t)));
     B2_CUDA_CALL(cudaDeviceSynchronize());
 }
