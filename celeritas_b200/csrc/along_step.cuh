@@ -109,12 +109,12 @@ struct MscHelper
         else
         {
             u32 const lower = static_cast<u32>((loge - front) / delta);
-            real const upper_energy = exp(front + delta * (lower + 1));
+            real const* node_energy = msc.grid_energy + msc.xs_grid_energy_offset[idx];
+            real const upper_energy = node_energy[lower + 1];
             real upper_xs = values[lower + 1];
             if (lower + 1 == prime)
                 upper_xs /= upper_energy;
-            xs = lerp_points(
-                exp(front + delta * lower), values[lower], upper_energy, upper_xs, energy);
+            xs = lerp_points(node_energy[lower], values[lower], upper_energy, upper_xs, energy);
             if (lower >= prime)
                 xs /= energy;
         }

@@ -25,6 +25,8 @@ struct GridRef
     B2_D u32 prime() const { return p.grid_prime[id]; }
     B2_D real value(u32 i) const { return p.reals[p.grid_value_offset[id] + i]; }
     B2_D real log_node(u32 i) const { return front() + delta() * i; }
+    //! Energy of node i: exp(log_node(i)), tabulated on the host
+    B2_D real energy(u32 i) const { return p.grid_energy[p.grid_energy_offset[id] + i]; }
 };
 
 //! Cross section at `energy` (XsCalculator::operator())
@@ -51,12 +53,11 @@ B2_D real calc_xs(PhysParams const& p, u32 grid_id, real energy)
     }
     real const delta = g.delta();
     u32 const lower = static_cast<u32>((loge - front) / delta);
-    real const upper_energy = exp(front + delta * (lower + 1));
+    real const upper_energy = g.energy(lower + 1);
     real upper_xs = g.value(lower + 1);
     if (lower + 1 == prime)
         upper_xs /= upper_energy;
-    real result = lerp_points(
-        exp(front + delta * lower), g.value(lower), upper_energy, upper_xs, energy);
+    real result = lerp_points(g.energy(lower), g.value(lower), upper_energy, upper_xs, energy);
     if (lower >= prime)
         result /= energy;
     return result;
@@ -79,11 +80,7 @@ B2_D real calc_range(PhysParams const& p, u32 grid_id, real energy)
         return g.value(n - 1);
     real const delta = g.delta();
     u32 const idx = static_cast<u32>((loge - front) / delta);
-    return lerp_points(exp(front + delta * idx),
-                       g.value(idx),
-                       exp(front + delta * (idx + 1)),
-                       g.value(idx + 1),
-                       energy);
+    return lerp_points(g.energy(idx), g.value(idx), g.energy(idx + 1), g.value(idx + 1), energy);
 }
 
 //! Energy for a given range (InverseRangeCalculator::operator())
@@ -93,7 +90,7 @@ B2_D real calc_inverse_range(PhysParams const& p, u32 grid_id, real range)
     u32 const n = g.size();
     real const r_front = g.value(0);
     if (range < r_front)
-        return exp(g.front()) * ipow2(range / r_front);
+        return g.energy(0) * ipow2(range / r_front);
     real const r_back = g.value(n - 1);
     if (range >= r_back)
         return exp(g.back());
@@ -115,18 +112,14 @@ B2_D real calc_inverse_range(PhysParams const& p, u32 grid_id, real range)
     u32 idx = lo;
     if (range != g.value(idx))
         --idx;
-    return lerp_points(g.value(idx),
-                       exp(g.log_node(idx)),
-                       g.value(idx + 1),
-                       exp(g.log_node(idx + 1)),
-                       range);
+    return lerp_points(g.value(idx), g.energy(idx), g.value(idx + 1), g.energy(idx + 1), range);
 }
 
 //! Tabulated xs at node i (XsCalculator::operator[])
 B2_D real calc_xs_at_node(PhysParams const& p, u32 grid_id, u32 i)
 {
     GridRef g{p, grid_id};
-    real energy = exp(g.log_node(i));
+    real energy = g.energy(i);
     real r = g.value(i);
     if (i >= g.prime())
         r /= energy;

@@ -213,6 +213,12 @@ struct PhysParams
     u32 const* grid_prime;
     u32 const* grid_value_offset;
     real const* reals;
+    // Node energies exp(log_front + i * log_delta) of every grid, tabulated by the host
+    // loader with the host libm: the same doubles the reference computes at run time
+    // (UniformGrid::operator[] + std::exp in XsCalculator), without two exp() calls per
+    // lookup on the device
+    u32 const* grid_energy_offset;  // [grid] into grid_energy
+    real const* grid_energy;
 
     // Per (particle, ppid)
     u32 const* pp_num;        // [particle]
@@ -341,6 +347,8 @@ struct UrbanMscParams
     u32 const* xs_grid_u32;   // 3 per entry: size, prime_index, value_offset
     real const* xs_grid_f64;  // 3 per entry: log_front, log_back, log_delta
     real const* reals;
+    u32 const* xs_grid_energy_offset;  // [entry] into grid_energy (host-tabulated node energies)
+    real const* grid_energy;
 };
 
 //! Energy-loss fluctuation (em/data/FluctuationData.hh)

@@ -3,7 +3,11 @@
 //---------------------------------------------------------------------------//
 #include "CoreParams.hh"
 
+#include <cmath>
+#include <cstring>
+#include <map>
 #include <sstream>
+#include <tuple>
 
 #include "../csrc/orange.cuh"
 
@@ -22,6 +26,36 @@ std::vector<std::string> split_lines(std::string const& s)
         out.push_back(line);
     return out;
 }
+
+// Node energies of the log-uniform grids, computed once on the host exactly as the
+// reference computes them at every lookup: E_i = std::exp(log_front + log_delta * i)
+// (corecel/grid/UniformGrid.hh operator[], celeritas/grid/XsCalculator.hh:139-152).
+// Identical (front, delta, size) grids share one table.
+struct NodeEnergyPool
+{
+    std::map<std::tuple<uint64_t, uint64_t, uint32_t>, uint32_t> index;
+    std::vector<double> values;
+
+    uint32_t get(double front, double delta, uint32_t size)
+    {
+        uint64_t fb, db;
+        std::memcpy(&fb, &front, 8);
+        std::memcpy(&db, &delta, 8);
+        auto key = std::make_tuple(fb, db, size);
+        auto it = index.find(key);
+        if (it != index.end())
+            return it->second;
+        uint32_t offset = values.size();
+        for (uint32_t i = 0; i < size; ++i)
+        {
+            // two roundings (no contraction), as in the reference's host build
+            volatile double scaled = delta * i;
+            values.push_back(std::exp(front + scaled));
+        }
+        index.emplace(key, offset);
+        return offset;
+    }
+};
 }  // namespace
 
 std::shared_ptr<CoreParams> CoreParams::from_image(std::string const& path)
@@ -221,6 +255,17 @@ void CoreParams::load(Image const& img)
         p.grid_prime = U32("phys.grid_prime");
         p.grid_value_offset = U32("phys.grid_value_offset");
         p.reals = F64("phys.reals");
+        {
+            NodeEnergyPool pool;
+            auto size = img.get<uint32_t>("phys.grid_size");
+            auto front = img.get<double>("phys.grid_log_front");
+            auto delta = img.get<double>("phys.grid_log_delta");
+            std::vector<uint32_t> offsets(size.size());
+            for (size_t g = 0; g < size.size(); ++g)
+                offsets[g] = pool.get(front[g], delta[g], size[g]);
+            p.grid_energy_offset = arena_.upload(offsets);
+            p.grid_energy = arena_.upload(pool.values);
+        }
         p.pp_num = U32("phys.pp_num");
         p.pp_eloss_ppid = U32("phys.pp_eloss_ppid");
         p.pp_has_at_rest = U32("phys.pp_has_at_rest");
@@ -347,6 +392,16 @@ void CoreParams::load(Image const& img)
             m.msc.xs_grid_u32 = U32("msc.xs_grid_u32");
             m.msc.xs_grid_f64 = F64("msc.xs_grid_f64");
             m.msc.reals = F64("msc.reals");
+            {
+                NodeEnergyPool pool;
+                auto gu = img.get<uint32_t>("msc.xs_grid_u32");
+                auto gf = img.get<double>("msc.xs_grid_f64");
+                std::vector<uint32_t> offsets(gu.size() / 3);
+                for (size_t e = 0; e < offsets.size(); ++e)
+                    offsets[e] = pool.get(gf[3 * e], gf[3 * e + 2], gu[3 * e]);
+                m.msc.xs_grid_energy_offset = arena_.upload(offsets);
+                m.msc.grid_energy = arena_.upload(pool.values);
+            }
         }
         m.fluct.enabled = 0;
         if (img.has("fluct.urban"))
