@@ -35,7 +35,10 @@ NUM_EVENTS = 100
 PRIMARIES_PER_EVENT = 100
 ENERGY_MEV = 1000.0
 NUM_TRACK_SLOTS = 1 << 20
-NUM_STREAMS = 1
+# two steppers (CUDA streams) per GPU share the 2^20 slots: the latency-bound shower tails
+# of one overlap the throughput-bound iterations of the other (measured sweep:
+# profiles/README_r01.md; 1 stream 6.8e8, 2 streams 7.5e8, 3 streams 7.6e8, 4 streams 7.5e8)
+NUM_STREAMS = 2
 ALG_BYTES_PER_TRACK_STEP = 672  # 2 * S_live, D=1, P=4
 
 
@@ -52,7 +55,12 @@ def make_events(num_events, per_event, first_event, particle_id, dtype):
 
 
 class ClockSampler:
-    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md
+    clocks line). Sampled in-process through NVML, the library behind nvidia-smi: forking
+    nvidia-smi every 200 ms stalled the launching threads for tens of milliseconds and
+    showed up in the end-to-end number. nvidia-smi is the fallback if NVML cannot load."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown',
+               0x4: 'sw_power_cap'}
 
     def __init__(self, index):
         self.samples = []
@@ -61,26 +69,60 @@ class ClockSampler:
         self._stop = threading.Event()
         self.index = index
         self._thread = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: map through CUDA_VISIBLE_DEVICES
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = index
+            if visible:
+                ids = [v.strip() for v in visible.split(',') if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle,
+                                                                  pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
 
-    def _run(self):
+    def _sample_nvml(self):
+        n = self._nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM)))
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._handle)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle)
+        for bit, name in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
         q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                              '--format=csv,noheader,nounits'],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        f = [x.strip() for x in out.split(',')]
+        self.samples.append(float(f[0]))
+        self.max_mhz = float(f[1])
+        for nm, v in zip(names, f[2:]):
+            if v.lower().startswith('active'):
+                self.reasons.add(nm)
+
+    def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
-                                      '--format=csv,noheader,nounits'],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                f = [x.strip() for x in out.split(',')]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
-                for nm, v in zip(names, f[2:]):
-                    if v.lower().startswith('active'):
-                        self.reasons.add(nm)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05 if self._nvml is not None else 0.5)
 
     def __enter__(self):
         self._thread.start()
@@ -92,7 +134,9 @@ class ClockSampler:
 
     def summary(self):
         return {'sm_mhz': float(np.median(self.samples)) if self.samples else None,
-                'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+                'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'source': 'nvml' if self._nvml is not None else 'nvidia-smi',
+                'samples': len(self.samples)}
 
 
 def measured_peak_gbs():

@@ -42,6 +42,8 @@ def lib():
         L.celerref_export_image.argtypes = [C.c_void_p, C.c_char_p]
         L.celerref_stepper_create.restype = C.c_void_p
         L.celerref_stepper_create.argtypes = [C.c_void_p, C.c_uint32]
+        L.celerref_stepper_create_stream.restype = C.c_void_p
+        L.celerref_stepper_create_stream.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         L.celerref_stepper_destroy.argtypes = [C.c_void_p]
         L.celerref_step.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         L.celerref_reseed.argtypes = [C.c_void_p, C.c_uint64]
@@ -92,8 +94,8 @@ class Problem:
     def export_image(self, path):
         _check(lib().celerref_export_image(self.h, path.encode()))
 
-    def stepper(self, num_track_slots):
-        return Stepper(self, num_track_slots)
+    def stepper(self, num_track_slots, stream_id=0):
+        return Stepper(self, num_track_slots, stream_id)
 
     def calo(self, n):
         out = np.zeros(n)
@@ -156,10 +158,10 @@ class Problem:
 
 
 class Stepper:
-    def __init__(self, problem, num_track_slots):
+    def __init__(self, problem, num_track_slots, stream_id=0):
         self.problem = problem
         self.n = num_track_slots
-        self.h = lib().celerref_stepper_create(problem.h, num_track_slots)
+        self.h = lib().celerref_stepper_create_stream(problem.h, num_track_slots, stream_id)
         if not self.h:
             raise RuntimeError(lib().celerref_last_error().decode())
 

@@ -125,14 +125,23 @@ uint32_t celerref_num_actions(void* p)
 }
 
 //---------------------------------------------------------------------------//
+void* celerref_stepper_create_stream(void* problem, uint32_t num_track_slots, uint32_t stream_id);
+
 void* celerref_stepper_create(void* problem, uint32_t num_track_slots)
+{
+    return celerref_stepper_create_stream(problem, num_track_slots, 0);
+}
+
+// Stepper on a given stream (the problem's max_streams must exceed it): the RNG states
+// of a stream are seeded from {seed, stream_id} (random/XorwowRngData.cc:28-58)
+void* celerref_stepper_create_stream(void* problem, uint32_t num_track_slots, uint32_t stream_id)
 {
     void* result = nullptr;
     guarded([&] {
         auto* p = static_cast<celerref::Problem*>(problem);
         StepperInput inp;
         inp.params = p->core;
-        inp.stream_id = StreamId{0};
+        inp.stream_id = StreamId{stream_id};
         inp.num_track_slots = num_track_slots;
         auto s = std::make_unique<RefStepper>();
         s->problem = p;

@@ -88,12 +88,14 @@ def run_reference(refp, primaries, offsets, slots, max_steps=0):
     return ref, events
 
 
-def test_diagnostics_match_reference():
+@pytest.mark.parametrize('fuse', [0, 0xffffffff], ids=['fused', 'per-action'])
+def test_diagnostics_match_reference(fuse):
     import celeritas_b200 as cb
     slots, bins = 2048, 30
     refp = reference_problem('testem3-small', action_diagnostic=True, step_diagnostic_bins=bins)
     params = cb.Params(data_path('images', 'testem3-small.b2img'))
-    gpu = cb.Stepper(params, slots, action_diagnostic=True, step_diagnostic_bins=bins)
+    gpu = cb.Stepper(params, slots, action_diagnostic=True, step_diagnostic_bins=bins,
+                     fuse_threshold=fuse)
     assert 'action-diagnostic' in gpu.step_action_labels
     assert 'step-diagnostic' in gpu.step_action_labels
     opts = dict(PRIMARY_OPTIONS, num_events=1, primaries_per_event=6, position=[-22, 0, 0],

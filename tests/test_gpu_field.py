@@ -22,8 +22,9 @@ def isotropic_mix(n, energy, params, seed=1):
     return prim
 
 
+@pytest.mark.parametrize('fuse', [0, 0xffffffff], ids=['fused', 'per-action'])
 @pytest.mark.parametrize('energy,nprim,slots', [(10.0, 16, 1024), (1000.0, 4, 65536)])
-def test_lockstep_field(energy, nprim, slots):
+def test_lockstep_field(energy, nprim, slots, fuse):
     import celeritas_b200 as cb
     import celerref
     from parity import lockstep
@@ -31,7 +32,7 @@ def test_lockstep_field(energy, nprim, slots):
     refp = celerref.Problem(cfg)
     ref = refp.stepper(slots)
     params = cb.Params(data_path('images', 'simple-cms-em-field.b2img'))
-    gpu = cb.Stepper(params, slots)
+    gpu = cb.Stepper(params, slots, fuse_threshold=fuse)
     hist = lockstep(ref, gpu, isotropic_mix(nprim, energy, params), max_iters=20000)
     assert not (hist[-1]['alive'] or hist[-1]['queued'])
     assert np.allclose(refp.calo(5), gpu.calo(), rtol=1e-9, atol=1e-9)

@@ -12,14 +12,20 @@ from conftest import data_path
 pytestmark = pytest.mark.gpu
 
 
-def setup(name, slots):
+NEVER_FUSE = 0xffffffff
+
+
+def setup(name, slots, fuse_threshold=0):
+    """fuse_threshold: 0 = library default (these small problems then run every iteration
+    as ONE fused launch); NEVER_FUSE = one launch per action (the path large iterations
+    take). Both must reproduce the reference."""
     import celeritas_b200 as cb
     import celerref
     cfg = json.load(open(data_path('images', name + '.json')))
     ref_problem = celerref.Problem(cfg)
     ref = ref_problem.stepper(slots)
     params = cb.Params(data_path('images', name + '.b2img'))
-    gpu = cb.Stepper(params, slots)
+    gpu = cb.Stepper(params, slots, fuse_threshold=fuse_threshold)
     return ref_problem, ref, params, gpu
 
 
@@ -36,17 +42,28 @@ def test_lockstep_nomsc(energy, nprim, slots, iters):
     lockstep(ref, gpu, electrons(nprim, energy, params), max_iters=iters)
 
 
+@pytest.mark.parametrize('fuse', [0, NEVER_FUSE], ids=['fused', 'per-action'])
 @pytest.mark.parametrize('energy,nprim,slots,iters', [(10.0, 8, 256, 300), (1000.0, 2, 4096, 100000)])
-def test_lockstep_full_em(energy, nprim, slots, iters):
+def test_lockstep_full_em(energy, nprim, slots, iters, fuse):
     from parity import lockstep
-    _, ref, params, gpu = setup('testem3-small', slots)
+    _, ref, params, gpu = setup('testem3-small', slots, fuse)
     lockstep(ref, gpu, electrons(nprim, energy, params), max_iters=iters)
+
+
+def test_mixed_fused_and_per_action_iterations():
+    """A threshold inside the shower's size range: iterations switch between the fused
+    launch and the per-action launches (with their per-model interaction lists)."""
+    from parity import lockstep
+    _, ref, params, gpu = setup('testem3-small', 4096, fuse_threshold=150)
+    hist = lockstep(ref, gpu, electrons(3, 1000.0, params), compare_every=7)
+    sizes = [h['active'] for h in hist]
+    assert min(sizes) < 150 < max(sizes)
 
 
 def test_calo_tally_matches_reference():
     """Per-layer energy deposition of a whole shower vs the reference (same RNG streams)."""
     from parity import lockstep
-    refp, ref, params, gpu = setup('testem3-small', 8192)
+    refp, ref, params, gpu = setup('testem3-small', 8192, NEVER_FUSE)
     lockstep(ref, gpu, electrons(4, 1000.0, params), compare_every=50)
     a = refp.calo(100)
     b = gpu.calo()
