@@ -688,6 +688,52 @@ B2_D Intersection unit_intersect(GeoParams const& g,
     u32 on_face = (st.surface != INVALID) ? volume_find_face(g, vol, st.surface) : INVALID;
     bool const simple = !(vol.flags & (VOL_INTERNAL_SURFACES | VOL_IMPLICIT));
 
+    if (simple)
+    {
+        // Nearest intersection over the faces, kept in registers. Same choice as the
+        // general path below (first of the smallest distances in face order) without
+        // its per-thread arrays: those are indexed by a per-thread count, so every
+        // lane's access landed in a different local-memory sector (ncu: 1.1 useful
+        // bytes per 32-byte sector, profiles/README_r01.md).
+        real best_dist = real_inf();
+        u32 best_face = INVALID;
+        for (u32 f = 0; f < vol.num_faces; ++f)
+        {
+            SurfaceRef s = get_surface(g, u, volume_surface(g, vol, f));
+            bool on = (f == on_face);
+            int nroots = surface_num_isect(s.type);
+            if (nroots == 1 && on)
+                continue;
+            Roots r = surface_intersect(s, st.pos, st.dir, on);
+            for (int k = 0; k < nroots; ++k)
+            {
+                real d = r.r[k];
+                bool valid = limited ? (d <= max_dist) : (d < real_max());
+                if (valid && (best_face == INVALID || d < best_dist))
+                {
+                    best_dist = d;
+                    best_face = f;
+                }
+            }
+        }
+        Intersection result{INVALID, 0, real_inf()};
+        if (best_face != INVALID)
+        {
+            u32 surface = volume_surface(g, vol, best_face);
+            u8 cur_sense;
+            if (surface == st.surface)
+                cur_sense = st.sense;
+            else
+                cur_sense = surface_sense(get_surface(g, u, surface), st.pos) >= 0;
+            result.surface = surface;
+            result.sense = cur_sense;
+            result.distance = best_dist;
+        }
+        if (limited && result.surface == INVALID)
+            result.distance = max_dist;
+        return result;
+    }
+
     real dist[ORANGE_MAX_ISECT];
     u8 face_of[ORANGE_MAX_ISECT];
     u32 num_isect = 0;
