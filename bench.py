@@ -29,7 +29,10 @@ sys.path.insert(0, REPO)
 
 import numpy as np  # noqa: E402
 
-IMAGE = os.path.join(REPO, 'data', 'images', 'testem3.b2img')
+# GPU arm: track_order = init_charge, the reference's own default when use_device is true
+# (app/celer-sim/RunnerInputIO.json.cc:113-120); CPU arm: the reference's CPU default (none).
+# Same geometry, physics tables, seed and primaries.
+IMAGE = os.path.join(REPO, 'data', 'images', 'testem3-initcharge.b2img')
 CONFIG = os.path.join(REPO, 'data', 'images', 'testem3.json')
 NUM_EVENTS = 100
 PRIMARIES_PER_EVENT = 100
@@ -40,6 +43,12 @@ NUM_TRACK_SLOTS = 1 << 20
 # profiles/README_r01.md; 1 stream 6.8e8, 2 streams 7.5e8, 3 streams 7.6e8, 4 streams 7.5e8)
 NUM_STREAMS = 2
 ALG_BYTES_PER_TRACK_STEP = 672  # 2 * S_live, D=1, P=4
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE along-step launch (charged + neutral
+# kernels) at a saturated iteration, ~8.0e5 live tracks, from `ncu --set full`
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 557.8e6 + 324.0e6 + 181.3e6 + 77.0e6
+NCU_TRAFFIC_SOURCE = ('profiles/saturated_kernels_r01d.txt: k_along_step_charged<0> + '
+                      'k_along_step_neutral at one saturated iteration (8.0e5 live tracks = '
+                      '5.4e8 algorithmic bytes at 672 B per track-step)')
 
 
 def make_events(num_events, per_event, first_event, particle_id, dtype):
@@ -227,7 +236,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
-    params = cb.Params(IMAGE)
+    params = cb.Params(os.environ.get('B200_BENCH_IMAGE', IMAGE))
     nstreams = max(args.streams, 1)
     steppers = [cb.Stepper(params, args.slots // nstreams, stream_id=rank * nstreams + k)
                 for k in range(nstreams)]
@@ -270,7 +279,7 @@ def main():
         return calo.cpu().numpy(), counts.cpu().numpy()
 
     for _ in range(args.warmup):
-        one_pass()
+        reduce_tallies(one_pass())
 
     # ---- timed region 1: e2e through the public C-ABI with HOST buffers
     launches0 = cb.launch_count()
@@ -324,8 +333,8 @@ def main():
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': 'TestEm3 full EM (Urban MSC + eloss fluctuations), %d x %d 1 GeV e- '
                                'primaries per GPU, merged events, %d track slots over %d '
-                               'concurrent stream(s); steel/lAr stand-in physics '
-                               '(tools/make_physics.py)'
+                               'concurrent stream(s), track_order init_charge; steel/lAr '
+                               'stand-in physics (tools/make_physics.py)'
                                % (args.events, args.primaries_per_event, args.slots, nstreams),
                    'l2': 'working set %.0f MB of SoA state per pass exceeds the 126 MB L2'
                          % (args.slots * 336 / 1e6),
@@ -339,7 +348,8 @@ def main():
         'gpu_launches': int(launches),
         'clocks': clocks.summary(),
         'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': achieved, 'peak': peak,
-                     'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                     'unit': 'GB/s', 'frac': achieved / peak, 'traffic': NCU_TRAFFIC_BYTES_PER_LAUNCH,
+                     'traffic_source': NCU_TRAFFIC_SOURCE,
                      'peak_kind': peak_kind,
                      'kernel_share_of_step': top_secs / total_action_secs,
                      'per_action_seconds': per_action},

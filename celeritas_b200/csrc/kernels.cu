@@ -78,6 +78,7 @@ B2_D u32 active_slot(StateView const& s, u32 tid)
 __global__ void k_extend_from_primaries(StateView s,
                                         B200Primary const* __restrict__ primaries,
                                         u32 const* __restrict__ rank_in_event,
+                                        u32 const* __restrict__ neutral_inclusive,
                                         u32 n)
 {
     u32 tid = thread_id();
@@ -102,6 +103,13 @@ __global__ void k_extend_from_primaries(StateView s,
     {
         s.ti_pos[k * s.init_capacity + idx] = pr.pos[k];
         s.ti_dir[k * s.init_capacity + idx] = pr.dir[k];
+    }
+    if (s.ti_neutral_prefix && neutral_inclusive)
+    {
+        // init_charge: neutral initializers in [0, idx] (host-side inclusive count of the
+        // neutral primaries up to this one, on top of the queue's count so far)
+        s.ti_neutral_prefix[idx + 1]
+            = s.ti_neutral_prefix[s.counters[CTR_NUM_INITIALIZERS]] + neutral_inclusive[tid];
     }
 }
 
@@ -134,7 +142,29 @@ __global__ void __launch_bounds__(BLOCK) k_initialize_tracks(B2_GRID_CONSTANT Pa
     if (tid >= num_new)
         return;
     u32 ti = num_init - tid - 1;
-    u32 slot = s.vacancies[num_vac - tid - 1];
+    u32 slot;
+    if (p.scalars.track_order == ORDER_INIT_CHARGE)
+    {
+        // The reference stable-partitions the num_new initializers about to start into
+        // neutral | charged and walks them from the back: charged tracks take the highest
+        // vacancies, neutral tracks the lowest (InitTracksExecutor.hh:71-96,
+        // detail/Utils.hh:88-98, TrackInitAlgorithms.cc:80-96). With the running neutral
+        // count of the queue that is, for the initializer of rank r among the starting
+        // neutral (charged) ones: vacancies[r] (vacancies[num_vac - num_charged + r]).
+        u32 const first = num_init - num_new;
+        u32 const neutral_before_first = s.ti_neutral_prefix[first];
+        u32 const num_neutral = s.ti_neutral_prefix[num_init] - neutral_before_first;
+        u32 const neutral_rank = s.ti_neutral_prefix[ti] - neutral_before_first;
+        bool const is_neutral = p.particle.charge[s.ti_particle_id[ti]] == 0;
+        if (is_neutral)
+            slot = s.vacancies[neutral_rank];
+        else
+            slot = s.vacancies[num_vac - (num_new - num_neutral) + ((ti - first) - neutral_rank)];
+    }
+    else
+    {
+        slot = s.vacancies[num_vac - tid - 1];
+    }
 
     // sim
     s.track_id[slot] = s.ti_track_id[ti];
@@ -696,6 +726,7 @@ struct SlotEnd
     u32 is_vacant;
     u32 num_sec;      // secondaries that become initializers
     u32 num_sec_all;  // including one that reuses the slot in place
+    u32 num_sec_neutral;  // of num_sec, how many are neutral (init_charge bookkeeping)
     u32 charged;      // stays active with a charged particle
     u32 neutral;      // stays active with a neutral particle
     bool reuse_slot;  // first secondary replaces a dead parent in place
@@ -703,11 +734,12 @@ struct SlotEnd
 
 B2_D SlotEnd classify_slot(ParamsView const& p, StateView const& s, u32 slot)
 {
-    SlotEnd r{0, 0, 0, 0, 0, false};
+    SlotEnd r{0, 0, 0, 0, 0, 0, false};
     if (slot >= s.num_slots)
         return r;
     u8 status = s.status[slot];
     u32 first_sec = INVALID;
+    bool const by_charge = p.scalars.track_order == ORDER_INIT_CHARGE;
     if (status != ST_INACTIVE)
     {
         for (int i = MAX_SECONDARIES - 1; i >= 0; --i)
@@ -717,6 +749,8 @@ B2_D SlotEnd classify_slot(ParamsView const& p, StateView const& s, u32 slot)
             {
                 ++r.num_sec;
                 first_sec = sp;
+                if (by_charge && p.particle.charge[sp] == 0)
+                    ++r.num_sec_neutral;
             }
         }
     }
@@ -746,8 +780,13 @@ B2_D SlotEnd classify_slot(ParamsView const& p, StateView const& s, u32 slot)
 }
 
 // Packed scan words: A = vacant | charged << 10 | neutral << 20 (each <= BLOCK),
-//                    B = num_sec | num_sec_all << 16 (each <= 2 * BLOCK)
-static_assert(BLOCK <= 512 && MAX_SECONDARIES * BLOCK < 65536, "packed scan field widths");
+//   B = num_sec | num_sec_all << 10 | num_sec_neutral << 20 (each <= MAX_SECONDARIES * BLOCK)
+static_assert(BLOCK <= 512 && MAX_SECONDARIES * BLOCK < 1024, "packed scan field widths");
+
+B2_D u32 pack_secondaries(SlotEnd const& e)
+{
+    return e.num_sec | (e.num_sec_all << 10) | (e.num_sec_neutral << 20);
+}
 
 __global__ void __launch_bounds__(BLOCK) k_end_pass1(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
@@ -755,7 +794,7 @@ __global__ void __launch_bounds__(BLOCK) k_end_pass1(B2_GRID_CONSTANT ParamsView
     SlotEnd e = classify_slot(p, s, slot);
     u32 ta, tb;
     block_exclusive_scan<BLOCK, u32>(e.is_vacant | (e.charged << 10) | (e.neutral << 20), &ta);
-    block_exclusive_scan<BLOCK, u32>(e.num_sec | (e.num_sec_all << 16), &tb);
+    block_exclusive_scan<BLOCK, u32>(pack_secondaries(e), &tb);
     // Lowest block that held a track during this step: next step's passes start there
     bool const busy = slot < s.num_slots && s.status[slot] != ST_INACTIVE;
     bool const any_busy = __syncthreads_or(busy);
@@ -767,14 +806,15 @@ __global__ void __launch_bounds__(BLOCK) k_end_pass1(B2_GRID_CONSTANT ParamsView
         s.block_scratch[blockIdx.x] = ta & 0x3ffu;
         s.block_scratch[nb + blockIdx.x] = (ta >> 10) & 0x3ffu;
         s.block_scratch[2 * nb + blockIdx.x] = (ta >> 20) & 0x3ffu;
-        s.block_scratch[3 * nb + blockIdx.x] = tb & 0xffffu;
-        s.block_scratch[4 * nb + blockIdx.x] = tb >> 16;
+        s.block_scratch[3 * nb + blockIdx.x] = tb & 0x3ffu;
+        s.block_scratch[4 * nb + blockIdx.x] = (tb >> 10) & 0x3ffu;
+        s.block_scratch[5 * nb + blockIdx.x] = (tb >> 20) & 0x3ffu;
     }
 }
 
 __global__ void __launch_bounds__(1024) k_end_pass2(StateView s, u32 num_blocks)
 {
-    // Five blocks, one per scanned quantity: each thread owns a run of consecutive
+    // Six blocks, one per scanned quantity: each thread owns a run of consecutive
     // block totals; the last block to finish publishes the global counters.
     constexpr int B = 1024;
     u32 const a = blockIdx.x;
@@ -823,15 +863,15 @@ __global__ void __launch_bounds__(1024) k_end_pass2(StateView s, u32 num_blocks)
         s.counters[CTR_SCAN_TOTALS + a] = total;
         __threadfence();
         u32 done = atomicAdd(&s.counters[CTR_SCAN_DONE], 1u);
-        is_last = (done == 4);
+        is_last = (done == gridDim.x - 1);
     }
     __syncthreads();
     if (is_last && threadIdx.x == 0)
     {
         __threadfence();
         s.counters[CTR_SCAN_DONE] = 0;
-        u32 carry[5];
-        for (int k = 0; k < 5; ++k)
+        u32 carry[6];
+        for (int k = 0; k < 6; ++k)
             carry[k] = reinterpret_cast<u32 volatile*>(s.counters)[CTR_SCAN_TOTALS + k];
         // slots below slot_begin are all vacant
         u32 num_vac = carry[0] + s.slot_begin;
@@ -863,13 +903,15 @@ __global__ void __launch_bounds__(BLOCK) k_end_pass3(B2_GRID_CONSTANT ParamsView
     u32 const nb = gridDim.x;
     u32 sa = block_exclusive_scan<BLOCK, u32>(
         e.is_vacant | (e.charged << 10) | (e.neutral << 20), &ta);
-    u32 sb = block_exclusive_scan<BLOCK, u32>(e.num_sec | (e.num_sec_all << 16), &tb);
+    u32 sb = block_exclusive_scan<BLOCK, u32>(pack_secondaries(e), &tb);
     // vacancies[i] = i for the (all vacant) slots below slot_begin
     u32 vac_off = s.slot_begin + (sa & 0x3ffu) + s.block_scratch[blockIdx.x];
     u32 chg_off = ((sa >> 10) & 0x3ffu) + s.block_scratch[nb + blockIdx.x];
     u32 neu_off = ((sa >> 20) & 0x3ffu) + s.block_scratch[2 * nb + blockIdx.x];
-    u32 sec_off = (sb & 0xffffu) + s.block_scratch[3 * nb + blockIdx.x];
-    u32 all_off = (sb >> 16) + s.block_scratch[4 * nb + blockIdx.x];
+    u32 sec_off = (sb & 0x3ffu) + s.block_scratch[3 * nb + blockIdx.x];
+    u32 all_off = ((sb >> 10) & 0x3ffu) + s.block_scratch[4 * nb + blockIdx.x];
+    // neutral initializers created by lower slots in this step (init_charge only)
+    u32 neutral_off = ((sb >> 20) & 0x3ffu) + s.block_scratch[5 * nb + blockIdx.x];
     if (slot >= s.num_slots)
         return;
     if (s.counters[CTR_ERROR] != 0)
@@ -901,6 +943,9 @@ __global__ void __launch_bounds__(BLOCK) k_end_pass3(B2_GRID_CONSTANT ParamsView
     u32 const num_init = s.counters[CTR_NUM_INITIALIZERS];
     u32 const num_sec_total = s.counters[CTR_NUM_SECONDARIES];
     u32 out = num_init - num_sec_total + sec_off;
+    u32 neutral_run = 0;
+    if (s.ti_neutral_prefix && e.num_sec_all > 0)
+        neutral_run = s.ti_neutral_prefix[num_init - num_sec_total] + neutral_off;
     bool initialized = false;
     u32 const n = s.num_slots;
     u32 const cap = s.init_capacity;
@@ -971,6 +1016,13 @@ __global__ void __launch_bounds__(BLOCK) k_end_pass3(B2_GRID_CONSTANT ParamsView
                 {
                     s.ti_vol[l * cap + out] = s.geo_vol[l * n + slot];
                     s.ti_univ[l * cap + out] = s.geo_univ[l * n + slot];
+                }
+                if (s.ti_neutral_prefix)
+                {
+                    // running count of neutral initializers in queue order
+                    if (p.particle.charge[spid] == 0)
+                        ++neutral_run;
+                    s.ti_neutral_prefix[out + 1] = neutral_run;
                 }
                 ++out;
             }
@@ -1055,14 +1107,17 @@ int b200_step_extend_from_primaries(B200StateView const* state,
                                     uint32_t const* d_rank_in_event,
                                     uint32_t const* d_event_ids,
                                     uint32_t const* d_event_counts,
+                                    uint32_t const* d_neutral_inclusive,
                                     uint32_t num_events,
                                     uint32_t n,
                                     cudaStream_t stream)
 {
     if (n == 0)
         return 0;
+    if (SV(state).ti_neutral_prefix && !d_neutral_inclusive)
+        return B200_ERR_INVALID_ARGUMENT;
     k_extend_from_primaries<<<grid_for(n), BLOCK, 0, stream>>>(
-        SV(state), d_primaries, d_rank_in_event, n);
+        SV(state), d_primaries, d_rank_in_event, d_neutral_inclusive, n);
     k_primaries_finalize<<<grid_for(num_events), BLOCK, 0, stream>>>(
         SV(state), d_event_ids, d_event_counts, num_events, n);
     B2_COUNT(2);
@@ -1232,7 +1287,7 @@ int b200_step_extend_from_secondaries(B200ParamsView const* params,
         return B200_ERR_INVALID_ARGUMENT;
     unsigned nb = grid_for(s.num_slots - s.slot_begin);
     k_end_pass1<<<nb, BLOCK, 0, stream>>>(PV(params), s);
-    k_end_pass2<<<5, 1024, 0, stream>>>(s, nb);
+    k_end_pass2<<<6, 1024, 0, stream>>>(s, nb);
     k_end_pass3<<<nb, BLOCK, 0, stream>>>(PV(params), s);
     B2_COUNT(3);
     return check_launch();

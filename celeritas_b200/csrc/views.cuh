@@ -538,7 +538,11 @@ struct StateView
 
     // device-resident counters (mirrors CoreStateCounters) + scratch
     u32* counters;           // see Counter enum
-    u32* block_scratch;      // [5 * num_blocks] per-block totals for the end-of-step scans
+    u32* block_scratch;      // [6 * num_blocks] per-block totals for the end-of-step scans
+    // TrackOrder::init_charge only: ti_neutral_prefix[i] = neutral initializers in [0, i),
+    // kept up to date as the queue grows; gives every starting track its rank among the
+    // neutral / charged tracks started in the same step without a partition pass
+    u32* ti_neutral_prefix;  // [init_capacity + 1]
     u32 single_event;        // event id if exactly one event is in flight, else INVALID
     // host-side upper bounds used only to size grids (kernels re-check device counters)
     u32 hint_active;
@@ -585,8 +589,8 @@ enum Counter : u32
     CTR_NUM_CHARGED,   // entries at the front of track_slots
     CTR_NUM_NEUTRAL,   // entries at the back of track_slots
     CTR_SCAN_DONE,     // blocks of the end-of-step scan that have finished
-    CTR_SCAN_TOTALS,   // 5 totals
-    CTR_FIRST_BUSY_BLOCK = CTR_SCAN_TOTALS + 5,  // first 128-slot block that held a track this step
+    CTR_SCAN_TOTALS,   // 6 totals
+    CTR_FIRST_BUSY_BLOCK = CTR_SCAN_TOTALS + 6,  // first 128-slot block that held a track this step
     CTR_SIZE = 24
 };
 

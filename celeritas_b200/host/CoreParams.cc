@@ -207,6 +207,7 @@ void CoreParams::load(Image const& img)
         pp.num_particles = img.get<double>("particle.mass").size();
         pp.mass = F64("particle.mass");
         pp.charge = F64("particle.charge");
+        particle_charge_ = img.get<double>("particle.charge");
         pp.decay_constant = F64("particle.decay_constant");
         pp.matter = U8("particle.matter");
         particle_names_ = split_lines(img.get_string("particle.names"));

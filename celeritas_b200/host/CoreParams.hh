@@ -66,6 +66,10 @@ class CoreParams
     uint32_t max_events() const { return max_events_; }
     uint32_t rng_seed() const { return view_.rng.seed; }
     uint32_t find_particle(int pdg) const;
+    bool particle_is_neutral(uint32_t particle_id) const
+    {
+        return particle_id < particle_charge_.size() && particle_charge_[particle_id] == 0;
+    }
     size_t device_bytes() const { return arena_.bytes(); }
 
     //!@{
@@ -89,6 +93,7 @@ class CoreParams
     std::vector<std::string> volume_labels_;
     std::vector<std::string> particle_names_;
     std::vector<int> particle_pdg_;
+    std::vector<double> particle_charge_;
     std::vector<std::string> detector_volumes_;
     uint32_t const* d_detector_of_volume_{nullptr};
     uint32_t init_capacity_{0};

@@ -119,7 +119,9 @@ CoreState::CoreState(std::shared_ptr<CoreParams const> params,
         ctr[CTR_NUM_VACANCIES] = n;
         s.counters = const_cast<u32*>(arena_.upload(ctr));
         uint32_t num_blocks = (n + 127) / 128;
-        s.block_scratch = arena_.alloc<u32>(size_t(5) * num_blocks);
+        s.block_scratch = arena_.alloc<u32>(size_t(6) * num_blocks);
+        if (p.scalars.track_order == ORDER_INIT_CHARGE)
+            s.ti_neutral_prefix = arena_.alloc<u32>(size_t(params_->init_capacity()) + 1);
         s.single_event = INVALID;
         s.step_counters = arena_.alloc<u64>(4);
     }

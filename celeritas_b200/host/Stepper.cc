@@ -58,7 +58,8 @@ struct Stepper::Staging
     uint32_t count{0};
     uint32_t num_events{0};
     B200Primary* h_primaries{nullptr};  // pinned
-    uint32_t* h_aux{nullptr};           // pinned: rank[cap], event_ids[cap], event_counts[cap]
+    // pinned: rank[cap], event_ids[cap], event_counts[cap], neutral_inclusive[cap]
+    uint32_t* h_aux{nullptr};
     B200Primary* d_primaries{nullptr};
     uint32_t* d_aux{nullptr};
 
@@ -70,9 +71,9 @@ struct Stepper::Staging
         capacity = std::max<uint32_t>(n, 1024);
         B2_CUDA_CALL(cudaMallocHost(reinterpret_cast<void**>(&h_primaries),
                                     capacity * sizeof(B200Primary)));
-        B2_CUDA_CALL(cudaMallocHost(reinterpret_cast<void**>(&h_aux), 3 * capacity * sizeof(uint32_t)));
+        B2_CUDA_CALL(cudaMallocHost(reinterpret_cast<void**>(&h_aux), 4 * capacity * sizeof(uint32_t)));
         B2_CUDA_CALL(cudaMalloc(reinterpret_cast<void**>(&d_primaries), capacity * sizeof(B200Primary)));
-        B2_CUDA_CALL(cudaMalloc(reinterpret_cast<void**>(&d_aux), 3 * capacity * sizeof(uint32_t)));
+        B2_CUDA_CALL(cudaMalloc(reinterpret_cast<void**>(&d_aux), 4 * capacity * sizeof(uint32_t)));
     }
     void release()
     {
@@ -341,6 +342,17 @@ void Stepper::insert(B200Primary const* primaries, uint32_t n)
             throw std::runtime_error("primary event id exceeds max_events");
         rank[i] = counts[primaries[i].event_id]++;
     }
+    // TrackOrder::init_charge: running count of neutral primaries (see k_initialize_tracks)
+    {
+        uint32_t* neutral_inclusive = st.h_aux + 3 * st.capacity;
+        uint32_t running = 0;
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            if (params_->particle_is_neutral(primaries[i].particle_id))
+                ++running;
+            neutral_inclusive[i] = running;
+        }
+    }
     uint32_t ne = 0;
     for (auto const& kv : counts)
     {
@@ -376,6 +388,9 @@ void Stepper::step_async()
                                   ? n
                                   : std::min<uint64_t>(n, last_.first_busy_block * block);
         uint64_t slot_begin = busy_begin > fresh ? (busy_begin - fresh) / block * block : 0;
+        // init_charge gives neutral tracks the LOWEST vacancies: the whole range is live
+        if (params_->view().scalars.track_order == ORDER_INIT_CHARGE)
+            slot_begin = 0;
         state.launch_hints(std::min<uint64_t>(n, last_.num_alive + fresh),
                            std::min<uint64_t>(n, last_.num_charged + fresh),
                            std::min<uint64_t>(n, last_.num_neutral + fresh),
@@ -392,7 +407,7 @@ void Stepper::step_async()
                                      stream));
         B2_CUDA_CALL(cudaMemcpyAsync(st.d_aux,
                                      st.h_aux,
-                                     3 * st.capacity * sizeof(uint32_t),
+                                     4 * st.capacity * sizeof(uint32_t),
                                      cudaMemcpyHostToDevice,
                                      stream));
         check_rc(b200_step_extend_from_primaries(sv(state),
@@ -400,6 +415,7 @@ void Stepper::step_async()
                                                  st.d_aux,
                                                  st.d_aux + st.capacity,
                                                  st.d_aux + 2 * st.capacity,
+                                                 st.d_aux + 3 * st.capacity,
                                                  st.num_events,
                                                  st.count,
                                                  stream),

@@ -146,6 +146,7 @@ int b200_step_extend_from_primaries(B200StateView const* state,
                                     uint32_t const* d_rank_in_event,
                                     uint32_t const* d_event_ids,
                                     uint32_t const* d_event_counts,
+                                    uint32_t const* d_neutral_inclusive, /* [n] number of neutral primaries in [0, i]; required for TrackOrder::init_charge problems, else may be NULL */
                                     uint32_t num_events,
                                     uint32_t n,
                                     cudaStream_t stream);

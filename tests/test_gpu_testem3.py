@@ -80,3 +80,23 @@ def test_lockstep_nested_geometry():
     hist = lockstep(ref, gpu, electrons(2, 1000.0, params), compare_every=1)
     assert not (hist[-1]['alive'] or hist[-1]['queued'])
     assert np.allclose(refp.calo(2), gpu.calo(), rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize('fuse', [0, NEVER_FUSE], ids=['fused', 'per-action'])
+@pytest.mark.parametrize('energy,nprim,slots', [(10.0, 8, 256), (1000.0, 3, 4096), (1000.0, 4, 512)])
+def test_lockstep_init_charge(energy, nprim, slots, fuse):
+    """TrackOrder::init_charge (the reference's GPU default, RunnerInputIO.json.cc:113-120):
+    starting tracks are partitioned by charge, neutral ones take the lowest vacancies and
+    charged ones the highest, and secondaries never reuse their parent's slot. Slot
+    assignment is part of the compared state (every field is compared slot by slot); the
+    512-slot case keeps initializers queued so that partial starts are exercised."""
+    from parity import lockstep
+    import celeritas_b200 as cb
+    _, ref, params, gpu = setup('testem3-small-initcharge', slots, fuse)
+    prim = electrons(nprim, energy, params)
+    # mixed charges among the primaries too
+    prim['particle_id'][1::2] = params.find_particle(22)
+    hist = lockstep(ref, gpu, prim, max_iters=100000)
+    assert not (hist[-1]['alive'] or hist[-1]['queued'])
+    if slots == 512:
+        assert max(h['queued'] for h in hist) > 0

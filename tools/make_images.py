@@ -53,6 +53,17 @@ PROBLEMS = {
                        'physics_file': 'data/physics/testem3-nested-steel-lar.json',
                        'seed': 20220904, 'initializer_capacity': 1 << 18, 'max_events': 64,
                        'simple_calo': ['gap', 'absorber']},
+    # the reference's GPU default track order: new tracks partitioned by charge
+    'testem3-small-initcharge': {'geometry_file': 'data/geometry/testem3-flat.org.json',
+                                 'physics_file': 'data/physics/testem3-steel-lar.json',
+                                 'seed': 20220904, 'initializer_capacity': 1 << 18,
+                                 'max_events': 64, 'track_order': 'init_charge',
+                                 'simple_calo': GAPS + ABSORBERS},
+    'testem3-initcharge': {'geometry_file': 'data/geometry/testem3-flat.org.json',
+                           'physics_file': 'data/physics/testem3-steel-lar.json',
+                           'seed': 20220904, 'initializer_capacity': 1 << 25,
+                           'max_events': 16384, 'track_order': 'init_charge',
+                           'simple_calo': GAPS + ABSORBERS},
     # small-capacity variant of the same physics for lock-step tests
     'testem3-small': {'geometry_file': 'data/geometry/testem3-flat.org.json',
                       'physics_file': 'data/physics/testem3-steel-lar.json',
