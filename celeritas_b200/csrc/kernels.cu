@@ -50,6 +50,12 @@ constexpr int BLOCK = 128;
 #    define B2_ALONG_SPLIT_THRESHOLD 0
 #endif
 constexpr int ALONG_MIN_BLOCKS = B2_ALONG_MIN_BLOCKS;
+// Software prefetch of the per-slot state at kernel entry (see prefetch_l2): 1 = to L2,
+// 2 = to L1. Measured: no effect either way (99.9 / 100.0 / 99.8 ms per pass for 0 / 1 / 2,
+// profiles/README_r01.md), so it is off.
+#ifndef B2_PREFETCH
+#    define B2_PREFETCH 0
+#endif
 
 // Size of StateView::interact_count (CoreState allocates this many counters)
 constexpr u32 MAX_INTERACT_MODELS_RESET = 16;
@@ -57,6 +63,80 @@ constexpr u32 MAX_INTERACT_MODELS_RESET = 16;
 B2_D u32 thread_id()
 {
     return blockIdx.x * blockDim.x + threadIdx.x;
+}
+
+//---------------------------------------------------------------------------//
+// The step kernels are bound by the latency of dependent loads of per-slot state
+// (ncu: ~60 % of stall samples are long-scoreboard, spread evenly over ~40 fields;
+// L2 hit rate 44 % because the state of 2^20 slots is three times the L2). A thread
+// knows its slot at entry, so it asks for every line it is going to touch right away:
+// the later loads then find their sectors in (or on the way to) L2.
+//---------------------------------------------------------------------------//
+B2_D void prefetch_l2(void const* ptr)
+{
+#if B2_PREFETCH == 2
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+#elif B2_PREFETCH
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+#else
+    (void)ptr;
+#endif
+}
+
+template<bool CHARGED>
+B2_D void prefetch_along_step_state(StateView const& s, u32 slot)
+{
+    u32 const n = s.num_slots;
+    prefetch_l2(s.step_length + slot);
+    prefetch_l2(s.energy + slot);
+    prefetch_l2(s.particle_id + slot);
+    prefetch_l2(s.material_id + slot);
+    prefetch_l2(s.post_step_action + slot);
+    prefetch_l2(s.interaction_mfp + slot);
+    prefetch_l2(s.macro_xs + slot);
+    prefetch_l2(s.time + slot);
+    prefetch_l2(s.num_steps + slot);
+    // geometry (level 0; deeper levels are rare and follow on demand)
+    u32 const ng = n * s.max_depth;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+        prefetch_l2(s.geo_pos + k * ng + slot);
+        prefetch_l2(s.geo_dir + k * ng + slot);
+    }
+    prefetch_l2(s.geo_vol + slot);
+    prefetch_l2(s.geo_univ + slot);
+    prefetch_l2(s.geo_level + slot);
+    prefetch_l2(s.geo_surface_level + slot);
+    prefetch_l2(s.geo_surf + slot);
+    prefetch_l2(s.geo_sense + slot);
+    prefetch_l2(s.geo_boundary + slot);
+    if (CHARGED)
+    {
+        prefetch_l2(s.dedx_range + slot);
+        prefetch_l2(s.energy_deposition + slot);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            prefetch_l2(s.msc_range + k * n + slot);
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            prefetch_l2(s.rng + k * n + slot);
+    }
+}
+
+B2_D void prefetch_pre_step_state(StateView const& s, u32 slot)
+{
+    u32 const n = s.num_slots;
+    prefetch_l2(s.interaction_mfp + slot);
+    prefetch_l2(s.particle_id + slot);
+    prefetch_l2(s.energy + slot);
+    prefetch_l2(s.material_id + slot);
+    prefetch_l2(s.geo_level + slot);
+    prefetch_l2(s.geo_vol + slot);
+    prefetch_l2(s.geo_univ + slot);
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        prefetch_l2(s.rng + k * n + slot);
 }
 
 //! i-th active slot: charged from the front, neutral from the back
@@ -295,7 +375,10 @@ __global__ void __launch_bounds__(BLOCK) k_pre_step(B2_GRID_CONSTANT ParamsView 
 {
     u32 slot = active_slot(s, thread_id());
     if (slot != INVALID)
+    {
+        prefetch_pre_step_state(s, slot);
         do_pre_step(p, s, slot);
+    }
 }
 
 //---------------------------------------------------------------------------//
@@ -308,6 +391,7 @@ __global__ void __launch_bounds__(BLOCK, ALONG_MIN_BLOCKS) k_along_step_charged(
     if (tid >= s.counters[CTR_NUM_CHARGED])
         return;
     u32 slot = s.track_slots[tid];
+    prefetch_along_step_state<true>(s, slot);
     if (s.status[slot] != ST_ALIVE)
         return;
     along_step<true, FIELD>(p, s, slot);
@@ -340,6 +424,7 @@ __global__ void __launch_bounds__(BLOCK) k_along_step_neutral(B2_GRID_CONSTANT P
     if (tid >= s.counters[CTR_NUM_NEUTRAL])
         return;
     u32 slot = s.track_slots[s.num_slots - 1 - tid];
+    prefetch_along_step_state<false>(s, slot);
     if (s.status[slot] != ST_ALIVE)
         return;
     along_step<false, false>(p, s, slot);
@@ -665,6 +750,94 @@ __global__ void __launch_bounds__(BLOCK, B2_FUSED_MIN_BLOCKS)
         u32 const nb = s.diag_step_bins;
         u32 const n = s.num_steps[slot];
         atomicAdd(&s.diag_step_counts[s.particle_id[slot] * nb + (n < nb - 1 ? n : nb - 1)], 1u);
+    }
+}
+
+//---------------------------------------------------------------------------//
+// The tail of a step in one launch for LARGE iterations: boundary crossing, tracking
+// cut, action diagnostic (order post), calorimeter tally and step diagnostic (order
+// user_post) are consecutive in the action sequence, each touches only its own slot, and
+// all but the boundary crossing are a few instructions per track: as separate launches
+// they each re-read the slot lists and the status and post-step action of every track.
+// Tallies go through per-block shared-memory bins as in k_tally / k_diagnostic.
+//---------------------------------------------------------------------------//
+__global__ void __launch_bounds__(BLOCK)
+    k_post_tail(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
+{
+    __shared__ real calo_bins[TALLY_SMEM_BINS];
+    __shared__ u32 action_bins[DIAG_SMEM_BINS];
+    __shared__ u32 step_bins[DIAG_SMEM_BINS];
+    u32 const num_det = s.calo_edep ? s.num_detectors : 0;
+    u32 const num_particles = p.particle.num_particles;
+    u32 const num_action = s.diag_action_counts ? s.diag_action_bins * num_particles : 0;
+    u32 const num_step = s.diag_step_counts ? s.diag_step_bins * num_particles : 0;
+    bool const calo_smem = num_det <= TALLY_SMEM_BINS;
+    bool const action_smem = num_action <= DIAG_SMEM_BINS;
+    bool const step_smem = num_step <= DIAG_SMEM_BINS;
+    static_assert(TALLY_SMEM_BINS == DIAG_SMEM_BINS, "one loop zeroes and flushes all bins");
+    u32 used_bins = calo_smem ? num_det : 0;
+    if (action_smem && num_action > used_bins)
+        used_bins = num_action;
+    if (step_smem && num_step > used_bins)
+        used_bins = num_step;
+    for (u32 i = threadIdx.x; i < used_bins; i += BLOCK)
+    {
+        calo_bins[i] = 0;
+        action_bins[i] = 0;
+        step_bins[i] = 0;
+    }
+    __syncthreads();
+
+    u32 const slot = active_slot(s, thread_id());
+    if (slot != INVALID)
+    {
+        do_boundary(p, s, slot);
+        do_tracking_cut(p, s, slot);
+        u8 const status = s.status[slot];
+        if (num_action && status != ST_INACTIVE)
+        {
+            u32 bin = s.particle_id[slot] * s.diag_action_bins + s.post_step_action[slot];
+            atomicAdd(action_smem ? &action_bins[bin] : &s.diag_action_counts[bin], 1u);
+        }
+        if (num_det && status != ST_INACTIVE)
+        {
+            real edep = s.energy_deposition[slot];
+            if (edep != 0)
+            {
+                u32 det = s.calo_detector_of_volume[s.pre_volume[slot]];
+                if (det != INVALID)
+                    atomicAdd(calo_smem ? &calo_bins[det] : &s.calo_edep[det], edep);
+            }
+        }
+        if (num_step && status == ST_KILLED)
+        {
+            u32 const nb = s.diag_step_bins;
+            u32 const n = s.num_steps[slot];
+            u32 bin = s.particle_id[slot] * nb + (n < nb - 1 ? n : nb - 1);
+            atomicAdd(step_smem ? &step_bins[bin] : &s.diag_step_counts[bin], 1u);
+        }
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < used_bins; i += BLOCK)
+    {
+        if (calo_smem && i < num_det)
+        {
+            real v = calo_bins[i];
+            if (v != 0)
+                atomicAdd(&s.calo_edep[i], v);
+        }
+        if (action_smem && i < num_action)
+        {
+            u32 v = action_bins[i];
+            if (v != 0)
+                atomicAdd(&s.diag_action_counts[i], v);
+        }
+        if (step_smem && i < num_step)
+        {
+            u32 v = step_bins[i];
+            if (v != 0)
+                atomicAdd(&s.diag_step_counts[i], v);
+        }
     }
 }
 
@@ -1248,6 +1421,14 @@ int b200_step_fused(B200ParamsView const* params, B200StateView const* state, cu
         k_step_fused<true><<<grid, BLOCK, 0, stream>>>(PV(params), s);
     else
         k_step_fused<false><<<grid, BLOCK, 0, stream>>>(PV(params), s);
+    B2_COUNT(1);
+    return check_launch();
+}
+
+int b200_step_post_tail(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    k_post_tail<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s);
     B2_COUNT(1);
     return check_launch();
 }

@@ -233,6 +233,32 @@ ActionSequence::ActionSequence(CoreParams const& params, Options options)
         fuse_threshold_ = static_cast<uint32_t>(std::strtoul(env, nullptr, 10));
     if (fuse_threshold_ == 0xffffffffu)
         fusable_ = false;
+
+    // The run [geo-boundary, tracking-cut, action-diagnostic?, tally?, step-diagnostic?] of
+    // consecutive built-in actions is one launch (b200_step_post_tail) when nothing else
+    // sits in between
+    tail_begin_ = tail_end_ = 0;
+    for (size_t i = 0; i < actions_.size(); ++i)
+    {
+        if (actions_[i]->label() != "geo-boundary")
+            continue;
+        size_t j = i + 1;
+        auto is_tail = [](std::string const& label) {
+            return label == "tracking-cut" || label == "action-diagnostic"
+                   || label == "step-diagnostic" || label.rfind("tally[", 0) == 0;
+        };
+        while (j < actions_.size() && is_tail(actions_[j]->label())
+               && dynamic_cast<KernelAction const*>(actions_[j].get()))
+            ++j;
+        if (j - i >= 2)
+        {
+            tail_begin_ = i;
+            tail_end_ = j;
+        }
+        break;
+    }
+    if (std::getenv("B200_NO_POST_TAIL"))
+        tail_begin_ = tail_end_ = 0;
 }
 
 ActionSequence::~ActionSequence()
@@ -262,8 +288,17 @@ void ActionSequence::step(CoreParams const& params, CoreState& state)
     }
     if (!action_times_)
     {
-        for (auto const& a : actions_)
-            a->step(params, state);
+        for (size_t i = 0; i < actions_.size(); ++i)
+        {
+            if (i == tail_begin_ && tail_end_ > tail_begin_)
+            {
+                check_rc(b200_step_post_tail(pv(params), sv(state), state.stream()),
+                         "step_post_tail");
+                i = tail_end_ - 1;
+                continue;
+            }
+            actions_[i]->step(params, state);
+        }
         return;
     }
     auto get_event = [this] {

@@ -105,6 +105,7 @@ class ActionSequence
     bool action_times_{false};
     bool fusable_{false};
     uint32_t fuse_threshold_{0};
+    size_t tail_begin_{0}, tail_end_{0};  // [begin, end) of the boundary..diagnostics run
     std::vector<double> accum_time_;
     struct Pending
     {

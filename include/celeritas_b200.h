@@ -166,6 +166,9 @@ int b200_step_extend_from_secondaries(B200ParamsView const*, B200StateView const
  * results: those actions only touch their own slot). The stepper uses it for small
  * iterations, where launch latency dominates; see B200StepperOptions::fuse_threshold. */
 int b200_step_fused(B200ParamsView const*, B200StateView const*, cudaStream_t);
+/* boundary + tracking-cut + action diagnostic + tally + step diagnostic (consecutive in the
+ * action sequence) in one launch; what the stepper uses for them in large iterations. */
+int b200_step_post_tail(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_step_action_diagnostic(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_step_step_diagnostic(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_reseed(B200ParamsView const*, B200StateView const*, uint64_t event_id, cudaStream_t);
