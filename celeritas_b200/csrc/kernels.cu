@@ -903,14 +903,40 @@ struct SlotEnd
     u32 charged;      // stays active with a charged particle
     u32 neutral;      // stays active with a neutral particle
     bool reuse_slot;  // first secondary replaces a dead parent in place
+    bool inactive;    // status == inactive at the end of the step
 };
+
+// The classification is computed once (pass 1) and handed to pass 3 as one byte per slot:
+// pass 3 then needs a single coalesced load instead of the chain status -> secondaries ->
+// particle -> charge that it took to classify.
+B2_D u8 pack_class(SlotEnd const& e)
+{
+    return u8(e.is_vacant | (e.charged << 1) | (u32(e.inactive) << 2) | (e.num_sec << 3)
+              | (e.num_sec_neutral << 5) | (u32(e.reuse_slot) << 7));
+}
+
+B2_D SlotEnd unpack_class(u8 c)
+{
+    SlotEnd e;
+    e.is_vacant = c & 1u;
+    e.charged = (c >> 1) & 1u;
+    e.inactive = (c >> 2) & 1u;
+    e.num_sec = (c >> 3) & 3u;
+    e.num_sec_neutral = (c >> 5) & 3u;
+    e.reuse_slot = (c >> 7) & 1u;
+    e.num_sec_all = e.num_sec + (e.reuse_slot ? 1u : 0u);
+    e.neutral = (!e.is_vacant && !e.charged) ? 1u : 0u;
+    return e;
+}
+static_assert(MAX_SECONDARIES <= 3, "two bits per secondary count in the class byte");
 
 B2_D SlotEnd classify_slot(ParamsView const& p, StateView const& s, u32 slot)
 {
-    SlotEnd r{0, 0, 0, 0, 0, 0, false};
+    SlotEnd r{0, 0, 0, 0, 0, 0, false, false};
     if (slot >= s.num_slots)
         return r;
     u8 status = s.status[slot];
+    r.inactive = (status == ST_INACTIVE);
     u32 first_sec = INVALID;
     bool const by_charge = p.scalars.track_order == ORDER_INIT_CHARGE;
     if (status != ST_INACTIVE)
@@ -969,7 +995,9 @@ __global__ void __launch_bounds__(BLOCK) k_end_pass1(B2_GRID_CONSTANT ParamsView
     block_exclusive_scan<BLOCK, u32>(e.is_vacant | (e.charged << 10) | (e.neutral << 20), &ta);
     block_exclusive_scan<BLOCK, u32>(pack_secondaries(e), &tb);
     // Lowest block that held a track during this step: next step's passes start there
-    bool const busy = slot < s.num_slots && s.status[slot] != ST_INACTIVE;
+    bool const busy = slot < s.num_slots && !e.inactive;
+    if (slot < s.num_slots)
+        s.slot_class[slot] = pack_class(e);
     bool const any_busy = __syncthreads_or(busy);
     if (threadIdx.x == 0)
     {
@@ -1071,7 +1099,8 @@ __global__ void __launch_bounds__(1024) k_end_pass2(StateView s, u32 num_blocks)
 __global__ void __launch_bounds__(BLOCK) k_end_pass3(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 slot = s.slot_begin + thread_id();
-    SlotEnd e = classify_slot(p, s, slot);
+    // classification of pass 1 (the same launch sequence; nothing changed in between)
+    SlotEnd e = unpack_class(slot < s.num_slots ? s.slot_class[slot] : u8(0));
     u32 ta, tb;
     u32 const nb = gridDim.x;
     u32 sa = block_exclusive_scan<BLOCK, u32>(
@@ -1096,8 +1125,7 @@ __global__ void __launch_bounds__(BLOCK) k_end_pass3(B2_GRID_CONSTANT ParamsView
     if (e.neutral)
         s.track_slots[s.num_slots - 1 - neu_off] = slot;
 
-    u8 status = s.status[slot];
-    if (status == ST_INACTIVE)
+    if (e.inactive)
     {
         // The reference's pre-step resets the step limit of inactive slots
         // (PreStepExecutor.hh:47-57); inactive slots are never visited by the dense
@@ -1201,7 +1229,8 @@ __global__ void __launch_bounds__(BLOCK) k_end_pass3(B2_GRID_CONSTANT ParamsView
             }
         }
     }
-    if (!initialized && status == ST_KILLED)
+    // a vacant slot that is not yet inactive holds a killed track
+    if (!initialized && e.is_vacant && s.status[slot] == ST_KILLED)
         s.status[slot] = ST_INACTIVE;
 }
 

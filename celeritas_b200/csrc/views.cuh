@@ -539,6 +539,7 @@ struct StateView
     // device-resident counters (mirrors CoreStateCounters) + scratch
     u32* counters;           // see Counter enum
     u32* block_scratch;      // [6 * num_blocks] per-block totals for the end-of-step scans
+    u8* slot_class;          // [slot] end-of-step classification, pass 1 -> pass 3
     // TrackOrder::init_charge only: ti_neutral_prefix[i] = neutral initializers in [0, i),
     // kept up to date as the queue grows; gives every starting track its rank among the
     // neutral / charged tracks started in the same step without a partition pass

@@ -120,6 +120,7 @@ CoreState::CoreState(std::shared_ptr<CoreParams const> params,
         s.counters = const_cast<u32*>(arena_.upload(ctr));
         uint32_t num_blocks = (n + 127) / 128;
         s.block_scratch = arena_.alloc<u32>(size_t(6) * num_blocks);
+        s.slot_class = arena_.alloc<u8>(n);
         if (p.scalars.track_order == ORDER_INIT_CHARGE)
             s.ti_neutral_prefix = arena_.alloc<u32>(size_t(params_->init_capacity()) + 1);
         s.single_event = INVALID;
