@@ -1166,7 +1166,26 @@ __global__ void __launch_bounds__(BLOCK) k_end_pass3(B2_GRID_CONSTANT ParamsView
         if (s.single_event != INVALID)
             id_base = s.counters[CTR_TRACK_ID_BASE] + all_off;
         else
-            id_base = atomicAdd(&s.track_counters[event], e.num_sec_all);
+        {
+            // One atomic per (warp, event) instead of one per track: with merged events
+            // a step creates ~1e5 secondaries on a few dozen counters. Lanes of the same
+            // event take consecutive ids in lane order (counts are 1 or 2 per lane).
+            unsigned const active = __activemask();
+            unsigned const group = __match_any_sync(active, event);
+            unsigned const lane = threadIdx.x & 31u;
+            unsigned const lower = group & ((1u << lane) - 1u);
+            unsigned const ones = __ballot_sync(active, e.num_sec_all == 1);
+            unsigned const twos = __ballot_sync(active, e.num_sec_all == 2);
+            static_assert(MAX_SECONDARIES == 2, "ballot-based offsets assume 1 or 2");
+            u32 const offset = __popc(lower & ones) + 2 * __popc(lower & twos);
+            u32 const total = __popc(group & ones) + 2 * __popc(group & twos);
+            int const leader = __ffs(group) - 1;
+            u32 base = 0;
+            if (int(lane) == leader)
+                base = atomicAdd(&s.track_counters[event], total);
+            base = __shfl_sync(group, base, leader);
+            id_base = base + offset;
+        }
 
         for (int i = 0; i < MAX_SECONDARIES; ++i)
         {
