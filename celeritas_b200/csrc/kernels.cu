@@ -50,6 +50,24 @@ constexpr int BLOCK = 128;
 #    define B2_ALONG_SPLIT_THRESHOLD 0
 #endif
 constexpr int ALONG_MIN_BLOCKS = B2_ALONG_MIN_BLOCKS;
+// Resident blocks per SM asked of the other large-iteration kernels. Measured, ms per pass
+// (profiles/README_r01.md): pre-step 15.3 -> 12.9, neutral along-step -1.9, end passes
+// 20.8 -> 16.7 when capped at 64 registers (8 blocks of 128 threads)
+#ifndef B2_PRE_MIN_BLOCKS
+#    define B2_PRE_MIN_BLOCKS 8
+#endif
+#ifndef B2_NEUTRAL_MIN_BLOCKS
+#    define B2_NEUTRAL_MIN_BLOCKS 8
+#endif
+#ifndef B2_INTERACT_MIN_BLOCKS
+#    define B2_INTERACT_MIN_BLOCKS 8
+#endif
+#ifndef B2_TAIL_MIN_BLOCKS
+#    define B2_TAIL_MIN_BLOCKS 8
+#endif
+#ifndef B2_END_MIN_BLOCKS
+#    define B2_END_MIN_BLOCKS 8
+#endif
 // Software prefetch of the per-slot state at kernel entry (see prefetch_l2): 1 = to L2,
 // 2 = to L1. Measured: no effect either way (99.9 / 100.0 / 99.8 ms per pass for 0 / 1 / 2,
 // profiles/README_r01.md), so it is off.
@@ -371,7 +389,7 @@ B2_D void do_pre_step(ParamsView const& p, StateView const& s, u32 slot)
     }
 }
 
-__global__ void __launch_bounds__(BLOCK) k_pre_step(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
+__global__ void __launch_bounds__(BLOCK, B2_PRE_MIN_BLOCKS) k_pre_step(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 slot = active_slot(s, thread_id());
     if (slot != INVALID)
@@ -418,7 +436,7 @@ B2_ALONG_PHASE_KERNEL(k_along_msc_apply, along_phase_msc_apply, B2_PHASE_MIN_BLO
 B2_ALONG_PHASE_KERNEL(k_along_finish, along_phase_finish, B2_PHASE_MIN_BLOCKS)
 #undef B2_ALONG_PHASE_KERNEL
 
-__global__ void __launch_bounds__(BLOCK) k_along_step_neutral(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
+__global__ void __launch_bounds__(BLOCK, B2_NEUTRAL_MIN_BLOCKS) k_along_step_neutral(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 tid = thread_id();
     if (tid >= s.counters[CTR_NUM_NEUTRAL])
@@ -516,7 +534,7 @@ __global__ void __launch_bounds__(BLOCK) k_interact(B2_GRID_CONSTANT ParamsView 
 
 //! Interactions over the per-model lists built by k_discrete_select: thread t works on
 //! the t-th interacting track in model order
-__global__ void __launch_bounds__(BLOCK) k_interact_lists(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
+__global__ void __launch_bounds__(BLOCK, B2_INTERACT_MIN_BLOCKS) k_interact_lists(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 tid = thread_id();
     u32 const num_models = p.phys.num_models;
@@ -761,7 +779,7 @@ __global__ void __launch_bounds__(BLOCK, B2_FUSED_MIN_BLOCKS)
 // they each re-read the slot lists and the status and post-step action of every track.
 // Tallies go through per-block shared-memory bins as in k_tally / k_diagnostic.
 //---------------------------------------------------------------------------//
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, B2_TAIL_MIN_BLOCKS)
     k_post_tail(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     __shared__ real calo_bins[TALLY_SMEM_BINS];
@@ -1096,7 +1114,7 @@ __global__ void __launch_bounds__(1024) k_end_pass2(StateView s, u32 num_blocks)
     }
 }
 
-__global__ void __launch_bounds__(BLOCK) k_end_pass3(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
+__global__ void __launch_bounds__(BLOCK, B2_END_MIN_BLOCKS) k_end_pass3(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 slot = s.slot_begin + thread_id();
     // classification of pass 1 (the same launch sequence; nothing changed in between)
