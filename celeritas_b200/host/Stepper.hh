@@ -73,7 +73,7 @@ class ActionSequence
         uint32_t fuse_threshold{0};
     };
     //! Default of Options::fuse_threshold (measured: profiles/README_r01.md)
-    static constexpr uint32_t default_fuse_threshold = 131072;
+    static constexpr uint32_t default_fuse_threshold = 65536;
     //! Build the B200 adapters for every step action in the problem's table
     explicit ActionSequence(CoreParams const& params) : ActionSequence(params, Options{}) {}
     ActionSequence(CoreParams const& params, Options options);
