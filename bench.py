@@ -44,11 +44,12 @@ NUM_TRACK_SLOTS = 1 << 20
 NUM_STREAMS = 2
 ALG_BYTES_PER_TRACK_STEP = 672  # 2 * S_live, D=1, P=4
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE along-step launch (charged + neutral
-# kernels) at a saturated iteration, ~8.0e5 live tracks, from `ncu --set full`
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 557.8e6 + 324.0e6 + 181.3e6 + 77.0e6
-NCU_TRAFFIC_SOURCE = ('profiles/saturated_kernels_r01d.txt: k_along_step_charged<0> + '
-                      'k_along_step_neutral at one saturated iteration (8.0e5 live tracks = '
-                      '5.4e8 algorithmic bytes at 672 B per track-step)')
+# kernels) at a saturated iteration (all 2^20 slots live), from `ncu --set full`
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 137.8e6 + 131.6e6 + 122.8e6 + 51.0e6
+NCU_TRAFFIC_SOURCE = ('profiles/saturated_kernels_r01e.txt: k_along_step_charged<0> + '
+                      'k_along_step_neutral at one saturated iteration (1.05e6 live tracks = '
+                      '7.0e8 algorithmic bytes at 672 B per track-step for the WHOLE step; the '
+                      'along-step touches about two thirds of the per-slot state)')
 
 
 def make_events(num_events, per_event, first_event, particle_id, dtype):

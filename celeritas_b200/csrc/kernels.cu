@@ -1121,20 +1121,40 @@ __global__ void __launch_bounds__(BLOCK, B2_END_MIN_BLOCKS) k_end_pass3(B2_GRID_
     SlotEnd e = unpack_class(slot < s.num_slots ? s.slot_class[slot] : u8(0));
     u32 ta, tb;
     u32 const nb = gridDim.x;
+    // Everything that does not depend on the scans is loaded BEFORE their barriers, so
+    // that these round trips overlap with the scans instead of queueing up behind them
+    // (the kernel is latency bound: 38 long-scoreboard stall cycles per issue, ncu)
+    u32 const block_vac = s.block_scratch[blockIdx.x];
+    u32 const block_chg = s.block_scratch[nb + blockIdx.x];
+    u32 const block_neu = s.block_scratch[2 * nb + blockIdx.x];
+    u32 const block_sec = s.block_scratch[3 * nb + blockIdx.x];
+    u32 const block_all = s.block_scratch[4 * nb + blockIdx.x];
+    u32 const block_neutral_sec = s.block_scratch[5 * nb + blockIdx.x];
+    u32 const device_error = s.counters[CTR_ERROR];
+    u32 const num_init = s.counters[CTR_NUM_INITIALIZERS];
+    u32 const num_sec_total = s.counters[CTR_NUM_SECONDARIES];
+    u32 event = 0, parent_track = 0;
+    real time = 0;
+    if (e.num_sec_all > 0)
+    {
+        event = s.event_id[slot];
+        parent_track = s.track_id[slot];
+        time = s.time[slot];
+    }
     u32 sa = block_exclusive_scan<BLOCK, u32>(
         e.is_vacant | (e.charged << 10) | (e.neutral << 20), &ta);
     u32 sb = block_exclusive_scan<BLOCK, u32>(pack_secondaries(e), &tb);
     // vacancies[i] = i for the (all vacant) slots below slot_begin
-    u32 vac_off = s.slot_begin + (sa & 0x3ffu) + s.block_scratch[blockIdx.x];
-    u32 chg_off = ((sa >> 10) & 0x3ffu) + s.block_scratch[nb + blockIdx.x];
-    u32 neu_off = ((sa >> 20) & 0x3ffu) + s.block_scratch[2 * nb + blockIdx.x];
-    u32 sec_off = (sb & 0x3ffu) + s.block_scratch[3 * nb + blockIdx.x];
-    u32 all_off = ((sb >> 10) & 0x3ffu) + s.block_scratch[4 * nb + blockIdx.x];
+    u32 vac_off = s.slot_begin + (sa & 0x3ffu) + block_vac;
+    u32 chg_off = ((sa >> 10) & 0x3ffu) + block_chg;
+    u32 neu_off = ((sa >> 20) & 0x3ffu) + block_neu;
+    u32 sec_off = (sb & 0x3ffu) + block_sec;
+    u32 all_off = ((sb >> 10) & 0x3ffu) + block_all;
     // neutral initializers created by lower slots in this step (init_charge only)
-    u32 neutral_off = ((sb >> 20) & 0x3ffu) + s.block_scratch[5 * nb + blockIdx.x];
+    u32 neutral_off = ((sb >> 20) & 0x3ffu) + block_neutral_sec;
     if (slot >= s.num_slots)
         return;
-    if (s.counters[CTR_ERROR] != 0)
+    if (device_error != 0)
         return;
     if (e.is_vacant)
         s.vacancies[vac_off] = slot;
@@ -1159,8 +1179,6 @@ __global__ void __launch_bounds__(BLOCK, B2_END_MIN_BLOCKS) k_end_pass3(B2_GRID_
 
     // Initializers created this step occupy [num_init - num_sec, num_init)
     // in slot order (exclusive scan of the per-slot counts)
-    u32 const num_init = s.counters[CTR_NUM_INITIALIZERS];
-    u32 const num_sec_total = s.counters[CTR_NUM_SECONDARIES];
     u32 out = num_init - num_sec_total + sec_off;
     u32 neutral_run = 0;
     if (s.ti_neutral_prefix && e.num_sec_all > 0)
@@ -1171,9 +1189,6 @@ __global__ void __launch_bounds__(BLOCK, B2_END_MIN_BLOCKS) k_end_pass3(B2_GRID_
 
     if (e.num_sec_all > 0)
     {
-        u32 const event = s.event_id[slot];
-        u32 const parent_track = s.track_id[slot];
-        real const time = s.time[slot];
         GeoTrack geo(p, s, slot);
         Real3 const pos = geo.pos();
         u32 const lev = geo.level();
