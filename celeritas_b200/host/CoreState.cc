@@ -268,6 +268,25 @@ void CoreState::get_field(std::string const& f, void* out)
             }
         }
     }
+    else if (f == "interact_count")
+    {
+        // [16] interacting tracks per model in the last per-action step
+        if (!s.interact_count)
+            throw std::runtime_error("this state has no interaction lists");
+        copy(s.interact_count, 4 * 16);
+    }
+    else if (f == "interact_list")
+    {
+        // [num_models][num_slots] slots of the interacting tracks, model-major
+        if (!s.interact_list)
+            throw std::runtime_error("this state has no interaction lists");
+        copy(s.interact_list, 4 * n * params_->view().phys.num_models);
+    }
+    else if (f == "track_slots")
+    {
+        // dense active lists: charged from the front, neutral from the back
+        copy(s.track_slots, 4 * n);
+    }
     else
     {
         throw std::runtime_error("unknown state field '" + f + "'");

@@ -128,6 +128,16 @@ uint32_t b200_params_num_particles(B200Params const* params)
     return params->params->particle_names().size();
 }
 
+uint32_t b200_params_num_models(B200Params const* params)
+{
+    return params->params->view().phys.num_models;
+}
+
+uint32_t b200_params_model_action_begin(B200Params const* params)
+{
+    return params->params->view().phys.model_to_action;
+}
+
 uint32_t b200_params_find_particle(B200Params const* params, int pdg)
 {
     return params->params->find_particle(pdg);

@@ -63,7 +63,7 @@ EXPORTS = [
     'b200_stepper_step_diagnostic_bins', 'b200_stepper_diagnostics_clear',
     'b200_primaries_generate', 'b200_celer_sim_run', 'b200_string_free',
     'b200_params_num_particles', 'b200_run_events_streams', 'b200_step_fused',
-    'b200_step_post_tail',
+    'b200_step_post_tail', 'b200_params_num_models', 'b200_params_model_action_begin',
 ]
 
 _lib = None
@@ -106,6 +106,10 @@ def load_library():
     L.b200_params_find_particle.restype = C.c_uint32
     L.b200_params_num_particles.argtypes = [vp]
     L.b200_params_num_particles.restype = C.c_uint32
+    L.b200_params_num_models.argtypes = [vp]
+    L.b200_params_num_models.restype = C.c_uint32
+    L.b200_params_model_action_begin.argtypes = [vp]
+    L.b200_params_model_action_begin.restype = C.c_uint32
     L.b200_state_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]
     L.b200_state_destroy.argtypes = [vp]
     L.b200_state_view.argtypes = [vp]
@@ -351,6 +355,27 @@ class Stepper:
         out = np.zeros((self.n, w) if w > 1 else self.n, dtype=dt)
         _check(L.b200_state_get(L.b200_stepper_state(self.h), field.encode(), out.ctypes.data))
         return out
+
+    def interaction_lists(self):
+        """Per-model slot lists of the last per-action step: {action id: sorted slots}."""
+        L = load_library()
+        nm = L.b200_params_num_models(self.params.h)
+        first = L.b200_params_model_action_begin(self.params.h)
+        counts = np.zeros(16, dtype=np.uint32)
+        lists = np.zeros((nm, self.n), dtype=np.uint32)
+        state = L.b200_stepper_state(self.h)
+        _check(L.b200_state_get(state, b'interact_count', counts.ctypes.data))
+        _check(L.b200_state_get(state, b'interact_list', lists.ctypes.data))
+        return {first + m: np.sort(lists[m, :counts[m]]) for m in range(nm)}
+
+    def dense_lists(self, counts):
+        """(charged slots, neutral slots) of the dense active lists, given the sizes."""
+        L = load_library()
+        slots = np.zeros(self.n, dtype=np.uint32)
+        _check(L.b200_state_get(L.b200_stepper_state(self.h), b'track_slots',
+                                slots.ctypes.data))
+        nc, nn = counts
+        return slots[:nc], slots[self.n - nn:][::-1]
 
     def calo(self):
         L = load_library()

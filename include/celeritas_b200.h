@@ -126,6 +126,9 @@ char const* b200_params_volume_label(B200Params const* params, uint32_t volume_i
 uint32_t b200_params_num_detectors(B200Params const* params);
 uint32_t b200_params_find_particle(B200Params const* params, int pdg); /* 0xffffffff if absent */
 uint32_t b200_params_num_particles(B200Params const* params);
+/* Discrete models are the actions [model_action_begin, model_action_begin + num_models) */
+uint32_t b200_params_num_models(B200Params const* params);
+uint32_t b200_params_model_action_begin(B200Params const* params);
 
 /*--- per-stream state -------------------------------------------------------*/
 int b200_state_create(B200Params const* params,

@@ -100,3 +100,39 @@ def test_lockstep_init_charge(energy, nprim, slots, fuse):
     assert not (hist[-1]['alive'] or hist[-1]['queued'])
     if slots == 512:
         assert max(h['queued'] for h in hist) > 0
+
+
+def test_action_sorted_lists_match_reference_actions():
+    """The per-model interaction lists (the action-sorted order the interaction kernel
+    runs in) hold exactly the slots whose post-step action in the REFERENCE state is that
+    model, every step; the dense charged/neutral lists of the next step hold exactly the
+    reference's active slots of each charge, in slot order."""
+    import celeritas_b200 as cb
+    _, ref, params, gpu = setup('testem3-small-initcharge', 2048, NEVER_FUSE)
+    prim = electrons(4, 1000.0, params)
+    cr, cg = ref.step(prim), gpu.step(prim)
+    charge_of = {params.find_particle(11): 1, params.find_particle(-11): 1,
+                 params.find_particle(22): 0}
+    checked = interactions = 0
+    for it in range(120):
+        assert cr == cg
+        lists = gpu.interaction_lists()
+        action = ref.get('post_step_action')
+        status = ref.get('status')
+        for act, slots in lists.items():
+            # in init_charge mode a slot keeps its post-step action until the next step
+            want = np.nonzero((action == act))[0]
+            assert np.array_equal(slots, want.astype(np.uint32)), (it, act)
+            interactions += len(slots)
+        if it % 10 == 0:
+            pid = ref.get('particle_id')
+            alive = np.nonzero(status == 2)[0]
+            charged = np.array([s for s in alive if charge_of[int(pid[s])]], dtype=np.uint32)
+            neutral = np.array([s for s in alive if not charge_of[int(pid[s])]], dtype=np.uint32)
+            gc, gn = gpu.dense_lists((len(charged), len(neutral)))
+            assert np.array_equal(gc, charged) and np.array_equal(gn, neutral), it
+            checked += 1
+        if not (cr['alive'] or cr['queued']):
+            break
+        cr, cg = ref.step(), gpu.step()
+    assert interactions > 500 and checked >= 5
