@@ -363,6 +363,15 @@ B2_D void do_pre_step(ParamsView const& p, StateView const& s, u32 slot)
     for (int i = 0; i < MAX_SECONDARIES; ++i)
         s.sec_particle[i * s.num_slots + slot] = INVALID;
     s.element[slot] = INVALID;
+    // pre-step volume for detector scoring (StepGatherExecutor<pre> runs for every
+    // non-inactive track, errored ones included: their energy is deposited by the
+    // tracking cut in the volume they are in; a track that started outside the geometry
+    // is in the exterior volume, which never is a detector)
+    if (s.pre_volume)
+    {
+        GeoTrack geo(p, s, slot);
+        s.pre_volume[slot] = geo.volume_id();
+    }
     if (status == ST_ERRORED)
         return;
     s.status[slot] = ST_ALIVE;
@@ -381,12 +390,6 @@ B2_D void do_pre_step(ParamsView const& p, StateView const& s, u32 slot)
     s.post_step_action[slot] = limit.action;
     s.along_step_action[slot] = (particle.charge == 0) ? p.scalars.along_step_neutral_action
                                                        : p.scalars.along_step_user_action;
-    // pre-step volume for detector scoring (StepGatherExecutor<pre>)
-    if (s.pre_volume)
-    {
-        GeoTrack geo(p, s, slot);
-        s.pre_volume[slot] = geo.volume_id();
-    }
 }
 
 __global__ void __launch_bounds__(BLOCK, B2_PRE_MIN_BLOCKS) k_pre_step(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)

@@ -362,6 +362,15 @@ void Stepper::insert(B200Primary const* primaries, uint32_t n)
         throw std::runtime_error("multiple consecutive primary insertions");
     if (n == 0)
         return;
+    // reference: CELER_VALIDATE in ExtendFromPrimariesAction::insert
+    // (track/ExtendFromPrimariesAction.cc:107-113)
+    if (uint64_t(n) + last_.num_initializers > params_->init_capacity())
+    {
+        throw std::runtime_error("insufficient initializer capacity ("
+                                 + std::to_string(params_->init_capacity()) + ") with size ("
+                                 + std::to_string(last_.num_initializers) + ") for primaries ("
+                                 + std::to_string(n) + ")");
+    }
     staging_->reserve(n);
     Staging& st = *staging_;
     std::copy(primaries, primaries + n, st.h_primaries);

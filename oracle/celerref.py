@@ -47,6 +47,7 @@ def lib():
         L.celerref_stepper_destroy.argtypes = [C.c_void_p]
         L.celerref_step.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         L.celerref_reseed.argtypes = [C.c_void_p, C.c_uint64]
+        L.celerref_kill_active.argtypes = [C.c_void_p]
         L.celerref_state_get.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
         L.celerref_calo_get.argtypes = [C.c_void_p, C.c_void_p]
         L.celerref_calo_clear.argtypes = [C.c_void_p]
@@ -178,6 +179,9 @@ class Stepper:
 
     def reseed(self, event_id):
         _check(lib().celerref_reseed(self.h, event_id))
+
+    def kill_active(self):
+        _check(lib().celerref_kill_active(self.h))
 
     def get(self, field):
         dt, w = FIELDS[field]

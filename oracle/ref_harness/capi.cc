@@ -189,6 +189,12 @@ int celerref_reseed(void* stepper, uint64_t event_id)
     });
 }
 
+//! Stepper::kill_active (global/Stepper.cc:177-182)
+int celerref_kill_active(void* stepper)
+{
+    return guarded([&] { static_cast<RefStepper*>(stepper)->step->kill_active(); });
+}
+
 //! Copy a per-slot state field into `out` (caller sizes it)
 int celerref_state_get(void* stepper, char const* field, void* out)
 {
