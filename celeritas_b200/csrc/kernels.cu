@@ -50,6 +50,11 @@ constexpr int BLOCK = 128;
 #    define B2_ALONG_SPLIT_THRESHOLD 0
 #endif
 constexpr int ALONG_MIN_BLOCKS = B2_ALONG_MIN_BLOCKS;
+// The charged along-step WITH the field propagator (Dormand-Prince driver) needs more
+// registers than the field-free one
+#ifndef B2_ALONG_FIELD_MIN_BLOCKS
+#    define B2_ALONG_FIELD_MIN_BLOCKS 8
+#endif
 // Resident blocks per SM asked of the other large-iteration kernels. Measured, ms per pass
 // (profiles/README_r01.md): pre-step 15.3 -> 12.9, neutral along-step -1.9, end passes
 // 20.8 -> 16.7 when capped at 64 registers (8 blocks of 128 threads)
@@ -406,7 +411,7 @@ __global__ void __launch_bounds__(BLOCK, B2_PRE_MIN_BLOCKS) k_pre_step(B2_GRID_C
 // along-step: one launch per charge class over its dense list
 //---------------------------------------------------------------------------//
 template<bool FIELD>
-__global__ void __launch_bounds__(BLOCK, ALONG_MIN_BLOCKS) k_along_step_charged(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
+__global__ void __launch_bounds__(BLOCK, FIELD ? B2_ALONG_FIELD_MIN_BLOCKS : ALONG_MIN_BLOCKS) k_along_step_charged(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 tid = thread_id();
     if (tid >= s.counters[CTR_NUM_CHARGED])
