@@ -408,19 +408,85 @@ __global__ void __launch_bounds__(BLOCK, B2_PRE_MIN_BLOCKS) k_pre_step(B2_GRID_C
 }
 
 //---------------------------------------------------------------------------//
+// pre-post: discrete select (phys/detail/DiscreteSelectExecutor.hh:37-63)
+//---------------------------------------------------------------------------//
+B2_D void do_discrete_select(ParamsView const& p, StateView const& s, u32 slot)
+{
+    if (s.status[slot] != ST_ALIVE)
+        return;
+    if (s.post_step_action[slot] != p.phys.model_to_action - 2)
+        return;
+    s.interaction_mfp[slot] = 0;
+    Particle particle = load_particle(p, s, slot);
+    PhysTrack phys(p, particle.id, s.material_id[slot]);
+    Rng rng;
+    rng.load(s, slot);
+    u32 action = select_discrete_interaction(p, s, slot, particle, phys, rng);
+    rng.store(s, slot);
+    s.post_step_action[slot] = action;
+}
+
+// Select (if the track's step ended at a discrete interaction) and append the interacting
+// track to its model's slot list. Called by EVERY thread of the block (slot == INVALID for
+// the ones without a track): the appends are aggregated per block in shared memory.
+constexpr u32 MAX_INTERACT_MODELS = 16;
+
+B2_D void select_and_append(ParamsView const& p, StateView const& s, u32 slot)
+{
+    __shared__ u32 count[MAX_INTERACT_MODELS];
+    __shared__ u32 base[MAX_INTERACT_MODELS];
+    bool const build_lists = s.interact_list != nullptr;
+    if (build_lists)
+    {
+        if (threadIdx.x < MAX_INTERACT_MODELS)
+            count[threadIdx.x] = 0;
+        __syncthreads();
+    }
+    u32 model = INVALID;
+    if (slot != INVALID)
+    {
+        do_discrete_select(p, s, slot);
+        if (build_lists && s.status[slot] == ST_ALIVE)
+        {
+            u32 m = s.post_step_action[slot] - p.phys.model_to_action;
+            if (m < p.phys.num_models)
+                model = m;
+        }
+    }
+    if (!build_lists)
+        return;
+    u32 rank = 0;
+    if (model != INVALID)
+        rank = atomicAdd(&count[model], 1u);
+    __syncthreads();
+    if (threadIdx.x < p.phys.num_models && count[threadIdx.x] > 0)
+        base[threadIdx.x] = atomicAdd(&s.interact_count[threadIdx.x], count[threadIdx.x]);
+    __syncthreads();
+    if (model != INVALID)
+        s.interact_list[size_t(model) * s.num_slots + base[model] + rank] = slot;
+}
+
+//---------------------------------------------------------------------------//
 // along-step: one launch per charge class over its dense list
 //---------------------------------------------------------------------------//
-template<bool FIELD>
+// SELECT: the discrete-process selection (order pre_post, the next action in the sequence)
+// is done by the same thread right after its along-step, and the selected interactions are
+// appended to the per-model lists: one launch and one pass over the active tracks less.
+template<bool FIELD, bool SELECT>
 __global__ void __launch_bounds__(BLOCK, FIELD ? B2_ALONG_FIELD_MIN_BLOCKS : ALONG_MIN_BLOCKS) k_along_step_charged(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 tid = thread_id();
-    if (tid >= s.counters[CTR_NUM_CHARGED])
-        return;
-    u32 slot = s.track_slots[tid];
-    prefetch_along_step_state<true>(s, slot);
-    if (s.status[slot] != ST_ALIVE)
-        return;
-    along_step<true, FIELD>(p, s, slot);
+    u32 slot = INVALID;
+    if (tid < s.counters[CTR_NUM_CHARGED])
+        slot = s.track_slots[tid];
+    if (slot != INVALID)
+    {
+        prefetch_along_step_state<true>(s, slot);
+        if (s.status[slot] == ST_ALIVE)
+            along_step<true, FIELD>(p, s, slot);
+    }
+    if (SELECT)
+        select_and_append(p, s, slot);
 }
 
 // The same charged along-step as four phase kernels (see along_step.cuh). Used for large
@@ -444,77 +510,30 @@ B2_ALONG_PHASE_KERNEL(k_along_msc_apply, along_phase_msc_apply, B2_PHASE_MIN_BLO
 B2_ALONG_PHASE_KERNEL(k_along_finish, along_phase_finish, B2_PHASE_MIN_BLOCKS)
 #undef B2_ALONG_PHASE_KERNEL
 
+template<bool SELECT>
 __global__ void __launch_bounds__(BLOCK, B2_NEUTRAL_MIN_BLOCKS) k_along_step_neutral(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 tid = thread_id();
-    if (tid >= s.counters[CTR_NUM_NEUTRAL])
-        return;
-    u32 slot = s.track_slots[s.num_slots - 1 - tid];
-    prefetch_along_step_state<false>(s, slot);
-    if (s.status[slot] != ST_ALIVE)
-        return;
-    along_step<false, false>(p, s, slot);
-}
-
-//---------------------------------------------------------------------------//
-// pre-post: discrete select (phys/detail/DiscreteSelectExecutor.hh:37-63)
-//---------------------------------------------------------------------------//
-B2_D void do_discrete_select(ParamsView const& p, StateView const& s, u32 slot)
-{
-    if (s.status[slot] != ST_ALIVE)
-        return;
-    if (s.post_step_action[slot] != p.phys.model_to_action - 2)
-        return;
-    s.interaction_mfp[slot] = 0;
-    Particle particle = load_particle(p, s, slot);
-    PhysTrack phys(p, particle.id, s.material_id[slot]);
-    Rng rng;
-    rng.load(s, slot);
-    u32 action = select_discrete_interaction(p, s, slot, particle, phys, rng);
-    rng.store(s, slot);
-    s.post_step_action[slot] = action;
+    u32 slot = INVALID;
+    if (tid < s.counters[CTR_NUM_NEUTRAL])
+        slot = s.track_slots[s.num_slots - 1 - tid];
+    if (slot != INVALID)
+    {
+        prefetch_along_step_state<false>(s, slot);
+        if (s.status[slot] == ST_ALIVE)
+            along_step<false, false>(p, s, slot);
+    }
+    if (SELECT)
+        select_and_append(p, s, slot);
 }
 
 // Besides selecting, the launch sorts the interacting tracks BY MODEL into per-model slot
 // lists (block-aggregated appends), so that the interaction kernel runs warps in which
 // every lane executes the same interactor. Launched over all active tracks, only ~4 of
 // 32 lanes were active per instruction (ncu: profiles/README_r01.md).
-constexpr u32 MAX_INTERACT_MODELS = 16;
-
 __global__ void __launch_bounds__(BLOCK) k_discrete_select(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
-    __shared__ u32 count[MAX_INTERACT_MODELS];
-    __shared__ u32 base[MAX_INTERACT_MODELS];
-    bool const build_lists = s.interact_list != nullptr;
-    if (build_lists)
-    {
-        if (threadIdx.x < MAX_INTERACT_MODELS)
-            count[threadIdx.x] = 0;
-        __syncthreads();
-    }
-    u32 slot = active_slot(s, thread_id());
-    u32 model = INVALID;
-    if (slot != INVALID)
-    {
-        do_discrete_select(p, s, slot);
-        if (build_lists && s.status[slot] == ST_ALIVE)
-        {
-            u32 m = s.post_step_action[slot] - p.phys.model_to_action;
-            if (m < p.phys.num_models)
-                model = m;
-        }
-    }
-    if (!build_lists)
-        return;
-    u32 rank = 0;
-    if (model != INVALID)
-        rank = atomicAdd(&count[model], 1u);
-    __syncthreads();
-    if (threadIdx.x < p.phys.num_models && count[threadIdx.x] > 0)
-        base[threadIdx.x] = atomicAdd(&s.interact_count[threadIdx.x], count[threadIdx.x]);
-    __syncthreads();
-    if (model != INVALID)
-        s.interact_list[size_t(model) * s.num_slots + base[model] + rank] = slot;
+    select_and_append(p, s, active_slot(s, thread_id()));
 }
 
 //---------------------------------------------------------------------------//
@@ -1433,14 +1452,37 @@ int b200_step_along_step(B200ParamsView const* params, B200StateView const* stat
     else if (nc > 0)
     {
         if (PV(params).model.field.enabled)
-            k_along_step_charged<true><<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
+            k_along_step_charged<true, false><<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
         else
-            k_along_step_charged<false><<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
+            k_along_step_charged<false, false><<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
         B2_COUNT(1);
     }
     if (nn > 0)
     {
-        k_along_step_neutral<<<grid_for(nn), BLOCK, 0, stream>>>(PV(params), s);
+        k_along_step_neutral<false><<<grid_for(nn), BLOCK, 0, stream>>>(PV(params), s);
+        B2_COUNT(1);
+    }
+    return check_launch();
+}
+
+int b200_step_along_select(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    if (!s.interact_list)
+        return B200_ERR_INVALID_ARGUMENT;
+    u32 nc = s.hint_charged < s.num_slots ? s.hint_charged : s.num_slots;
+    u32 nn = s.hint_neutral < s.num_slots ? s.hint_neutral : s.num_slots;
+    if (nc > 0)
+    {
+        if (PV(params).model.field.enabled)
+            k_along_step_charged<true, true><<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
+        else
+            k_along_step_charged<false, true><<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
+        B2_COUNT(1);
+    }
+    if (nn > 0)
+    {
+        k_along_step_neutral<true><<<grid_for(nn), BLOCK, 0, stream>>>(PV(params), s);
         B2_COUNT(1);
     }
     return check_launch();

@@ -106,6 +106,7 @@ class ActionSequence
     bool fusable_{false};
     uint32_t fuse_threshold_{0};
     size_t tail_begin_{0}, tail_end_{0};  // [begin, end) of the boundary..diagnostics run
+    size_t along_select_{0};  // index of the along-step action when the select follows it
     std::vector<double> accum_time_;
     struct Pending
     {

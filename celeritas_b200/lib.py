@@ -63,7 +63,7 @@ EXPORTS = [
     'b200_stepper_step_diagnostic_bins', 'b200_stepper_diagnostics_clear',
     'b200_primaries_generate', 'b200_celer_sim_run', 'b200_string_free',
     'b200_params_num_particles', 'b200_run_events_streams', 'b200_step_fused',
-    'b200_step_post_tail', 'b200_params_num_models', 'b200_params_model_action_begin',
+    'b200_step_post_tail', 'b200_step_along_select', 'b200_params_num_models', 'b200_params_model_action_begin',
 ]
 
 _lib = None

@@ -172,6 +172,10 @@ int b200_step_fused(B200ParamsView const*, B200StateView const*, cudaStream_t);
 /* boundary + tracking-cut + action diagnostic + tally + step diagnostic (consecutive in the
  * action sequence) in one launch; what the stepper uses for them in large iterations. */
 int b200_step_post_tail(B200ParamsView const*, B200StateView const*, cudaStream_t);
+/* along-step immediately followed, in the same threads, by the discrete-process selection
+ * (the next action in the sequence) and the per-model list build: replaces
+ * b200_step_along_step + b200_step_discrete_select in large iterations. */
+int b200_step_along_select(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_step_action_diagnostic(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_step_step_diagnostic(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_reseed(B200ParamsView const*, B200StateView const*, uint64_t event_id, cudaStream_t);
