@@ -1138,6 +1138,15 @@ __global__ void __launch_bounds__(1024) k_end_pass2(StateView s, u32 num_blocks)
             s.counters[CTR_TRACK_ID_BASE] = s.track_counters[s.single_event];
             s.track_counters[s.single_event] += carry[4];
         }
+        // Publish the step's counters to the host: nothing after this point changes them
+        if (s.host_counters)
+        {
+            u32 volatile* host = s.host_counters;
+            for (u32 k = 0; k < CTR_SIZE; ++k)
+                host[k] = reinterpret_cast<u32 volatile*>(s.counters)[k];
+            __threadfence_system();
+            host[CTR_SIZE] = s.iteration_seq;
+        }
     }
 }
 

@@ -545,6 +545,11 @@ struct StateView
     // neutral / charged tracks started in the same step without a partition pass
     u32* ti_neutral_prefix;  // [init_capacity + 1]
     u32 single_event;        // event id if exactly one event is in flight, else INVALID
+    // Host-mapped copy of the counters, written by the end-of-step scan as soon as they
+    // are final (before the last pass runs), followed by `iteration_seq`: the host picks
+    // up the step's result and prepares the next step while the last pass is still running
+    u32* host_counters;      // [CTR_SIZE + 1], pinned host memory mapped into the device
+    u32 iteration_seq;       // sequence number of this step iteration (host-set)
     // host-side upper bounds used only to size grids (kernels re-check device counters)
     u32 hint_active;
     u32 hint_charged;

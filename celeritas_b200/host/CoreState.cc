@@ -3,6 +3,7 @@
 //---------------------------------------------------------------------------//
 #include "CoreState.hh"
 
+#include <atomic>
 #include <cstring>
 #include <numeric>
 #include <random>
@@ -140,7 +141,15 @@ CoreState::CoreState(std::shared_ptr<CoreParams const> params,
         s.interact_list = arena_.alloc<u32>(size_t(p.phys.num_models) * n);
         s.interact_count = arena_.alloc<u32>(16);
     }
-    B2_CUDA_CALL(cudaMallocHost(reinterpret_cast<void**>(&h_counters_), CTR_SIZE * sizeof(uint32_t)));
+    B2_CUDA_CALL(cudaHostAlloc(reinterpret_cast<void**>(&h_counters_),
+                               (CTR_SIZE + 1) * sizeof(uint32_t),
+                               cudaHostAllocMapped));
+    std::memset(h_counters_, 0, (CTR_SIZE + 1) * sizeof(uint32_t));
+    {
+        void* mapped = nullptr;
+        B2_CUDA_CALL(cudaHostGetDevicePointer(&mapped, h_counters_, 0));
+        s.host_counters = static_cast<u32*>(mapped);
+    }
     B2_CUDA_CALL(cudaDeviceSynchronize());
 }
 
@@ -160,6 +169,40 @@ CoreStateCounters CoreState::sync_counters()
                                  cudaMemcpyDeviceToHost,
                                  stream_));
     B2_CUDA_CALL(cudaStreamSynchronize(stream_));
+    return this->unpack_counters();
+}
+
+CoreStateCounters CoreState::wait_counters()
+{
+    // The end-of-step scan writes the counters and then this iteration's sequence number
+    // into mapped host memory (k_end_pass2)
+    uint32_t volatile* flag = h_counters_ + CTR_SIZE;
+    uint32_t const want = iteration_seq_;
+    for (uint64_t spins = 0; *flag != want; ++spins)
+    {
+        if ((spins & 0x3ff) == 0x3ff)
+        {
+            // stream idle (or failed) without the flag: the kernels did not publish
+            cudaError_t q = cudaStreamQuery(stream_);
+            if (q == cudaSuccess)
+            {
+                if (*flag == want)
+                    break;
+                return this->sync_counters();
+            }
+            if (q != cudaErrorNotReady)
+                B2_CUDA_CALL(q);
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return this->unpack_counters();
+}
+
+CoreStateCounters CoreState::unpack_counters()
+{
     CoreStateCounters c;
     c.num_generated = h_counters_[CTR_NUM_GENERATED];
     c.num_initializers = h_counters_[CTR_NUM_INITIALIZERS];

@@ -54,6 +54,7 @@ class CoreState
         view_.hint_neutral = neutral;
         view_.hint_new = fresh;
         view_.slot_begin = slot_begin;
+        view_.iteration_seq = ++iteration_seq_;
     }
     uint32_t size() const { return view_.num_slots; }
     uint32_t stream_id() const { return stream_id_; }
@@ -62,6 +63,10 @@ class CoreState
 
     //! Copy device counters to the host (synchronises the stream)
     CoreStateCounters sync_counters();
+    //! Counters of the step iteration launched after the last launch_hints(), as soon as
+    //! the end-of-step scan has published them (the stream may still be running the last
+    //! pass); falls back to sync_counters() if the kernels did not publish
+    CoreStateCounters wait_counters();
     //! Nonzero if a kernel flagged an error (B200_ERR_*)
     uint32_t last_device_error() const { return last_error_; }
 
@@ -90,7 +95,9 @@ class CoreState
     cudaStream_t stream_{nullptr};
     DeviceArena arena_;
     b200::StateView view_{};
-    uint32_t* h_counters_{nullptr};  // pinned
+    uint32_t* h_counters_{nullptr};  // pinned, mapped: [CTR_SIZE + 1]
+    uint32_t iteration_seq_{0};
+    CoreStateCounters unpack_counters();
     uint32_t last_error_{0};
 };
 }  // namespace celeritas_b200

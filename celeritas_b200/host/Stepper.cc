@@ -496,7 +496,11 @@ void Stepper::step_async()
 StepperResult Stepper::operator()()
 {
     this->step_async();
-    CoreStateCounters c = state_->sync_counters();
+    // With per-action timing the event pairs must have completed: full synchronisation.
+    // Otherwise take the counters as soon as the end-of-step scan has published them.
+    CoreStateCounters c = (actions_->action_times() || std::getenv("B200_FULL_SYNC"))
+                              ? state_->sync_counters()
+                              : state_->wait_counters();
     last_ = c;
     actions_->collect_times();
     if (uint32_t err = state_->last_device_error())
