@@ -237,3 +237,29 @@ def test_ref_primary_generator_matches_restatement():
             assert float(g['energy']) == w['energy']
             assert g['pos'].tolist() == w['pos']
             assert g['dir'].tolist() == w['dir']
+
+
+@needs_ref
+def test_golden_fixtures_match_the_reference():
+    """tests/golden/*.json are what oracle/_ref produces today (regenerate with
+    tests/golden/make_golden.py): re-run the two smallest cases and compare everything."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(REPO, 'tests', 'golden'))
+    from make_golden import primaries_for, state_crcs
+    for name in ('simple-cms-em-field', 'testem3-small-initcharge'):
+        gold = json.load(open(os.path.join(REPO, 'tests', 'golden', name + '.json')))
+        case = gold['case']
+        cfg = json.load(open(data_path('images', case['image'] + '.json')))
+        problem = celerref.Problem(cfg)
+        stepper = problem.stepper(case['slots'])
+        ids = {int(k): v for k, v in gold['particle_ids'].items()}
+        prim = primaries_for(case, lambda pdg: ids[pdg], celerref.make_primaries)
+        c = stepper.step(prim)
+        for it, want in enumerate(gold['steps']):
+            assert c == {k: want[k] for k in c}, (name, it)
+            if 'crc' in want:
+                assert state_crcs(stepper) == want['crc'], (name, it)
+            if it + 1 < len(gold['steps']):
+                c = stepper.step()
+        assert np.allclose(problem.calo(len(gold['calo'])), gold['calo'], rtol=0, atol=0)
