@@ -50,6 +50,11 @@ constexpr int BLOCK = 128;
 #    define B2_ALONG_SPLIT_THRESHOLD 0
 #endif
 constexpr int ALONG_MIN_BLOCKS = B2_ALONG_MIN_BLOCKS;
+// Threads per block of the along-step kernels (the same register budget per SM: the
+// resident-block request scales with BLOCK / B2_ALONG_BLOCK)
+#ifndef B2_ALONG_BLOCK
+#    define B2_ALONG_BLOCK 128
+#endif
 // The charged along-step WITH the field propagator (Dormand-Prince driver) needs more
 // registers than the field-free one
 #ifndef B2_ALONG_FIELD_MIN_BLOCKS
@@ -473,7 +478,7 @@ B2_D void select_and_append(ParamsView const& p, StateView const& s, u32 slot)
 // is done by the same thread right after its along-step, and the selected interactions are
 // appended to the per-model lists: one launch and one pass over the active tracks less.
 template<bool FIELD, bool SELECT>
-__global__ void __launch_bounds__(BLOCK, FIELD ? B2_ALONG_FIELD_MIN_BLOCKS : ALONG_MIN_BLOCKS) k_along_step_charged(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
+__global__ void __launch_bounds__(B2_ALONG_BLOCK, (FIELD ? B2_ALONG_FIELD_MIN_BLOCKS : ALONG_MIN_BLOCKS) * BLOCK / B2_ALONG_BLOCK) k_along_step_charged(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 tid = thread_id();
     u32 slot = INVALID;
@@ -511,7 +516,7 @@ B2_ALONG_PHASE_KERNEL(k_along_finish, along_phase_finish, B2_PHASE_MIN_BLOCKS)
 #undef B2_ALONG_PHASE_KERNEL
 
 template<bool SELECT>
-__global__ void __launch_bounds__(BLOCK, B2_NEUTRAL_MIN_BLOCKS) k_along_step_neutral(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
+__global__ void __launch_bounds__(B2_ALONG_BLOCK, B2_NEUTRAL_MIN_BLOCKS * BLOCK / B2_ALONG_BLOCK) k_along_step_neutral(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 tid = thread_id();
     u32 slot = INVALID;
@@ -1461,14 +1466,14 @@ int b200_step_along_step(B200ParamsView const* params, B200StateView const* stat
     else if (nc > 0)
     {
         if (PV(params).model.field.enabled)
-            k_along_step_charged<true, false><<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
+            k_along_step_charged<true, false><<<(nc + B2_ALONG_BLOCK - 1) / B2_ALONG_BLOCK, B2_ALONG_BLOCK, 0, stream>>>(PV(params), s);
         else
-            k_along_step_charged<false, false><<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
+            k_along_step_charged<false, false><<<(nc + B2_ALONG_BLOCK - 1) / B2_ALONG_BLOCK, B2_ALONG_BLOCK, 0, stream>>>(PV(params), s);
         B2_COUNT(1);
     }
     if (nn > 0)
     {
-        k_along_step_neutral<false><<<grid_for(nn), BLOCK, 0, stream>>>(PV(params), s);
+        k_along_step_neutral<false><<<(nn + B2_ALONG_BLOCK - 1) / B2_ALONG_BLOCK, B2_ALONG_BLOCK, 0, stream>>>(PV(params), s);
         B2_COUNT(1);
     }
     return check_launch();
