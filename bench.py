@@ -52,6 +52,37 @@ NCU_TRAFFIC_SOURCE = ('profiles/saturated_kernels_r01e.txt: k_along_step_charged
                       'along-step touches about two thirds of the per-slot state)')
 
 
+# --workload: the headline (BASELINE configs[1]) and the CMS-scale stand-in (configs[3]/[4]:
+# tools/make_cms_scale.py, four universe levels, 3.8 T field, isotropic 10 GeV e-/gamma)
+WORKLOADS = {
+    'testem3': dict(image=IMAGE, config=CONFIG, alg_bytes=ALG_BYTES_PER_TRACK_STEP,
+                    events=NUM_EVENTS, per_event=PRIMARIES_PER_EVENT,
+                    label='TestEm3 full EM (Urban MSC + eloss fluctuations), %d x %d 1 GeV e- '
+                          'primaries per GPU'),
+    'cms-scale': dict(image=os.path.join(REPO, 'data', 'images', 'cms-scale.b2img'),
+                      config=os.path.join(REPO, 'data', 'images', 'cms-scale.json'),
+                      alg_bytes=2 * (248 + 56 * 4 + 8 * 4),  # SURVEY.md 8(d) with D=4, P=4
+                      events=100, per_event=10,
+                      label='CMS-scale stand-in geometry (tools/make_cms_scale.py: 4 levels, 2916 '
+                            'unit volumes, 2 rect arrays, BIH), 3.8 T uniform field, full EM, '
+                            '%d x %d isotropic 10 GeV e-/gamma primaries from the origin per GPU'),
+}
+
+
+def make_workload_events(workload, params_or_problem, num_events, per_event, first_event, dtype):
+    """Primaries of one rank: events [first_event, first_event + num_events)."""
+    if workload == 'testem3':
+        return make_events(num_events, per_event, first_event, 1, dtype)
+    opts = {'seed': 20220904, 'pdg': [11, 22], 'num_events': first_event + num_events,
+            'primaries_per_event': per_event, 'energy': 10000.0, 'position': [0, 0, 0],
+            'direction': {'distribution': 'isotropic'}}
+    out = params_or_problem.generate_primaries(opts)
+    prim = out[0] if isinstance(out, tuple) else out
+    prim = np.ascontiguousarray(prim[first_event * per_event:]).astype(dtype)
+    offsets = np.arange(0, len(prim) + 1, per_event, dtype=np.uint32)
+    return prim, offsets
+
+
 def make_events(num_events, per_event, first_event, particle_id, dtype):
     n = num_events * per_event
     p = np.zeros(n, dtype=dtype)
@@ -156,16 +187,18 @@ def measured_peak_gbs():
     return 6650.0, 'fallback'
 
 
-def cpu_reference_run(num_events, per_event, slots_per_stream, threads):
+def cpu_reference_run(num_events, per_event, slots_per_stream, threads, workload='testem3'):
     """Time the reference's own host Stepper (one Stepper per OpenMP thread)."""
     sys.path.insert(0, os.path.join(REPO, 'oracle'))
     import celerref
-    cfg = json.load(open(CONFIG))
+    cfg = json.load(open(WORKLOADS[workload]['config']))
     cfg['max_streams'] = max(threads, 1)
     cfg['initializer_capacity'] = 1 << 22
+    cfg['track_order'] = 'none'  # the reference's CPU default
     problem = celerref.Problem(cfg)
     # particle id of e- is fixed by the physics file order (e+, e-, gamma)
-    prim, offsets = make_events(num_events, per_event, 0, 1, celerref.PRIMARY_DTYPE)
+    prim, offsets = make_workload_events(workload, problem, num_events, per_event, 0,
+                                         celerref.PRIMARY_DTYPE)
     r = problem.run_events(prim, offsets, slots_per_stream, threads)
     return r
 
@@ -176,26 +209,28 @@ def run_reference_arm(args, rank, world):
     cores = os.cpu_count() or 1
     threads = cores
     per_event, num_events = 4, max(2 * threads, 8)
+    if args.workload == 'cms-scale':
+        per_event, num_events = 1, max(threads, 4)  # 10 GeV showers: ~10x the steps each
     # warm-up passes are smaller; each timed step is the same bounded sample
     for _ in range(args.warmup):
-        cpu_reference_run(max(threads, 4), 1, 4096, threads)
+        cpu_reference_run(max(threads, 4), 1, 4096, threads, args.workload)
     steps, secs = 0, 0.0
     iters = 0
     for _ in range(args.steps):
-        r = cpu_reference_run(num_events, per_event, 4096, threads)
+        r = cpu_reference_run(num_events, per_event, 4096, threads, args.workload)
         steps += r['num_steps']
         secs += r['seconds']
         iters += r['num_step_iterations']
     value = steps / secs
-    sample = ('%d events x %d primaries of 1 GeV e- per step on %d OpenMP threads, one Stepper '
+    sample = ('%d events x %d primaries per step on %d OpenMP threads, one Stepper '
               'per thread, 4096 track slots each' % (num_events, per_event, threads))
     line = {'impl': 'reference', 'metric': 'track-steps/sec', 'value': value,
             'unit': 'track-steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * secs / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
-            'config': {'workload': 'TestEm3 full EM (Urban MSC + eloss fluctuations), 1 GeV e-, '
-                                   'steel/lAr stand-in physics', 'sample': sample},
+            'config': {'workload': (WORKLOADS[args.workload]['label'] % (num_events, per_event))
+                                   + '; steel/lAr stand-in physics', 'sample': sample},
             'cpu_baseline': {'value': value, 'unit': 'track-steps/s', 'cores': threads,
                              'kind': 'reference', 'sample': sample},
             'e2e': {'value': value, 'unit': 'track-steps/s', 'h2d_bytes_per_step': 0,
@@ -210,8 +245,9 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--events', type=int, default=NUM_EVENTS)
-    ap.add_argument('--primaries-per-event', type=int, default=PRIMARIES_PER_EVENT)
+    ap.add_argument('--workload', default='testem3', choices=sorted(WORKLOADS))
+    ap.add_argument('--events', type=int, default=None)
+    ap.add_argument('--primaries-per-event', type=int, default=None)
     ap.add_argument('--slots', type=int, default=NUM_TRACK_SLOTS)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--streams', type=int, default=NUM_STREAMS,
@@ -219,6 +255,11 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    wl = WORKLOADS[args.workload]
+    if args.events is None:
+        args.events = wl['events']
+    if args.primaries_per_event is None:
+        args.primaries_per_event = wl['per_event']
 
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -237,18 +278,19 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
-    params = cb.Params(os.environ.get('B200_BENCH_IMAGE', IMAGE))
+    params = cb.Params(os.environ.get('B200_BENCH_IMAGE', wl['image']))
     nstreams = max(args.streams, 1)
     steppers = [cb.Stepper(params, args.slots // nstreams, stream_id=rank * nstreams + k)
                 for k in range(nstreams)]
     # per-action timing (roofline leg) is taken on one stream holding the whole workload
     stepper = steppers[0] if nstreams == 1 else cb.Stepper(params, args.slots,
                                                            stream_id=rank * nstreams)
-    electron = params.find_particle(11)
+    assert params.find_particle(11) == 1
     ndet = params.num_detectors
     # Events are sharded by rank: rank r owns global events [r*E, (r+1)*E)
-    prim, offsets = make_events(args.events, args.primaries_per_event, rank * args.events,
-                                electron, cb.PRIMARY_DTYPE)
+    prim, offsets = make_workload_events(args.workload, params, args.events,
+                                         args.primaries_per_event, rank * args.events,
+                                         cb.PRIMARY_DTYPE)
     nprim = len(prim)
 
     def barrier():
@@ -319,7 +361,7 @@ def main():
     top_secs = per_action[top]
     total_action_secs = sum(per_action.values())
     peak, peak_kind = measured_peak_gbs()
-    achieved = r2['num_steps'] * ALG_BYTES_PER_TRACK_STEP / top_secs / 1e9
+    achieved = r2['num_steps'] * wl['alg_bytes'] / top_secs / 1e9
 
     if rank != 0:
         if dist is not None:
@@ -332,11 +374,10 @@ def main():
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * dsecs / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'TestEm3 full EM (Urban MSC + eloss fluctuations), %d x %d 1 GeV e- '
-                               'primaries per GPU, merged events, %d track slots over %d '
-                               'concurrent stream(s), track_order init_charge; steel/lAr '
-                               'stand-in physics (tools/make_physics.py)'
-                               % (args.events, args.primaries_per_event, args.slots, nstreams),
+        'config': {'workload': (wl['label'] % (args.events, args.primaries_per_event))
+                               + (', merged events, %d track slots over %d concurrent stream(s), '
+                                  'track_order init_charge; steel/lAr stand-in physics '
+                                  '(tools/make_physics.py)' % (args.slots, nstreams)),
                    'l2': 'working set %.0f MB of SoA state per pass exceeds the 126 MB L2'
                          % (args.slots * 336 / 1e6),
                    'parallelism': 'events sharded by rank, NCCL all-reduce of tallies'},
@@ -353,16 +394,21 @@ def main():
                      'traffic_source': NCU_TRAFFIC_SOURCE,
                      'peak_kind': peak_kind,
                      'kernel_share_of_step': top_secs / total_action_secs,
+                     # the same algorithmic bytes over the WHOLE step (all kernels)
+                     'whole_step': {'achieved': value * wl['alg_bytes'] / 1e9,
+                                    'frac': value * wl['alg_bytes'] / 1e9 / peak},
                      'per_action_seconds': per_action},
     }
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         ne, pe = max(2 * cores, 8), 4
-        rc = cpu_reference_run(ne, pe, 4096, cores)
+        if args.workload == 'cms-scale':
+            ne, pe = max(cores, 4), 1
+        rc = cpu_reference_run(ne, pe, 4096, cores, args.workload)
         line['cpu_baseline'] = {
             'value': rc['num_steps'] / rc['seconds'], 'unit': 'track-steps/s', 'cores': cores,
             'kind': 'reference',
-            'sample': '%d events x %d primaries of 1 GeV e-, reference host Stepper '
+            'sample': '%d events x %d primaries of the same workload, reference host Stepper '
                       '(oracle/_ref), one per OpenMP thread, 4096 slots each' % (ne, pe)}
     print(json.dumps(line))
     if dist is not None:

@@ -34,6 +34,10 @@ CASES = {
                                      nprim=3, energy=500.0),
     'simple-cms-em-field': dict(image='simple-cms-em-field', slots=4096, particle=11, nprim=2,
                                 energy=300.0, pos=(0, 0, 0), direction=(0.6, 0.0, 0.8)),
+    # four-level CMS-scale stand-in (tools/make_cms_scale.py), 3.8 T: through the tracker
+    # shells into the ECAL rect array
+    'cms-scale-small': dict(image='cms-scale-small', slots=4096, particle=11, nprim=2,
+                            energy=500.0, pos=(0, 0, 0), direction=(0.6, 0.48, 0.64)),
 }
 
 
@@ -72,6 +76,8 @@ def run(stepper, prim, record):
 def main():
     import celerref
     for name, case in CASES.items():
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         cfg = json.load(open(os.path.join(REPO, 'data', 'images', case['image'] + '.json')))
         problem = celerref.Problem(cfg)
         stepper = problem.stepper(case['slots'])
