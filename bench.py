@@ -53,7 +53,7 @@ NCU_TRAFFIC_SOURCE = ('profiles/saturated_kernels_r01e.txt: k_along_step_charged
 
 
 # --workload: the headline (BASELINE configs[1]) and the CMS-scale stand-in (configs[3]/[4]:
-# tools/make_cms_scale.py, four universe levels, 3.8 T field, isotropic 10 GeV e-/gamma)
+# tools/make_cms_scale.py, four universe levels, 1 T field, isotropic 10 GeV e-/gamma)
 WORKLOADS = {
     'testem3': dict(image=IMAGE, config=CONFIG, alg_bytes=ALG_BYTES_PER_TRACK_STEP,
                     events=NUM_EVENTS, per_event=PRIMARIES_PER_EVENT,
@@ -64,7 +64,7 @@ WORKLOADS = {
                       alg_bytes=2 * (248 + 56 * 4 + 8 * 4),  # SURVEY.md 8(d) with D=4, P=4
                       events=100, per_event=10,
                       label='CMS-scale stand-in geometry (tools/make_cms_scale.py: 4 levels, 2916 '
-                            'unit volumes, 2 rect arrays, BIH), 3.8 T uniform field, full EM, '
+                            'unit volumes, 2 rect arrays, BIH), 1 T uniform field, full EM, '
                             '%d x %d isotropic 10 GeV e-/gamma primaries from the origin per GPU'),
 }
 

@@ -4,9 +4,12 @@ sys.path.insert(0, '.')
 import numpy as np
 import celeritas_b200 as cb
 import bench
-params = cb.Params(bench.IMAGE)
+workload = sys.argv[1] if len(sys.argv) > 1 else 'testem3'
+wl = bench.WORKLOADS[workload]
+params = cb.Params(wl['image'])
 st = cb.Stepper(params, 1 << 20)
-prim, offsets = bench.make_events(100, 100, 0, params.find_particle(11), cb.PRIMARY_DTYPE)
+prim, offsets = bench.make_workload_events(workload, params, wl['events'], wl['per_event'], 0,
+                                           cb.PRIMARY_DTYPE)
 for rep in range(3):
     st.reseed(0)
     rows = []
@@ -19,7 +22,7 @@ for rep in range(3):
         t1 = time.perf_counter(); rows.append((c['active'], c['alive'], c['queued'], t1 - t0))
 a = np.array(rows)
 print('iterations', len(a), 'total ms %.1f' % (a[:, 3].sum() * 1e3), 'track-steps %.3g' % a[:, 0].sum())
-edges = [0, 1024, 4096, 16384, 65536, 131072, 262144, 524288, 1 << 21]
+edges = [0, 16, 128, 1024, 4096, 16384, 65536, 131072, 262144, 524288, 1 << 21]
 for lo, hi in zip(edges[:-1], edges[1:]):
     m = (a[:, 0] >= lo) & (a[:, 0] < hi)
     if m.any():

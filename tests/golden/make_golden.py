@@ -34,7 +34,7 @@ CASES = {
                                      nprim=3, energy=500.0),
     'simple-cms-em-field': dict(image='simple-cms-em-field', slots=4096, particle=11, nprim=2,
                                 energy=300.0, pos=(0, 0, 0), direction=(0.6, 0.0, 0.8)),
-    # four-level CMS-scale stand-in (tools/make_cms_scale.py), 3.8 T: through the tracker
+    # four-level CMS-scale stand-in (tools/make_cms_scale.py), 1 T: through the tracker
     # shells into the ECAL rect array
     'cms-scale-small': dict(image='cms-scale-small', slots=4096, particle=11, nprim=2,
                             energy=500.0, pos=(0, 0, 0), direction=(0.6, 0.48, 0.64)),

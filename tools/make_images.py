@@ -72,14 +72,14 @@ PROBLEMS = {
 }
 
 # BASELINE configs 3/4: CMS-scale stand-in (tools/make_cms_scale.py): four levels, 2916 unit
-# volumes, two rect arrays, BIH trees over 276 / 2304 volumes, 3.8 T uniform field
+# volumes, two rect arrays, BIH trees over 276 / 2304 volumes, 1 T uniform field
 CMS_CALO = (['solenoid'] + ['ecal%s_%s_%d' % (a, k, i) for a in 'xy' for k in ('abs', 'gap')
                             for i in range(5)]
             + ['endcap_%s_%d' % (k, i) for k in ('abs', 'gap') for i in range(20)])
 PROBLEMS['cms-scale'] = {'geometry_file': 'data/geometry/cms-scale.org.json',
                          'physics_file': 'data/physics/cms-scale-steel-lar.json',
                          'seed': 20220904, 'initializer_capacity': 1 << 25, 'max_events': 16384,
-                         'field': [0, 0, 3.8], 'track_order': 'init_charge',
+                         'field': [0, 0, 1], 'track_order': 'init_charge',
                          'simple_calo': CMS_CALO}
 PROBLEMS['cms-scale-small'] = dict(PROBLEMS['cms-scale'], initializer_capacity=1 << 18,
                                    max_events=64, track_order='none')
