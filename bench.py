@@ -239,12 +239,52 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def run_reference_cuda_arm(args, rank, world):
+    """The reference's OWN CUDA build (oracle/_ref/libcelerref_cuda.so: its .cu files compiled
+    for sm_100 by oracle/Makefile) on this GPU, same workload, same primaries, same number of
+    track slots, events merged onto one state (celer-sim's GPU configuration: one stream,
+    track_order init_charge). Not the driver's reference arm (that is the CPU one): this is the
+    number BASELINE.json's target is stated against."""
+    if rank != 0:
+        return
+    os.environ['CELERREF_CUDA'] = '1'
+    sys.path.insert(0, os.path.join(REPO, 'oracle'))
+    import celerref
+    wl = WORKLOADS[args.workload]
+    events = args.events or wl['events']
+    per_event = args.primaries_per_event or wl['per_event']
+    cfg = json.load(open(wl['config']))
+    cfg['track_order'] = 'init_charge'
+    problem = celerref.Problem(cfg)
+    prim, _ = make_workload_events(args.workload, problem, events, per_event, 0,
+                                   celerref.PRIMARY_DTYPE)
+    for _ in range(args.warmup):
+        celerref.run_merged_device(problem, prim, args.slots)
+    steps, secs, iters = 0, 0.0, 0
+    for _ in range(args.steps):
+        r = celerref.run_merged_device(problem, prim, args.slots)
+        steps += r['num_steps']
+        secs += r['seconds']
+        iters += r['num_step_iterations']
+    line = {'impl': 'reference-cuda', 'metric': 'track-steps/sec', 'value': steps / secs,
+            'unit': 'track-steps/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * secs / args.steps, 'higher_is_better': True, 'dtype': 'f64',
+            'data': 'synthetic', 'num_step_iterations': iters,
+            'events_per_sec': events * args.steps / secs,
+            'config': {'workload': (wl['label'] % (events, per_event))
+                                   + ', merged events, %d track slots on one stream, track_order '
+                                     'init_charge; steel/lAr stand-in physics' % args.slots,
+                       'build': "the reference's own .cu sources, nvcc -O3 -gencode "
+                                'arch=compute_100,code=sm_100 (oracle/Makefile ref_cuda)'}}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'reference-cuda'])
     ap.add_argument('--workload', default='testem3', choices=sorted(WORKLOADS))
     ap.add_argument('--events', type=int, default=None)
     ap.add_argument('--primaries-per-event', type=int, default=None)
@@ -267,6 +307,9 @@ def main():
 
     if args.impl == 'reference':
         run_reference_arm(args, rank, world)
+        return
+    if args.impl == 'reference-cuda':
+        run_reference_cuda_arm(args, rank, world)
         return
 
     import torch

@@ -34,7 +34,11 @@ def available():
 def lib():
     global _lib
     if _lib is None:
-        L = C.CDLL(LIB_PATH, mode=C.RTLD_LOCAL)
+        # CELERREF_CUDA=1 selects the reference's own CUDA build (make -C oracle ref_cuda)
+        path = LIB_PATH
+        if os.environ.get('CELERREF_CUDA') == '1':
+            path = LIB_PATH.replace('libcelerref.so', 'libcelerref_cuda.so')
+        L = C.CDLL(path, mode=C.RTLD_LOCAL)
         L.celerref_last_error.restype = C.c_char_p
         L.celerref_problem_create.restype = C.c_void_p
         L.celerref_problem_create.argtypes = [C.c_char_p]
@@ -63,6 +67,9 @@ def lib():
         L.celerref_run_events.restype = C.c_double
         L.celerref_run_events.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                           C.c_uint32, C.c_int, C.c_void_p]
+        L.celerref_run_merged_device.restype = C.c_double
+        L.celerref_run_merged_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                                 C.c_void_p]
         _lib = L
     return _lib
 
@@ -156,6 +163,18 @@ class Problem:
             raise RuntimeError(lib().celerref_last_error().decode())
         return dict(seconds=t, num_steps=int(res[0]), num_step_iterations=int(res[1]),
                     num_primaries=int(res[2]), max_queued=int(res[3]))
+
+
+def run_merged_device(problem, primaries, num_track_slots):
+    """All primaries merged onto one device state, the reference's own CUDA kernels."""
+    primaries = np.ascontiguousarray(primaries, dtype=PRIMARY_DTYPE)
+    res = np.zeros(4, dtype=np.uint64)
+    t = lib().celerref_run_merged_device(problem.h, primaries.ctypes.data, len(primaries),
+                                         num_track_slots, res.ctypes.data)
+    if t < 0:
+        raise RuntimeError(lib().celerref_last_error().decode())
+    return dict(seconds=t, num_steps=int(res[0]), num_step_iterations=int(res[1]),
+                num_primaries=int(res[2]), max_queued=int(res[3]))
 
 
 class Stepper:

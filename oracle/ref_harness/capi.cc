@@ -15,6 +15,11 @@
 #include <nlohmann/json.hpp>
 
 #include "corecel/io/Logger.hh"
+#include "corecel/sys/Device.hh"
+#include "corecel/Config.hh"
+#if CELERITAS_USE_CUDA
+#    include <cuda_runtime_api.h>
+#endif
 #include "corecel/sys/ActionRegistry.hh"
 #include "corecel/sys/Environment.hh"
 #include "celeritas/geo/GeoTrackView.hh"
@@ -101,6 +106,14 @@ void* celerref_problem_create(char const* config_json)
             celeritas::world_logger().level(LogLevel::warning);
             celeritas::self_logger().level(LogLevel::warning);
         }
+#if CELERITAS_USE_CUDA
+        // The reference's CUDA build: params are mirrored to the device at construction,
+        // so the device must be active first (app/celer-sim/celer-sim.cc:185-195)
+        if (!celeritas::device())
+        {
+            celeritas::activate_device();
+        }
+#endif
         auto p = celerref::build_problem(json::parse(config_json));
         result = p.release();
     });
@@ -464,6 +477,54 @@ double celerref_run_events(void* problem,
         result[2] = num_prim;
         result[3] = max_queued;
     });
+    return elapsed;
+}
+
+//! Transport all primaries merged onto ONE device state (celer-sim `merge_events`,
+//! app/celer-sim/Transporter.cc:75-135) with the reference's own CUDA kernels; returns the
+//! wall time of the transport loop after warm_up (the reference's `time.total` definition).
+double celerref_run_merged_device(void* problem,
+                                  CPrimary const* primaries,
+                                  uint32_t num_primaries,
+                                  uint32_t num_track_slots,
+                                  uint64_t* result)
+{
+    double elapsed = -1;
+#if CELERITAS_USE_CUDA
+    guarded([&] {
+        auto* p = static_cast<celerref::Problem*>(problem);
+        StepperInput inp;
+        inp.params = p->core;
+        inp.stream_id = StreamId{0};
+        inp.num_track_slots = num_track_slots;
+        Stepper<MemSpace::device> step(inp);
+        step.warm_up();
+        auto prim = to_primaries(primaries, num_primaries);
+        uint64_t num_steps = 0, num_iters = 0, max_queued = 0;
+        cudaDeviceSynchronize();
+        auto t0 = std::chrono::steady_clock::now();
+        auto counts = step(make_span(prim));
+        while (true)
+        {
+            num_steps += counts.active;
+            ++num_iters;
+            max_queued = std::max<uint64_t>(max_queued, counts.queued);
+            if (!counts)
+                break;
+            counts = step();
+        }
+        cudaDeviceSynchronize();
+        auto t1 = std::chrono::steady_clock::now();
+        elapsed = std::chrono::duration<double>(t1 - t0).count();
+        result[0] = num_steps;
+        result[1] = num_iters;
+        result[2] = num_primaries;
+        result[3] = max_queued;
+    });
+#else
+    (void)problem; (void)primaries; (void)num_primaries; (void)num_track_slots; (void)result;
+    g_last_error = "celerref_run_merged_device: not a CUDA build (make -C oracle ref_cuda)";
+#endif
     return elapsed;
 }
 }  // extern "C"
