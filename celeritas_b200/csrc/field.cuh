@@ -38,6 +38,134 @@ struct FieldStepperResult
     OdeState err_state;
 };
 
+// The Dormand-Prince trial step has five call sites in the driver (short step, chord search,
+// one_good_step, integrate_step) and is ~1500 SASS instructions with --fmad=false: inlined
+// everywhere, the charged along-step kernel with field is 14 k instructions (224 KB), more
+// than the SM's instruction caches hold, and ncu shows 44 "no instruction" stall cycles per
+// issued instruction at a saturated CMS-scale iteration (profiles/README_r01.md). Out of
+// line it is one copy.  B2_FIELD_OUTLINE: 0 = inline, 1 = trial step out of line,
+// 2 = + right-hand side out of line.
+// MEASURED (CMS-scale stand-in, gpurun_out/variants_cms.log): out of line is SLOWER, 3.84 ->
+// 4.25 (level 1) / 4.62 (level 2) ns per track-step at saturation and 479 -> 557 / 724 us per
+// tail iteration: the call passes 18 doubles of result through local memory and the trial
+// step is only ~4 % of the kernel's code (division and square root slow paths are already
+// shared subroutines). Kept as a knob, default inline; what helps is running the
+// propagation as its own kernel (B2_ALONG_SPLIT_FIELD_THRESHOLD, kernels.cu).
+#ifndef B2_FIELD_OUTLINE
+#    define B2_FIELD_OUTLINE 0
+#endif
+#if B2_FIELD_OUTLINE >= 1
+#    define B2_FIELD_STEP_FN B2_NOINLINE inline
+#else
+#    define B2_FIELD_STEP_FN B2_D
+#endif
+#if B2_FIELD_OUTLINE >= 2
+#    define B2_FIELD_RHS_FN B2_NOINLINE inline
+#else
+#    define B2_FIELD_RHS_FN B2_D
+#endif
+
+//! Right-hand side of the equation of motion
+B2_FIELD_RHS_FN OdeState field_rhs(real coeffi, Real3 const& field, OdeState const& y)
+{
+    real momentum_inv = 1 / sqrt(dot(y.mom, y.mom));
+    OdeState r;
+    r.pos = make_real3(momentum_inv * y.mom[0], momentum_inv * y.mom[1], momentum_inv * y.mom[2]);
+    real c = coeffi * momentum_inv;
+    Real3 x = cross_product(y.mom, field);
+    r.mom = make_real3(c * x[0], c * x[1], c * x[2]);
+    return r;
+}
+
+//! One Dormand-Prince trial step
+B2_FIELD_STEP_FN void field_apply_step(real coeffi, Real3 const& field, real step, OdeState const& beg, FieldStepperResult& result)
+{
+    using R = real;
+    constexpr R a11 = 0.2;
+    constexpr R a21 = 0.075;
+    constexpr R a22 = 0.225;
+    constexpr R a31 = 44 / R(45);
+    constexpr R a32 = -56 / R(15);
+    constexpr R a33 = 32 / R(9);
+    constexpr R a41 = 19372 / R(6561);
+    constexpr R a42 = -25360 / R(2187);
+    constexpr R a43 = 64448 / R(6561);
+    constexpr R a44 = -212 / R(729);
+    constexpr R a51 = 9017 / R(3168);
+    constexpr R a52 = -355 / R(33);
+    constexpr R a53 = 46732 / R(5247);
+    constexpr R a54 = 49 / R(176);
+    constexpr R a55 = -5103 / R(18656);
+    constexpr R a61 = 35 / R(384);
+    constexpr R a63 = 500 / R(1113);
+    constexpr R a64 = 125 / R(192);
+    constexpr R a65 = -2187 / R(6784);
+    constexpr R a66 = 11 / R(84);
+    constexpr R d71 = a61 - 5179 / R(57600);
+    constexpr R d73 = a63 - 7571 / R(16695);
+    constexpr R d74 = a64 - 393 / R(640);
+    constexpr R d75 = a65 + 92097 / R(339200);
+    constexpr R d76 = a66 - 187 / R(2100);
+    constexpr R d77 = -1 / R(40);
+    constexpr R c71 = R(6025192743.) / R(30085553152.);
+    constexpr R c73 = R(51252292925.) / R(65400821598.);
+    constexpr R c74 = R(-2691868925.) / R(45128329728.);
+    constexpr R c75 = R(187940372067.) / R(1594534317056.);
+    constexpr R c76 = R(-1776094331.) / R(19743644256.);
+    constexpr R c77 = R(11237099.) / R(235043384.);
+
+    OdeState k1 = field_rhs(coeffi, field, beg);
+    OdeState state = beg;
+    ode_axpy(a11 * step, k1, state);
+    OdeState k2 = field_rhs(coeffi, field, state);
+    state = beg;
+    ode_axpy(a21 * step, k1, state);
+    ode_axpy(a22 * step, k2, state);
+    OdeState k3 = field_rhs(coeffi, field, state);
+    state = beg;
+    ode_axpy(a31 * step, k1, state);
+    ode_axpy(a32 * step, k2, state);
+    ode_axpy(a33 * step, k3, state);
+    OdeState k4 = field_rhs(coeffi, field, state);
+    state = beg;
+    ode_axpy(a41 * step, k1, state);
+    ode_axpy(a42 * step, k2, state);
+    ode_axpy(a43 * step, k3, state);
+    ode_axpy(a44 * step, k4, state);
+    OdeState k5 = field_rhs(coeffi, field, state);
+    state = beg;
+    ode_axpy(a51 * step, k1, state);
+    ode_axpy(a52 * step, k2, state);
+    ode_axpy(a53 * step, k3, state);
+    ode_axpy(a54 * step, k4, state);
+    ode_axpy(a55 * step, k5, state);
+    OdeState k6 = field_rhs(coeffi, field, state);
+    result.end_state = beg;
+    ode_axpy(a61 * step, k1, result.end_state);
+    ode_axpy(a63 * step, k3, result.end_state);
+    ode_axpy(a64 * step, k4, result.end_state);
+    ode_axpy(a65 * step, k5, result.end_state);
+    ode_axpy(a66 * step, k6, result.end_state);
+    OdeState k7 = field_rhs(coeffi, field, result.end_state);
+    result.err_state.pos = make_real3(0, 0, 0);
+    result.err_state.mom = make_real3(0, 0, 0);
+    ode_axpy(d71 * step, k1, result.err_state);
+    ode_axpy(d73 * step, k3, result.err_state);
+    ode_axpy(d74 * step, k4, result.err_state);
+    ode_axpy(d75 * step, k5, result.err_state);
+    ode_axpy(d76 * step, k6, result.err_state);
+    ode_axpy(d77 * step, k7, result.err_state);
+    real half_step = step / real(2);
+    result.mid_state = beg;
+    ode_axpy(c71 * half_step, k1, result.mid_state);
+    ode_axpy(c73 * half_step, k3, result.mid_state);
+    ode_axpy(c74 * half_step, k4, result.mid_state);
+    ode_axpy(c75 * half_step, k5, result.mid_state);
+    ode_axpy(c76 * half_step, k6, result.mid_state);
+    ode_axpy(c77 * half_step, k7, result.mid_state);
+}
+
+
 struct FieldDriver
 {
     FieldParams const& opt;
@@ -51,105 +179,11 @@ struct FieldDriver
         field = make_real3(f.field[0], f.field[1], f.field[2]);
     }
 
-    //! Right-hand side of the equation of motion
-    B2_D OdeState rhs(OdeState const& y) const
-    {
-        real momentum_inv = 1 / sqrt(dot(y.mom, y.mom));
-        OdeState r;
-        r.pos = make_real3(momentum_inv * y.mom[0], momentum_inv * y.mom[1], momentum_inv * y.mom[2]);
-        real c = coeffi * momentum_inv;
-        Real3 x = cross_product(y.mom, field);
-        r.mom = make_real3(c * x[0], c * x[1], c * x[2]);
-        return r;
-    }
-
     //! One Dormand-Prince trial step
     B2_D FieldStepperResult apply_step(real step, OdeState const& beg) const
     {
-        using R = real;
-        constexpr R a11 = 0.2;
-        constexpr R a21 = 0.075;
-        constexpr R a22 = 0.225;
-        constexpr R a31 = 44 / R(45);
-        constexpr R a32 = -56 / R(15);
-        constexpr R a33 = 32 / R(9);
-        constexpr R a41 = 19372 / R(6561);
-        constexpr R a42 = -25360 / R(2187);
-        constexpr R a43 = 64448 / R(6561);
-        constexpr R a44 = -212 / R(729);
-        constexpr R a51 = 9017 / R(3168);
-        constexpr R a52 = -355 / R(33);
-        constexpr R a53 = 46732 / R(5247);
-        constexpr R a54 = 49 / R(176);
-        constexpr R a55 = -5103 / R(18656);
-        constexpr R a61 = 35 / R(384);
-        constexpr R a63 = 500 / R(1113);
-        constexpr R a64 = 125 / R(192);
-        constexpr R a65 = -2187 / R(6784);
-        constexpr R a66 = 11 / R(84);
-        constexpr R d71 = a61 - 5179 / R(57600);
-        constexpr R d73 = a63 - 7571 / R(16695);
-        constexpr R d74 = a64 - 393 / R(640);
-        constexpr R d75 = a65 + 92097 / R(339200);
-        constexpr R d76 = a66 - 187 / R(2100);
-        constexpr R d77 = -1 / R(40);
-        constexpr R c71 = R(6025192743.) / R(30085553152.);
-        constexpr R c73 = R(51252292925.) / R(65400821598.);
-        constexpr R c74 = R(-2691868925.) / R(45128329728.);
-        constexpr R c75 = R(187940372067.) / R(1594534317056.);
-        constexpr R c76 = R(-1776094331.) / R(19743644256.);
-        constexpr R c77 = R(11237099.) / R(235043384.);
-
         FieldStepperResult result;
-        OdeState k1 = rhs(beg);
-        OdeState state = beg;
-        ode_axpy(a11 * step, k1, state);
-        OdeState k2 = rhs(state);
-        state = beg;
-        ode_axpy(a21 * step, k1, state);
-        ode_axpy(a22 * step, k2, state);
-        OdeState k3 = rhs(state);
-        state = beg;
-        ode_axpy(a31 * step, k1, state);
-        ode_axpy(a32 * step, k2, state);
-        ode_axpy(a33 * step, k3, state);
-        OdeState k4 = rhs(state);
-        state = beg;
-        ode_axpy(a41 * step, k1, state);
-        ode_axpy(a42 * step, k2, state);
-        ode_axpy(a43 * step, k3, state);
-        ode_axpy(a44 * step, k4, state);
-        OdeState k5 = rhs(state);
-        state = beg;
-        ode_axpy(a51 * step, k1, state);
-        ode_axpy(a52 * step, k2, state);
-        ode_axpy(a53 * step, k3, state);
-        ode_axpy(a54 * step, k4, state);
-        ode_axpy(a55 * step, k5, state);
-        OdeState k6 = rhs(state);
-        result.end_state = beg;
-        ode_axpy(a61 * step, k1, result.end_state);
-        ode_axpy(a63 * step, k3, result.end_state);
-        ode_axpy(a64 * step, k4, result.end_state);
-        ode_axpy(a65 * step, k5, result.end_state);
-        ode_axpy(a66 * step, k6, result.end_state);
-        OdeState k7 = rhs(result.end_state);
-        result.err_state.pos = make_real3(0, 0, 0);
-        result.err_state.mom = make_real3(0, 0, 0);
-        ode_axpy(d71 * step, k1, result.err_state);
-        ode_axpy(d73 * step, k3, result.err_state);
-        ode_axpy(d74 * step, k4, result.err_state);
-        ode_axpy(d75 * step, k5, result.err_state);
-        ode_axpy(d76 * step, k6, result.err_state);
-        ode_axpy(d77 * step, k7, result.err_state);
-        real half_step = step / real(2);
-        result.mid_state = beg;
-        ode_axpy(c71 * half_step, k1, result.mid_state);
-        ode_axpy(c73 * half_step, k3, result.mid_state);
-        ode_axpy(c74 * half_step, k4, result.mid_state);
-        ode_axpy(c75 * half_step, k5, result.mid_state);
-        ode_axpy(c76 * half_step, k6, result.mid_state);
-        ode_axpy(c77 * half_step, k7, result.mid_state);
+        field_apply_step(coeffi, field, step, beg, result);
         return result;
     }
 

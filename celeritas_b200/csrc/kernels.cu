@@ -49,6 +49,22 @@ constexpr int BLOCK = 128;
 #ifndef B2_ALONG_SPLIT_THRESHOLD
 #    define B2_ALONG_SPLIT_THRESHOLD 0
 #endif
+// With a magnetic field the split IS faster (CMS-scale stand-in, saturated iterations:
+// 3.84 -> 3.06 ns per track-step; profiles/README_r01.md): the propagation phase is a substep
+// loop over Dormand-Prince trials and boundary searches through several universe levels,
+// and as one kernel with MSC and energy loss the charged along-step (14 k instructions) spends
+// 44 stall cycles per issued instruction waiting for instruction fetch (ncu). Charged
+// tracks from which the along-step of a FIELD problem runs as phase kernels (0 = never):
+#ifndef B2_ALONG_SPLIT_FIELD_THRESHOLD
+#    define B2_ALONG_SPLIT_FIELD_THRESHOLD 1
+#endif
+// Resident blocks per SM asked of the field-propagation phase kernel. Measured at
+// saturation (gpurun_out/variants_cms2.log): 8 / 6 / 4 / 3 blocks (64 / 80 / 128 / 158
+// registers; 3.4 kB / 2.1 kB / 0.3 kB / 0 of spill loads) = 2.52 / 2.46 / 2.37 / 2.37 ns per
+// track-step
+#ifndef B2_PROPAGATE_FIELD_MIN_BLOCKS
+#    define B2_PROPAGATE_FIELD_MIN_BLOCKS 4
+#endif
 constexpr int ALONG_MIN_BLOCKS = B2_ALONG_MIN_BLOCKS;
 // Threads per block of the along-step kernels (the same register budget per SM: the
 // resident-block request scales with BLOCK / B2_ALONG_BLOCK)
@@ -510,7 +526,7 @@ __global__ void __launch_bounds__(B2_ALONG_BLOCK, (FIELD ? B2_ALONG_FIELD_MIN_BL
     }
 B2_ALONG_PHASE_KERNEL(k_along_msc_limit, along_phase_msc_limit, B2_PHASE_MIN_BLOCKS)
 B2_ALONG_PHASE_KERNEL(k_along_propagate_linear, along_phase_propagate<false>, B2_PHASE_MIN_BLOCKS)
-B2_ALONG_PHASE_KERNEL(k_along_propagate_field, along_phase_propagate<true>, ALONG_MIN_BLOCKS)
+B2_ALONG_PHASE_KERNEL(k_along_propagate_field, along_phase_propagate<true>, B2_PROPAGATE_FIELD_MIN_BLOCKS)
 B2_ALONG_PHASE_KERNEL(k_along_msc_apply, along_phase_msc_apply, B2_PHASE_MIN_BLOCKS)
 B2_ALONG_PHASE_KERNEL(k_along_finish, along_phase_finish, B2_PHASE_MIN_BLOCKS)
 #undef B2_ALONG_PHASE_KERNEL
@@ -1448,7 +1464,11 @@ int b200_step_along_step(B200ParamsView const* params, B200StateView const* stat
     StateView const& s = SV(state);
     u32 nc = s.hint_charged < s.num_slots ? s.hint_charged : s.num_slots;
     u32 nn = s.hint_neutral < s.num_slots ? s.hint_neutral : s.num_slots;
-    if (B2_ALONG_SPLIT_THRESHOLD != 0 && nc >= B2_ALONG_SPLIT_THRESHOLD)
+    bool const split = PV(params).model.field.enabled
+                           ? (B2_ALONG_SPLIT_FIELD_THRESHOLD != 0
+                              && nc >= B2_ALONG_SPLIT_FIELD_THRESHOLD)
+                           : (B2_ALONG_SPLIT_THRESHOLD != 0 && nc >= B2_ALONG_SPLIT_THRESHOLD);
+    if (split)
     {
         ParamsView const& p = PV(params);
         unsigned const grid = grid_for(nc);
