@@ -7,7 +7,9 @@ import bench
 workload = sys.argv[1] if len(sys.argv) > 1 else 'testem3'
 wl = bench.WORKLOADS[workload]
 params = cb.Params(wl['image'])
-st = cb.Stepper(params, 1 << 20)
+import os
+fuse = os.environ.get('FUSE')
+st = cb.Stepper(params, 1 << 20, **({'fuse_threshold': int(fuse)} if fuse else {}))
 prim, offsets = bench.make_workload_events(workload, params, wl['events'], wl['per_event'], 0,
                                            cb.PRIMARY_DTYPE)
 for rep in range(3):
