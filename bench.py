@@ -56,12 +56,19 @@ NCU_TRAFFIC_SOURCE = ('profiles/saturated_kernels_r01e.txt: k_along_step_charged
 # tools/make_cms_scale.py, four universe levels, 1 T field, isotropic 10 GeV e-/gamma)
 WORKLOADS = {
     'testem3': dict(image=IMAGE, config=CONFIG, alg_bytes=ALG_BYTES_PER_TRACK_STEP,
+                    traffic=NCU_TRAFFIC_BYTES_PER_LAUNCH, traffic_source=NCU_TRAFFIC_SOURCE,
                     events=NUM_EVENTS, per_event=PRIMARIES_PER_EVENT,
                     label='TestEm3 full EM (Urban MSC + eloss fluctuations), %d x %d 1 GeV e- '
                           'primaries per GPU'),
     'cms-scale': dict(image=os.path.join(REPO, 'data', 'images', 'cms-scale.b2img'),
                       config=os.path.join(REPO, 'data', 'images', 'cms-scale.json'),
                       alg_bytes=2 * (248 + 56 * 4 + 8 * 4),  # SURVEY.md 8(d) with D=4, P=4
+                      # the four phase kernels of one charged along-step at a saturated
+                      # iteration (5.8e5 charged tracks): read + written bytes
+                      traffic=(168.4 + 21.6 + 203.9 + 149.8 + 206.4 + 83.6 + 49.4 + 0.6) * 1e6,
+                      traffic_source='profiles/cms_scale_kernels_r01.txt: k_along_msc_limit + '
+                                     'k_along_propagate_field + k_along_msc_apply + k_along_finish '
+                                     'at one saturated iteration (ncu --set full)',
                       events=100, per_event=10,
                       label='CMS-scale stand-in geometry (tools/make_cms_scale.py: 4 levels, 2916 '
                             'unit volumes, 2 rect arrays, BIH), 1 T uniform field, full EM, '
@@ -433,8 +440,8 @@ def main():
         'gpu_launches': int(launches),
         'clocks': clocks.summary(),
         'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': achieved, 'peak': peak,
-                     'unit': 'GB/s', 'frac': achieved / peak, 'traffic': NCU_TRAFFIC_BYTES_PER_LAUNCH,
-                     'traffic_source': NCU_TRAFFIC_SOURCE,
+                     'unit': 'GB/s', 'frac': achieved / peak, 'traffic': wl['traffic'],
+                     'traffic_source': wl['traffic_source'],
                      'peak_kind': peak_kind,
                      'kernel_share_of_step': top_secs / total_action_secs,
                      # the same algorithmic bytes over the WHOLE step (all kernels)

@@ -263,3 +263,16 @@ def test_golden_fixtures_match_the_reference():
             if it + 1 < len(gold['steps']):
                 c = stepper.step()
         assert np.allclose(problem.calo(len(gold['calo'])), gold['calo'], rtol=0, atol=0)
+
+
+@needs_ref
+def test_ref_orange_tracking_golden():
+    """The oracle's ray trace (the reference's OrangeTrackView through oracle/ref_harness)
+    reproduces the golden tracks of the reference's own ORANGE tests
+    (test/orange/OrangeJson.test.cc:105-153, 622-638): volume names and segment lengths."""
+    import celerref
+    from orange_golden import GOLDEN, check_trace
+    for geometry, pos, direction, names, dist in GOLDEN:
+        ref = celerref.Problem({'problem': 'geometry',
+                                'geometry_file': 'data/geometry/%s.org.json' % geometry})
+        check_trace(ref.trace, geometry, pos, direction, names, dist)

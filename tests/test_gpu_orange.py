@@ -57,3 +57,13 @@ def test_trace_matches_reference(name):
     assert np.array_equal(rsafe, gsafe)
     # the ray set actually exercises the geometry
     assert (rc[located] & 0x7fffffff).max() >= 2
+
+
+def test_reference_golden_tracks():
+    """The reference's own golden tracks (test/orange/OrangeJson.test.cc:105-153, 622-638)
+    on the GPU: volume names and segment lengths (tests/orange_golden.py)."""
+    import celeritas_b200 as cb
+    from orange_golden import GOLDEN, check_trace
+    for geometry, pos, direction, names, dist in GOLDEN:
+        gpu = cb.Params(data_path('images', 'geo-%s.b2img' % geometry))
+        check_trace(gpu.trace, geometry, pos, direction, names, dist)
