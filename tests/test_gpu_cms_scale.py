@@ -44,6 +44,29 @@ def test_lockstep_cms_scale(energy, nprim, slots, seed, fuse):
     assert gpu.calo().sum() > 0.5 * nprim * energy
 
 
+@pytest.mark.parametrize('fuse', [0, 0xffffffff], ids=['fused', 'per-action'])
+def test_lockstep_cms_scale_init_charge(fuse):
+    """The bench image (track_order init_charge, the reference's GPU default) in lock-step:
+    slot assignment by charge through four universe levels, incl. starts from the queue."""
+    import celeritas_b200 as cb
+    import celerref
+    from parity import lockstep
+    cfg = json.load(open(data_path('images', 'cms-scale.json')))
+    # host-side capacity of the reference only (no overflow at this size; results do not
+    # depend on it)
+    cfg['initializer_capacity'] = 1 << 18
+    refp = celerref.Problem(cfg)
+    slots = 2048  # small on purpose: initializers queue up and start in later iterations
+    ref = refp.stepper(slots)
+    params = cb.Params(data_path('images', 'cms-scale.b2img'))
+    gpu = cb.Stepper(params, slots, fuse_threshold=fuse)
+    hist = lockstep(ref, gpu, isotropic_mix(6, 1000.0, params, seed=13), max_iters=50000,
+                    rtol=REAL_TOL, atol=REAL_TOL)
+    assert not (hist[-1]['alive'] or hist[-1]['queued'])
+    assert max(h['queued'] for h in hist) > 0
+    assert np.allclose(refp.calo(len(cfg['simple_calo'])), gpu.calo(), rtol=1e-9, atol=1e-9)
+
+
 def test_cms_scale_init_charge_many_events():
     """The bench configuration (track_order init_charge, events merged) at a reduced size:
     most of the energy is deposited in the tallied calorimeter cells, and two streams agree
