@@ -48,6 +48,33 @@ constexpr u32 INVALID = 0xffffffffu;
 #    define B2_GEO_FN B2_D
 #endif
 
+// Read-only column of the problem description (ParamsView). Element loads go through
+// the non-coherent path (LDG.E.CONSTANT): the compiler may then move table loads across
+// the stores to the track state, which it cannot prove not to alias.
+// Measured (gpurun_out/variants_ro.log, TestEm3 bench, two A/B pairs): 4447 of 18.9 k loads
+// become LDG.E.CONSTANT; along-step 47.1 -> 46.6 ms, pass 92.2 ms either way: the kernels wait
+// on dependent loads, not on load/store ordering. Kept (no cost). B2_RO_LDG=0 restores plain loads.
+#ifndef B2_RO_LDG
+#    define B2_RO_LDG 1
+#endif
+template<class T>
+struct RO
+{
+    T const* p;
+    RO() = default;
+    B2_HD RO(T const* q) : p(q) {}
+    B2_HD operator T const*() const { return p; }
+    template<class I>
+    B2_D T operator[](I i) const
+    {
+#if B2_RO_LDG && defined(__CUDA_ARCH__)
+        return __ldg(p + i);
+#else
+        return p[i];
+#endif
+    }
+};
+
 // Transcendentals are called out of line. Everything else in the track loop is
 // force-inlined into a handful of large kernels; with ~70 call sites the inlined
 // libdevice bodies (40-150 instructions each) made the charged along-step ~600 KB

@@ -95,50 +95,50 @@ struct GeoParams
     real tol_rel;
     real tol_abs;
 
-    u8 const* universe_type;
-    u32 const* universe_index;
-    u32 const* universe_surface_offset;
-    u32 const* universe_volume_offset;
+    RO<u8> universe_type;
+    RO<u32> universe_index;
+    RO<u32> universe_surface_offset;
+    RO<u32> universe_volume_offset;
 
     SimpleUnit const* simple_units;
-    u32 const* rect_arrays;  // 16 u32 per array (see orange.cuh)
+    RO<u32> rect_arrays;  // 16 u32 per array (see orange.cuh)
 
-    u32 const* local_surface_ids;
-    u32 const* local_volume_ids;
-    u32 const* real_ids;
-    u16 const* logic_ints;
-    real const* reals;
-    u8 const* surface_types;
+    RO<u32> local_surface_ids;
+    RO<u32> local_volume_ids;
+    RO<u32> real_ids;
+    RO<u16> logic_ints;
+    RO<real> reals;
+    RO<u8> surface_types;
 
-    u32 const* vol_face_begin;
-    u32 const* vol_face_end;
-    u32 const* vol_logic_begin;
-    u32 const* vol_logic_end;
-    u32 const* vol_max_isect;
-    u32 const* vol_flags;
-    u32 const* vol_daughter;
+    RO<u32> vol_face_begin;
+    RO<u32> vol_face_end;
+    RO<u32> vol_logic_begin;
+    RO<u32> vol_logic_end;
+    RO<u32> vol_max_isect;
+    RO<u32> vol_flags;
+    RO<u32> vol_daughter;
 
-    u32 const* conn_begin;
-    u32 const* conn_end;
+    RO<u32> conn_begin;
+    RO<u32> conn_end;
 
-    u32 const* daughter_universe;
-    u32 const* daughter_transform;
-    u8 const* transform_type;
-    u32 const* transform_offset;
+    RO<u32> daughter_universe;
+    RO<u32> daughter_transform;
+    RO<u8> transform_type;
+    RO<u32> transform_offset;
 
     float const* bih_bboxes;  // 6 per bbox: lower xyz, upper xyz
-    u32 const* bih_local_volume_ids;
-    u32 const* bih_inner_parent;
-    u32 const* bih_inner_axis;
+    RO<u32> bih_local_volume_ids;
+    RO<u32> bih_inner_parent;
+    RO<u32> bih_inner_axis;
     float const* bih_inner_left_pos;
-    u32 const* bih_inner_left_child;
+    RO<u32> bih_inner_left_child;
     float const* bih_inner_right_pos;
-    u32 const* bih_inner_right_child;
-    u32 const* bih_leaf_parent;
-    u32 const* bih_leaf_vol_begin;
-    u32 const* bih_leaf_vol_end;
+    RO<u32> bih_inner_right_child;
+    RO<u32> bih_leaf_parent;
+    RO<u32> bih_leaf_vol_begin;
+    RO<u32> bih_leaf_vol_end;
 
-    u32 const* volume_material;  // global volume id -> material id
+    RO<u32> volume_material;  // global volume id -> material id
 };
 
 //---------------------------------------------------------------------------//
@@ -149,13 +149,13 @@ struct MatParams
     u32 num_materials;
     u32 num_elements;
     u32 max_element_components;
-    u32 const* element_z;
-    real const* element_reals;   // 6 per element: mass, cbrt_z, cbrt_zzp, log_z, coulomb, mass_rad_coeff
-    u32 const* elcomp_element;
-    real const* elcomp_fraction;
-    u32 const* material_elcomp_begin;
-    u32 const* material_elcomp_end;
-    real const* material_reals;  // 8 per material: number_density, temperature, zeff, density, electron_density, rad_length, mean_exc_energy, log_mean_exc_energy
+    RO<u32> element_z;
+    RO<real> element_reals;   // 6 per element: mass, cbrt_z, cbrt_zzp, log_z, coulomb, mass_rad_coeff
+    RO<u32> elcomp_element;
+    RO<real> elcomp_fraction;
+    RO<u32> material_elcomp_begin;
+    RO<u32> material_elcomp_end;
+    RO<real> material_reals;  // 8 per material: number_density, temperature, zeff, density, electron_density, rad_length, mean_exc_energy, log_mean_exc_energy
 };
 
 enum ElementReal { EL_MASS = 0, EL_CBRT_Z, EL_CBRT_ZZP, EL_LOG_Z, EL_COULOMB, EL_MASS_RAD_COEFF, EL_NUM_REALS };
@@ -164,10 +164,10 @@ enum MaterialReal { MAT_NUMBER_DENSITY = 0, MAT_TEMPERATURE, MAT_ZEFF, MAT_DENSI
 struct ParticleParams
 {
     u32 num_particles;
-    real const* mass;
-    real const* charge;
-    real const* decay_constant;
-    u8 const* matter;  // 1 = antiparticle
+    RO<real> mass;
+    RO<real> charge;
+    RO<real> decay_constant;
+    RO<u8> matter;  // 1 = antiparticle
 };
 
 struct CutoffParams
@@ -176,9 +176,9 @@ struct CutoffParams
     u32 num_materials;
     u32 apply_post_interaction;
     u32 id_gamma, id_electron, id_positron;
-    real const* energy;  // [index][material]
-    real const* range;
-    u32 const* id_to_index;
+    RO<real> energy;  // [index][material]
+    RO<real> range;
+    RO<u32> id_to_index;
 };
 
 //---------------------------------------------------------------------------//
@@ -206,37 +206,37 @@ struct PhysParams
     u32 fixed_step_action;
 
     // Grids
-    u32 const* grid_size;
-    real const* grid_log_front;
-    real const* grid_log_back;
-    real const* grid_log_delta;
-    u32 const* grid_prime;
-    u32 const* grid_value_offset;
-    real const* reals;
+    RO<u32> grid_size;
+    RO<real> grid_log_front;
+    RO<real> grid_log_back;
+    RO<real> grid_log_delta;
+    RO<u32> grid_prime;
+    RO<u32> grid_value_offset;
+    RO<real> reals;
     // Node energies exp(log_front + i * log_delta) of every grid, tabulated by the host
     // loader with the host libm: the same doubles the reference computes at run time
     // (UniformGrid::operator[] + std::exp in XsCalculator), without two exp() calls per
     // lookup on the device
-    u32 const* grid_energy_offset;  // [grid] into grid_energy
-    real const* grid_energy;
+    RO<u32> grid_energy_offset;  // [grid] into grid_energy
+    RO<real> grid_energy;
 
     // Per (particle, ppid)
-    u32 const* pp_num;        // [particle]
-    u32 const* pp_eloss_ppid; // [particle]
-    u32 const* pp_has_at_rest;
-    u32 const* pp_process;    // [particle][P]
-    u32 const* pp_grid;       // [3][particle][P][material]
-    u8 const* pp_integral;    // [particle][P]
-    real const* pp_energy_max_xs;  // [particle][P][material]
-    u32 const* pp_model_begin;     // [particle][P] -> pm_pmid
-    u32 const* pp_model_count;
-    u32 const* pm_energy_begin;    // [particle][P] -> pm_energy
-    real const* pm_energy;
-    u32 const* pm_pmid;
-    u32 const* pmid_model;         // [pmid] -> model id
-    u32 const* elsel_begin;        // [pmid][material] -> elsel_grid or INVALID
-    u32 const* elsel_count;
-    u32 const* elsel_grid;
+    RO<u32> pp_num;        // [particle]
+    RO<u32> pp_eloss_ppid; // [particle]
+    RO<u32> pp_has_at_rest;
+    RO<u32> pp_process;    // [particle][P]
+    RO<u32> pp_grid;       // [3][particle][P][material]
+    RO<u8> pp_integral;    // [particle][P]
+    RO<real> pp_energy_max_xs;  // [particle][P][material]
+    RO<u32> pp_model_begin;     // [particle][P] -> pm_pmid
+    RO<u32> pp_model_count;
+    RO<u32> pm_energy_begin;    // [particle][P] -> pm_energy
+    RO<real> pm_energy;
+    RO<u32> pm_pmid;
+    RO<u32> pmid_model;         // [pmid] -> model id
+    RO<u32> elsel_begin;        // [pmid][material] -> elsel_grid or INVALID
+    RO<u32> elsel_count;
+    RO<u32> elsel_grid;
 
     // Hardwired (on-the-fly xs) models
     u32 hw_photoelectric;       // process id
@@ -295,9 +295,9 @@ struct SeltzerBergerParams
     u32 gamma;
     real electron_mass;
     // per element: 8 u32 {x_begin, x_size, y_begin, y_size, values_begin, argmax_begin, 0, 0}
-    u32 const* elements;
-    u32 const* sizes;   // argmax values (y index of the row maximum)
-    real const* reals;
+    RO<u32> elements;
+    RO<u32> sizes;   // argmax values (y index of the row maximum)
+    RO<real> reals;
 };
 
 struct RelativisticBremParams
@@ -309,7 +309,7 @@ struct RelativisticBremParams
     u32 enable_lpm;
     real electron_mass;
     // per element: fz, factor1, factor2, gamma_factor, epsilon_factor
-    real const* elem_data;
+    RO<real> elem_data;
 };
 
 //! Livermore photoelectric data (em/data/LivermorePEData.hh)
@@ -321,13 +321,13 @@ struct LivermorePEParams
     real inv_electron_mass;
     // per element: 8 u32 {xs_lo grid begin, xs_lo size, xs_lo value begin, xs_hi grid begin,
     //                     xs_hi size, xs_hi value begin, shell begin, shell count}
-    u32 const* elements;
-    real const* element_thresh;  // 2 per element: thresh_lo, thresh_hi
+    RO<u32> elements;
+    RO<real> element_thresh;  // 2 per element: thresh_lo, thresh_hi
     // per shell: 4 u32 {grid begin, size, value begin, 0}
-    u32 const* shells;
+    RO<u32> shells;
     // per shell: 13 reals {binding_energy, param_lo[6], param_hi[6]}
-    real const* shell_reals;
-    real const* reals;
+    RO<real> shell_reals;
+    RO<real> reals;
 };
 
 //! Urban multiple scattering (em/data/UrbanMscData.hh)
@@ -340,15 +340,15 @@ struct UrbanMscParams
     real tau_small, tau_big, tau_limit, safety_tol, geom_limit;
     real low_energy_limit, high_energy_limit;
     // per material: 8 reals {stepmin_coeff[2], theta_coeff[2], tail_coeff[3], tail_corr}
-    real const* material_data;
+    RO<real> material_data;
     // per (material, particle in {e-, e+}): 2 reals {scaled_zeff, d_over_r}
-    real const* par_mat_data;
+    RO<real> par_mat_data;
     // per (material, particle): xs grid {size, prime, value offset} + log grid
-    u32 const* xs_grid_u32;   // 3 per entry: size, prime_index, value_offset
-    real const* xs_grid_f64;  // 3 per entry: log_front, log_back, log_delta
-    real const* reals;
-    u32 const* xs_grid_energy_offset;  // [entry] into grid_energy (host-tabulated node energies)
-    real const* grid_energy;
+    RO<u32> xs_grid_u32;   // 3 per entry: size, prime_index, value_offset
+    RO<real> xs_grid_f64;  // 3 per entry: log_front, log_back, log_delta
+    RO<real> reals;
+    RO<u32> xs_grid_energy_offset;  // [entry] into grid_energy (host-tabulated node energies)
+    RO<real> grid_energy;
 };
 
 //! Energy-loss fluctuation (em/data/FluctuationData.hh)
@@ -358,7 +358,7 @@ struct FluctuationParams
     u32 electron;
     real electron_mass;
     // per material: 6 reals {binding_energy[2], log_binding_energy[2], oscillator_strength[2]}
-    real const* urban;
+    RO<real> urban;
 };
 
 //! Uniform magnetic field + driver options (field/FieldDriverOptions.hh:26-93)
@@ -411,15 +411,15 @@ struct ModelParams
 struct RngParams
 {
     u32 seed;
-    u32 const* jump;              // [32][5]
-    u32 const* jump_subsequence;  // [32][5]
+    RO<u32> jump;              // [32][5]
+    RO<u32> jump_subsequence;  // [32][5]
 };
 
 struct SimParams
 {
     u32 has_looping;
-    u32 const* looping_steps;  // 2 per particle: max_subthreshold_steps, max_steps
-    real const* looping_energy;
+    RO<u32> looping_steps;  // 2 per particle: max_subthreshold_steps, max_steps
+    RO<real> looping_energy;
 };
 
 struct CoreScalars
