@@ -52,7 +52,8 @@ NCU_TRAFFIC_SOURCE = ('profiles/saturated_kernels_r01e.txt: k_along_step_charged
                       'along-step touches about two thirds of the per-slot state)')
 
 
-# --workload: the headline (BASELINE configs[1]) and the CMS-scale stand-in (configs[3]/[4]:
+# --workload: the headline (BASELINE configs[1]), simple-CMS (configs[2]) and the CMS-scale
+# stand-in (configs[3]/[4]:
 # tools/make_cms_scale.py, four universe levels, 1 T field, isotropic 10 GeV e-/gamma)
 WORKLOADS = {
     'testem3': dict(image=IMAGE, config=CONFIG, alg_bytes=ALG_BYTES_PER_TRACK_STEP,
@@ -73,6 +74,15 @@ WORKLOADS = {
                       label='CMS-scale stand-in geometry (tools/make_cms_scale.py: 4 levels, 2916 '
                             'unit volumes, 2 rect arrays, BIH), 1 T uniform field, full EM, '
                             '%d x %d isotropic 10 GeV e-/gamma primaries from the origin per GPU'),
+    # BASELINE configs[2]: simple-CMS nested cylinders, 1 T uniform field, 10 GeV e-/gamma mix
+    'simple-cms': dict(image=os.path.join(REPO, 'data', 'images',
+                                          'simple-cms-em-field-initcharge.b2img'),
+                       config=os.path.join(REPO, 'data', 'images', 'simple-cms-em-field.json'),
+                       alg_bytes=ALG_BYTES_PER_TRACK_STEP, events=100, per_event=10,
+                       traffic=None, traffic_source='no ncu capture for this workload',
+                       label='simple-CMS nested cylinders (test/geocel/data/simple-cms.org.json), '
+                             '1 T uniform field, full EM, %d x %d isotropic 10 GeV e-/gamma '
+                             'primaries from the origin per GPU'),
 }
 
 
@@ -216,7 +226,7 @@ def run_reference_arm(args, rank, world):
     cores = os.cpu_count() or 1
     threads = cores
     per_event, num_events = 4, max(2 * threads, 8)
-    if args.workload == 'cms-scale':
+    if args.workload != 'testem3':
         per_event, num_events = 1, max(threads, 4)  # 10 GeV showers: ~10x the steps each
     # warm-up passes are smaller; each timed step is the same bounded sample
     for _ in range(args.warmup):
@@ -452,7 +462,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         ne, pe = max(2 * cores, 8), 4
-        if args.workload == 'cms-scale':
+        if args.workload != 'testem3':
             ne, pe = max(cores, 4), 1
         rc = cpu_reference_run(ne, pe, 4096, cores, args.workload)
         line['cpu_baseline'] = {

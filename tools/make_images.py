@@ -81,6 +81,8 @@ PROBLEMS['cms-scale'] = {'geometry_file': 'data/geometry/cms-scale.org.json',
                          'seed': 20220904, 'initializer_capacity': 1 << 25, 'max_events': 16384,
                          'field': [0, 0, 1], 'track_order': 'init_charge',
                          'simple_calo': CMS_CALO}
+PROBLEMS['simple-cms-em-field-initcharge'] = dict(PROBLEMS['simple-cms-em-field'],
+                                                     track_order='init_charge')
 PROBLEMS['cms-scale-small'] = dict(PROBLEMS['cms-scale'], initializer_capacity=1 << 18,
                                    max_events=64, track_order='none')
 
