@@ -155,3 +155,19 @@ def test_celer_sim_input_validation_without_gpu():
     if cb.device_count() == 0:
         with pytest.raises(cb.B200Error):
             cb.celer_sim_run(base)
+
+
+def test_cms_scale_geometry_is_reproducible():
+    """data/geometry/cms-scale.org.json is exactly what tools/make_cms_scale.py writes."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(REPO, 'tools'))
+    import make_cms_scale
+    geo, mats = make_cms_scale.build()
+    committed = json.load(open(os.path.join(REPO, 'data', 'geometry', 'cms-scale.org.json')))
+    assert json.loads(json.dumps(geo)) == committed
+    assert len(geo['universes']) == 11
+    assert sum(len(u.get('volumes', [])) for u in geo['universes']) == 2916
+    # every material-bearing volume of the geometry is named in the physics file
+    phys = json.load(open(os.path.join(REPO, 'data', 'physics', 'cms-scale-steel-lar.json')))
+    assert {v['name'] for v in phys['volumes']} == set(mats)
