@@ -347,6 +347,41 @@ def calc_xs(log_front, log_back, values, prime_index, energy):
     return r
 
 
+def calc_range(log_front, log_back, values, energy):
+    """RangeCalculator::operator() (/root/reference/src/celeritas/grid/RangeCalculator.hh:
+    79-108): scaled by sqrt(E/Emin) below the grid, clipped above, linear in E between nodes."""
+    n = len(values)
+    loge = math.log(energy)
+    log_delta = (log_back - log_front) / (n - 1)
+    if loge <= log_front:
+        return values[0] * math.exp(0.5 * (loge - log_front))
+    if loge >= log_back:
+        return values[n - 1]
+    lo = int((loge - log_front) / log_delta)
+    e_lo = math.exp(log_front + log_delta * lo)
+    e_hi = math.exp(log_front + log_delta * (lo + 1))
+    slope = (values[lo + 1] - values[lo]) / (e_hi - e_lo)
+    return fma(slope, energy - e_lo, values[lo])
+
+
+def calc_inverse_range(log_front, log_back, ranges, rng):
+    """InverseRangeCalculator::operator() (grid/InverseRangeCalculator.hh:86-116): energy of a
+    particle with the given range; E = Emin (r / r0)^2 below the first node."""
+    n = len(ranges)
+    log_delta = (log_back - log_front) / (n - 1)
+    assert 0 <= rng <= ranges[-1]
+    if rng < ranges[0]:
+        return math.exp(log_front) * (rng / ranges[0]) ** 2
+    if rng >= ranges[-1]:
+        return math.exp(log_back)
+    # NonuniformGrid::find: the last node not above the value
+    lo = max(i for i in range(n) if ranges[i] <= rng)
+    e_lo = math.exp(log_front + log_delta * lo)
+    e_hi = math.exp(log_front + log_delta * (lo + 1))
+    slope = (e_hi - e_lo) / (ranges[lo + 1] - ranges[lo])
+    return fma(slope, rng - ranges[lo], e_lo)
+
+
 # --------------------------------------------------------------------------- #
 # ORANGE logic
 # --------------------------------------------------------------------------- #

@@ -116,6 +116,21 @@ def test_xs_calculator_golden():
         assert restate.calc_xs(front, back, vals, 3, e) == pytest.approx(want, rel=1e-12)
 
 
+def test_range_calculators_golden():
+    """test/celeritas/grid/RangeCalculator.test.cc:20-62 and InverseRangeCalculator.test.cc:
+    20-72: energy grid 10 .. 1e4 MeV in 4 points, range = E / 20."""
+    front, back = math.log(10.0), math.log(1e4)
+    delta = (back - front) / 3
+    values = [0.05 * math.exp(front + delta * i) for i in range(4)]
+    for e, want in [(1, 0.5 * math.sqrt(1 / 10.)), (2, 0.5 * math.sqrt(2 / 10.)), (10, 0.5),
+                    (20, 1.0), (100, 5.0), (1e4, 500), (1.001e4, 500)]:
+        assert restate.calc_range(front, back, values, e) == pytest.approx(want, rel=1e-12)
+    values[-1] = 500.0
+    for r, want in [(0.5 * math.sqrt(1 / 10.), 1.0), (0.5 * math.sqrt(2 / 10.), 2.0), (0.5, 10.0),
+                    (1, 20.0), (5, 100.0), (500, 1e4)]:
+        assert restate.calc_inverse_range(front, back, values, r) == pytest.approx(want, rel=1e-12)
+
+
 def test_logic_evaluator():
     """Logic strings of the reference's two-boxes geometry (data/geometry/two-boxes.org.json)."""
     inner = restate.parse_logic('0 1 ~ & 2 & 3 ~ & 4 & 5 ~ &')
