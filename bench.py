@@ -258,10 +258,11 @@ def run_reference_arm(args, rank, world):
 
 def run_reference_cuda_arm(args, rank, world):
     """The reference's OWN CUDA build (oracle/_ref/libcelerref_cuda.so: its .cu files compiled
-    for sm_100 by oracle/Makefile) on this GPU, same workload, same primaries, same number of
-    track slots, events merged onto one state (celer-sim's GPU configuration: one stream,
-    track_order init_charge). Not the driver's reference arm (that is the CPU one): this is the
-    number BASELINE.json's target is stated against."""
+    for sm_100 by oracle/Makefile with the reference's CMake defaults, CELERITAS_MAX_BLOCK_SIZE
+    256) on this GPU, same workload, same primaries, same number of track slots, events merged
+    onto one state (celer-sim's GPU configuration: one stream, track_order init_charge). Not the
+    driver's reference arm (that is the CPU one): this is the number BASELINE.json's target is
+    stated against. SM clocks are sampled during the timed region like in the main arm."""
     if rank != 0:
         return
     os.environ['CELERREF_CUDA'] = '1'
@@ -278,78 +279,89 @@ def run_reference_cuda_arm(args, rank, world):
     for _ in range(args.warmup):
         celerref.run_merged_device(problem, prim, args.slots)
     steps, secs, iters = 0, 0.0, 0
-    for _ in range(args.steps):
-        r = celerref.run_merged_device(problem, prim, args.slots)
-        steps += r['num_steps']
-        secs += r['seconds']
-        iters += r['num_step_iterations']
+    with ClockSampler(int(os.environ.get('LOCAL_RANK', '0'))) as clocks:
+        for _ in range(args.steps):
+            r = celerref.run_merged_device(problem, prim, args.slots)
+            steps += r['num_steps']
+            secs += r['seconds']
+            iters += r['num_step_iterations']
     line = {'impl': 'reference-cuda', 'metric': 'track-steps/sec', 'value': steps / secs,
             'unit': 'track-steps/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 * secs / args.steps, 'higher_is_better': True, 'dtype': 'f64',
             'data': 'synthetic', 'num_step_iterations': iters,
+            'track_steps_per_pass': steps // max(args.steps, 1),
             'events_per_sec': events * args.steps / secs,
+            'clocks': clocks.summary(),
             'config': {'workload': (wl['label'] % (events, per_event))
                                    + ', merged events, %d track slots on one stream, track_order '
                                      'init_charge; steel/lAr stand-in physics' % args.slots,
                        'build': "the reference's own .cu sources, nvcc -O3 -gencode "
-                                'arch=compute_100,code=sm_100 (oracle/Makefile ref_cuda)'}}
+                                'arch=compute_100,code=sm_100, CELERITAS_MAX_BLOCK_SIZE 256 '
+                                '(oracle/Makefile ref_cuda)'}}
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=3)
-    ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'reference-cuda'])
-    ap.add_argument('--workload', default='testem3', choices=sorted(WORKLOADS))
-    ap.add_argument('--events', type=int, default=None)
-    ap.add_argument('--primaries-per-event', type=int, default=None)
-    ap.add_argument('--slots', type=int, default=NUM_TRACK_SLOTS)
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--streams', type=int, default=NUM_STREAMS,
-                    help='concurrent steppers (CUDA streams) per GPU; slots are divided among them')
-    args = ap.parse_args()
-    if args.warmup < 3:
-        args.warmup = 3
-    wl = WORKLOADS[args.workload]
-    if args.events is None:
-        args.events = wl['events']
-    if args.primaries_per_event is None:
-        args.primaries_per_event = wl['per_event']
+def reference_cuda_subrecord(workload, slots, events, per_event, b200_value, steps=2, warmup=1):
+    """Run the reference's own CUDA build on the same GPU right after our timed region, in a
+    child process (its library and ours both own a CUDA context; the child keeps the CPU
+    oracle library out of this process), and return {value, ms_per_step, clocks, ratio}."""
+    lib = os.path.join(REPO, 'oracle', '_ref', 'libcelerref_cuda.so')
+    if not os.path.exists(lib):
+        return {'unavailable': 'oracle/_ref/libcelerref_cuda.so not built (make -C oracle ref_cuda)'}
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference-cuda',
+           '--workload', workload, '--steps', str(steps), '--warmup', str(warmup),
+           '--slots', str(slots), '--events', str(events),
+           '--primaries-per-event', str(per_event)]
+    env = dict(os.environ)
+    for k in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE'):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    except subprocess.TimeoutExpired:
+        return {'unavailable': 'reference CUDA build timed out after 600 s'}
+    for text in reversed(out.stdout.strip().splitlines()):
+        if text.startswith('{'):
+            r = json.loads(text)
+            return {'value': r['value'], 'unit': r['unit'], 'ms_per_step': r['ms_per_step'],
+                    'steps': r['steps'], 'warmup': r['warmup'],
+                    'num_step_iterations': r['num_step_iterations'],
+                    'track_steps_per_pass': r['track_steps_per_pass'],
+                    'clocks': r['clocks'], 'ratio': b200_value / r['value'],
+                    'ratio_is': 'this library (value) / reference CUDA build (value), same GPU, '
+                                'same workload and primaries, measured back to back',
+                    'build': r['config']['build']}
+    return {'unavailable': 'reference CUDA arm failed: ' + (out.stderr.strip()[-300:] or 'no output')}
 
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
 
-    if args.impl == 'reference':
-        run_reference_arm(args, rank, world)
-        return
-    if args.impl == 'reference-cuda':
-        run_reference_cuda_arm(args, rank, world)
-        return
+# Algorithmic bytes of ONE action per track-step (DESIGN.md section 4, "byte shares"): the
+# per-slot fields that action has to read plus the ones it has to write, at D levels and P
+# processes, out of the 2 * S_live of SURVEY.md 8(d).
+def action_alg_bytes(action, depth, nproc):
+    geo = 31 + 56 * depth
+    if action.startswith('along-step'):
+        # reads geo, particle 12, material 4, sim 45, phys scalars 48 + msc 32, rng 24;
+        # writes geo, sim 45, energy 8, phys 40 + msc 32, rng 24
+        return (geo + 12 + 4 + 45 + 48 + 32 + 24) + (geo + 45 + 8 + 40 + 32 + 24)
+    if action == 'pre-step':
+        return (12 + 4 + 45 + 8 + 24 + 8 + 4 * depth) + (45 + 8 + 8 * nproc + 16 + 24 + 16)
+    return None
 
+
+def run_b200(args, workload, steps, warmup, rank, local_rank, world, dist, events, per_event,
+             with_roofline=True):
+    """One workload on this rank's GPU: returns the measurements of the timed regions."""
     import torch
     import celeritas_b200 as cb
-    torch.cuda.set_device(local_rank)
-    cb.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-
-    params = cb.Params(os.environ.get('B200_BENCH_IMAGE', wl['image']))
+    wl = WORKLOADS[workload]
+    params = cb.Params(os.environ.get('B200_BENCH_IMAGE', wl['image'])
+                       if workload == 'testem3' else wl['image'])
     nstreams = max(args.streams, 1)
     steppers = [cb.Stepper(params, args.slots // nstreams, stream_id=rank * nstreams + k)
                 for k in range(nstreams)]
-    # per-action timing (roofline leg) is taken on one stream holding the whole workload
-    stepper = steppers[0] if nstreams == 1 else cb.Stepper(params, args.slots,
-                                                           stream_id=rank * nstreams)
     assert params.find_particle(11) == 1
     ndet = params.num_detectors
     # Events are sharded by rank: rank r owns global events [r*E, (r+1)*E)
-    prim, offsets = make_workload_events(args.workload, params, args.events,
-                                         args.primaries_per_event, rank * args.events,
+    prim, offsets = make_workload_events(workload, params, events, per_event, rank * events,
                                          cb.PRIMARY_DTYPE)
     nprim = len(prim)
 
@@ -381,7 +393,7 @@ def main():
             dist.all_reduce(counts)
         return calo.cpu().numpy(), counts.cpu().numpy()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         reduce_tallies(one_pass())
 
     # ---- timed region 1: e2e through the public C-ABI with HOST buffers
@@ -392,7 +404,7 @@ def main():
         ev0.record()
         total_steps = total_iters = 0
         dev_secs = 0.0
-        for _ in range(args.steps):
+        for _ in range(steps):
             r = one_pass()
             calo, counts = reduce_tallies(r)
             total_steps += int(counts[0])
@@ -408,57 +420,173 @@ def main():
         dist.all_reduce(dsecs, op=dist.ReduceOp.MAX)
     e2e_secs = float(e2e_secs.item())
     dsecs = float(dsecs.item())
+    value = total_steps / dsecs
+    depth = params.max_depth
+    out = {
+        'value': value, 'unit': 'track-steps/s', 'ms_per_step': 1e3 * dsecs / steps,
+        'steps': steps, 'warmup': warmup,
+        'events_per_sec': events * steps * world / dsecs,
+        'num_step_iterations': total_iters,
+        'track_steps_per_pass_per_gpu': total_steps // max(steps * world, 1),
+        'e2e': {'value': total_steps / e2e_secs, 'unit': 'track-steps/s',
+                'h2d_bytes_per_step': int(nprim * 72 + 12 * nprim),
+                'd2h_bytes_per_step': int(64 * (total_iters // max(steps * world, 1))
+                                          + 8 * ndet)},
+        'gpu_launches': int(launches),
+        'clocks': clocks.summary(),
+        'workload': (wl['label'] % (events, per_event))
+                    + (', merged events, %d track slots over %d concurrent stream(s), '
+                       'track_order init_charge; steel/lAr stand-in physics '
+                       '(tools/make_physics.py)' % (args.slots, nstreams)),
+        'calo_sum_mev': float(calo.sum()),
+    }
+    if with_roofline:
+        # ---- timed region 2: per-action CUDA-event timing (one stream holding the whole
+        # workload, one launch per action) for the roofline of the dominant kernel
+        stepper = steppers[0] if nstreams == 1 else cb.Stepper(params, args.slots,
+                                                               stream_id=rank * nstreams)
+        stepper.set_action_times(True)
+        before = stepper.action_times
+        stepper.calo_clear()
+        r2 = stepper.run_events(prim, offsets, merge_events=True)
+        after = stepper.action_times
+        stepper.set_action_times(False)
+        per_action = {k: after[k] - before.get(k, 0.0) for k in after}
+        top = max(per_action, key=per_action.get)
+        top_secs = per_action[top]
+        total_action_secs = sum(per_action.values())
+        peak, peak_kind = measured_peak_gbs()
+        nproc = 4
+        alg_step = 2 * (248 + 56 * depth + 8 * nproc)
+        alg_action = action_alg_bytes(top, depth, nproc) or alg_step
+        # every track-step of the pass goes through this action exactly once
+        achieved = r2['num_steps'] * alg_action / top_secs / 1e9
+        out['roofline'] = {
+            'bound': 'hbm', 'kernel': top, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            'frac': achieved / peak, 'traffic': wl['traffic'],
+            'traffic_source': wl['traffic_source'], 'peak_kind': peak_kind,
+            'alg_bytes_per_track_step_this_action': alg_action,
+            'alg_bytes_per_track_step_whole_step': alg_step,
+            'kernel_share_of_step': top_secs / total_action_secs,
+            # track-steps/s x B_alg over the peak of ALL GPUs of the job
+            'whole_step': {'achieved': value * alg_step / 1e9,
+                           'peak': peak * world,
+                           'frac': value * alg_step / 1e9 / (peak * world)},
+            'per_action_seconds': per_action}
+    del steppers
+    return out
 
-    # ---- timed region 2: per-action CUDA-event timing for the roofline of the top kernel
-    stepper.set_action_times(True)
-    before = stepper.action_times
-    stepper.calo_clear()
-    r2 = stepper.run_events(prim, offsets, merge_events=True)
-    after = stepper.action_times
-    stepper.set_action_times(False)
-    per_action = {k: after[k] - before.get(k, 0.0) for k in after}
-    top = max(per_action, key=per_action.get)
-    top_secs = per_action[top]
-    total_action_secs = sum(per_action.values())
-    peak, peak_kind = measured_peak_gbs()
-    achieved = r2['num_steps'] * wl['alg_bytes'] / top_secs / 1e9
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'reference-cuda'])
+    ap.add_argument('--workload', default='testem3', choices=sorted(WORKLOADS))
+    ap.add_argument('--events', type=int, default=None)
+    ap.add_argument('--primaries-per-event', type=int, default=None)
+    ap.add_argument('--slots', type=int, default=NUM_TRACK_SLOTS)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true',
+                    help='skip the reference-CUDA sub-record, the extra workloads and the '
+                         'strong-scaling pass (kernel tuning runs)')
+    ap.add_argument('--streams', type=int, default=NUM_STREAMS,
+                    help='concurrent steppers (CUDA streams) per GPU; slots are divided among them')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    wl = WORKLOADS[args.workload]
+    if args.events is None:
+        args.events = wl['events']
+    if args.primaries_per_event is None:
+        args.primaries_per_event = wl['per_event']
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+        return
+    if args.impl == 'reference-cuda':
+        run_reference_cuda_arm(args, rank, world)
+        return
+
+    import torch
+    import celeritas_b200 as cb
+    torch.cuda.set_device(local_rank)
+    cb.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    main_run = run_b200(args, args.workload, args.steps, args.warmup, rank, local_rank, world,
+                        dist, args.events, args.primaries_per_event)
+
+    # The other workloads of BASELINE.json (configs[2] simple-CMS, configs[3]/[4] CMS-scale)
+    # on every rank (weak scaling: every rank its own events), three timed passes each
+    extra = {}
+    strong = None
+    if not args.no_extra and args.workload == 'testem3':
+        for name in ('cms-scale', 'simple-cms'):
+            if name == 'simple-cms' and world > 1:
+                continue  # configs[4] is the CMS-scale sweep
+            w = WORKLOADS[name]
+            extra[name] = run_b200(args, name, 3, 3, rank, local_rank, world, dist,
+                                   w['events'], w['per_event'], with_roofline=(world == 1))
+        if world > 1 and args.events % world == 0:
+            # strong scaling: the SAME 100 x 100 primaries split over the N GPUs
+            strong = run_b200(args, args.workload, 3, 3, rank, local_rank, world, dist,
+                              args.events // world, args.primaries_per_event,
+                              with_roofline=False)
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    value = total_steps / dsecs
+    r = main_run
     line = {
-        'metric': 'track-steps/sec', 'value': value, 'unit': 'track-steps/s',
+        'metric': 'track-steps/sec', 'value': r['value'], 'unit': 'track-steps/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1e3 * dsecs / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': (wl['label'] % (args.events, args.primaries_per_event))
-                               + (', merged events, %d track slots over %d concurrent stream(s), '
-                                  'track_order init_charge; steel/lAr stand-in physics '
-                                  '(tools/make_physics.py)' % (args.slots, nstreams)),
+        'config': {'workload': r['workload'],
                    'l2': 'working set %.0f MB of SoA state per pass exceeds the 126 MB L2'
                          % (args.slots * 336 / 1e6),
                    'parallelism': 'events sharded by rank, NCCL all-reduce of tallies'},
-        'events_per_sec': args.events * args.steps * world / dsecs,
-        'num_step_iterations': total_iters,
-        'e2e': {'value': total_steps / e2e_secs, 'unit': 'track-steps/s',
-                'h2d_bytes_per_step': int(nprim * 72 + 12 * nprim),
-                'd2h_bytes_per_step': int(64 * (total_iters // max(args.steps * world, 1))
-                                          + 8 * ndet)},
-        'gpu_launches': int(launches),
-        'clocks': clocks.summary(),
-        'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': achieved, 'peak': peak,
-                     'unit': 'GB/s', 'frac': achieved / peak, 'traffic': wl['traffic'],
-                     'traffic_source': wl['traffic_source'],
-                     'peak_kind': peak_kind,
-                     'kernel_share_of_step': top_secs / total_action_secs,
-                     # the same algorithmic bytes over the WHOLE step (all kernels)
-                     'whole_step': {'achieved': value * wl['alg_bytes'] / 1e9,
-                                    'frac': value * wl['alg_bytes'] / 1e9 / peak},
-                     'per_action_seconds': per_action},
+        'events_per_sec': r['events_per_sec'],
+        'num_step_iterations': r['num_step_iterations'],
+        'e2e': r['e2e'], 'gpu_launches': r['gpu_launches'], 'clocks': r['clocks'],
+        'roofline': r['roofline'],
     }
+    if strong is not None:
+        line['strong_scaling'] = {
+            'what': 'the same %d x %d primaries split over %d GPUs (events sharded by rank)'
+                    % (args.events, args.primaries_per_event, world),
+            'value': strong['value'], 'unit': 'track-steps/s',
+            'events_per_sec': strong['events_per_sec'], 'ms_per_step': strong['ms_per_step'],
+            'e2e': strong['e2e'], 'clocks': strong['clocks']}
+    if not args.no_extra and world == 1:
+        line['reference_cuda'] = reference_cuda_subrecord(
+            args.workload, args.slots, args.events, args.primaries_per_event, r['value'])
+    if extra:
+        line['workloads'] = {}
+        for name, x in extra.items():
+            rec = {'b200': {k: x[k] for k in ('value', 'unit', 'ms_per_step', 'steps', 'warmup',
+                                              'events_per_sec', 'num_step_iterations', 'e2e',
+                                              'gpu_launches', 'track_steps_per_pass_per_gpu')},
+                   'clocks': x['clocks'], 'config': {'workload': x['workload']},
+                   'n_gpus': world, 'scaling': 'weak'}
+            if 'roofline' in x:
+                rec['roofline'] = x['roofline']
+            if world == 1:
+                w = WORKLOADS[name]
+                rec['reference_cuda'] = reference_cuda_subrecord(
+                    name, args.slots, w['events'], w['per_event'], x['value'])
+            line['workloads'][name] = rec
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         ne, pe = max(2 * cores, 8), 4
@@ -468,8 +596,10 @@ def main():
         line['cpu_baseline'] = {
             'value': rc['num_steps'] / rc['seconds'], 'unit': 'track-steps/s', 'cores': cores,
             'kind': 'reference',
-            'sample': '%d events x %d primaries of the same workload, reference host Stepper '
-                      '(oracle/_ref), one per OpenMP thread, 4096 slots each' % (ne, pe)}
+            'sample': '%d events x %d primaries of the same workload (a bounded sample: the GPU '
+                      'arm runs %d x %d merged onto one state), reference host Stepper '
+                      '(oracle/_ref), one per OpenMP thread, 4096 slots each, track_order none'
+                      % (ne, pe, args.events, args.primaries_per_event)}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

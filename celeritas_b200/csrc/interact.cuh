@@ -1004,7 +1004,10 @@ B2_D void run_interaction(ParamsView const& pv, StateView const& s, u32 slot, u3
         return mat.elcomp_element[mat.material_elcomp_begin[material] + elcomp];
     };
 
-    Interaction result = Interaction::from_unchanged();
+    // a model action without an interactor here is a load-time error (CoreParams::load);
+    // should one get through, the track fails loudly instead of silently not interacting
+    Interaction result;
+    result.action = IA_FAILED;
     if (action == m.kn.action)
     {
         result = interact_klein_nishina(m.kn, particle.energy, dir, rng);
@@ -1031,6 +1034,18 @@ B2_D void run_interaction(ParamsView const& pv, StateView const& s, u32 slot, u3
     {
         result = interact_relativistic_brem(
             pv, particle, dir, material, element_of(s.element[slot]), rng);
+    }
+    else if (action == m.cb.action)
+    {
+        // em/interactor/CombinedBremInteractor.hh:132-170: relativistic sampler at and above
+        // 1 GeV, Seltzer-Berger below; same angular distribution and final state either way
+        // The combined model has no element selector: its executor always interacts with the
+        // material's first element (em/executor/CombinedBremExecutor.hh:42-44)
+        u32 const element = element_of(0);
+        if (particle.energy >= m.cb.sb_upper_limit)
+            result = interact_relativistic_brem(pv, particle, dir, material, element, rng);
+        else
+            result = interact_seltzer_berger(pv, particle, dir, material, element, rng);
     }
     else if (action == m.pe.action)
     {

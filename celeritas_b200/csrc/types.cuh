@@ -105,6 +105,7 @@ enum TrackOrder : u32
 {
     ORDER_NONE = 0,
     ORDER_INIT_CHARGE = 1,
+    ORDER_SIZE_
 };
 
 struct Real3

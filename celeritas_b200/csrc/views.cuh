@@ -390,6 +390,14 @@ struct PhysConstants
     real alpha_fine_structure;
 };
 
+//! Combined bremsstrahlung (em/data/CombinedBremData.hh): Seltzer-Berger tables and
+//! relativistic-model data (held in ModelParams::sb / rb) behind one action
+struct CombinedBremParams
+{
+    u32 action;
+    real sb_upper_limit;  // detail::seltzer_berger_upper_limit() = 1 GeV
+};
+
 struct ModelParams
 {
     KleinNishinaParams kn;
@@ -399,6 +407,7 @@ struct ModelParams
     SeltzerBergerParams sb;
     RelativisticBremParams rb;
     LivermorePEParams pe;
+    CombinedBremParams cb;
     UrbanMscParams msc;
     FluctuationParams fluct;
     FieldParams field;

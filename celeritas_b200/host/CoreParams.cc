@@ -78,6 +78,14 @@ uint32_t CoreParams::find_particle(int pdg) const
     return 0xffffffffu;
 }
 
+bool CoreParams::has_action(std::string const& label) const
+{
+    for (ActionRecord const& a : actions_)
+        if (a.label == label)
+            return true;
+    return false;
+}
+
 void CoreParams::load(Image const& img)
 {
     auto U32 = [&](char const* n) { return arena_.upload(img.get<uint32_t>(n)); };
@@ -105,7 +113,7 @@ void CoreParams::load(Image const& img)
         init_capacity_ = init.at(0);
         max_events_ = init.at(1);
         view_.scalars.track_order = init.at(2);
-        if (init.at(2) > ORDER_INIT_CHARGE)
+        if (init.at(2) >= ORDER_SIZE_)
             throw std::runtime_error("unsupported track_order in image");
     }
 
@@ -372,6 +380,15 @@ void CoreParams::load(Image const& img)
             m.pe.shell_reals = F64("model.pe.shell_reals");
             m.pe.reals = F64("model.pe.reals");
         }
+        // Combined bremsstrahlung model (celer-sim `brem_combined`): uses the sb / rb data
+        m.cb.action = INVALID;
+        m.cb.sb_upper_limit = 1e3;  // em/interactor/detail/PhysicsConstants.hh:62-65
+        if (img.has("model.cb.action"))
+        {
+            if (!img.has("model.sb.ids") || !img.has("model.rb.ids"))
+                throw std::runtime_error("combined bremsstrahlung needs the sb and rb data");
+            m.cb.action = img.get_scalar<uint32_t>("model.cb.action");
+        }
         m.msc.enabled = 0;
         if (img.has("msc.ids"))
         {
@@ -436,6 +453,20 @@ void CoreParams::load(Image const& img)
             m.field.max_nsteps = u.at(0);
             m.field.max_substeps = u.at(1);
         }
+        // Every discrete model action must have an interactor here: an unclaimed one would
+        // limit steps through its cross section and then do nothing at the interaction
+        for (uint32_t a = view_.phys.model_to_action;
+             a < view_.phys.model_to_action + view_.phys.num_models;
+             ++a)
+        {
+            bool const claimed = a == m.kn.action || a == m.mb.action || a == m.epgg.action
+                                 || a == m.bh.action || a == m.sb.action || a == m.rb.action
+                                 || a == m.pe.action || a == m.cb.action;
+            if (!claimed)
+                throw std::runtime_error(
+                    "no B200 interactor for model action '"
+                    + (a < actions_.size() ? actions_[a].label : std::to_string(a)) + "'");
+        }
         auto c = img.get<double>("constants");
         m.constants.migdal_constant = c.at(0);
         m.constants.lpm_constant = c.at(1);
@@ -446,6 +477,8 @@ void CoreParams::load(Image const& img)
     //// RNG / SIM ////
     {
         auto r = img.get<uint32_t>("rng.params");
+        if (r.size() < 1 + 160 + 160)
+            throw std::runtime_error("rng.params: expected seed + 2 x [32][5] jump polynomials");
         view_.rng.seed = r.at(0);
         std::vector<uint32_t> jump(r.begin() + 1, r.begin() + 1 + 160);
         std::vector<uint32_t> jump_sub(r.begin() + 161, r.begin() + 161 + 160);
@@ -484,10 +517,24 @@ void CoreParams::load(Image const& img)
     }
 }
 
+namespace
+{
+void require_unfrozen(bool frozen, char const* what)
+{
+    // CoreState sizes track_counters, the initializer queue and ti_neutral_prefix from these
+    // at construction: changing them under a live state would overrun its arrays
+    if (frozen)
+        throw std::runtime_error(std::string(what)
+                                 + " cannot change after a CoreState has been created");
+}
+}  // namespace
+
 void CoreParams::init_capacity(uint32_t capacity)
 {
     if (capacity == 0)
         throw std::runtime_error("nonpositive initializer_capacity=0");
+    if (capacity != init_capacity_)
+        require_unfrozen(frozen_, "initializer_capacity");
     init_capacity_ = capacity;
 }
 
@@ -495,7 +542,18 @@ void CoreParams::max_events(uint32_t num_events)
 {
     if (num_events == 0)
         throw std::runtime_error("max_events must be positive");
+    if (num_events != max_events_)
+        require_unfrozen(frozen_, "max_events");
     max_events_ = num_events;
+}
+
+void CoreParams::track_order(uint32_t order)
+{
+    if (order >= ORDER_SIZE_)
+        throw std::runtime_error("unsupported track_order");
+    if (order != view_.scalars.track_order)
+        require_unfrozen(frozen_, "track_order");
+    view_.scalars.track_order = order;
 }
 
 void CoreParams::uniform_field_tesla(double const (&field)[3])

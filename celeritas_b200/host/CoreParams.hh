@@ -66,6 +66,8 @@ class CoreParams
     uint32_t max_events() const { return max_events_; }
     uint32_t rng_seed() const { return view_.rng.seed; }
     uint32_t find_particle(int pdg) const;
+    //! Whether the problem's action table has an action with this label
+    bool has_action(std::string const& label) const;
     bool particle_is_neutral(uint32_t particle_id) const
     {
         return particle_id < particle_charge_.size() && particle_charge_[particle_id] == 0;
@@ -78,6 +80,12 @@ class CoreParams
     void rng_seed(uint32_t seed) { view_.rng.seed = seed; }
     void init_capacity(uint32_t capacity);
     void max_events(uint32_t num_events);
+    //! Track order (b200::TrackOrder); slot assignment of starting tracks depends on it
+    void track_order(uint32_t order);
+    uint32_t track_order() const { return view_.scalars.track_order; }
+    //! True once a CoreState has been built on these params: the run options above are
+    //! frozen from then on (CoreState sizes its arrays from them)
+    void freeze() const { frozen_ = true; }
     //! Uniform field [T]; only for problems built with the uniform-field along-step
     void uniform_field_tesla(double const (&field)[3]);
     bool has_uniform_field() const { return view_.model.field.enabled != 0; }
@@ -98,5 +106,6 @@ class CoreParams
     uint32_t const* d_detector_of_volume_{nullptr};
     uint32_t init_capacity_{0};
     uint32_t max_events_{0};
+    mutable bool frozen_{false};
 };
 }  // namespace celeritas_b200

@@ -19,6 +19,7 @@ CoreState::CoreState(std::shared_ptr<CoreParams const> params,
 {
     if (num_track_slots == 0)
         throw std::runtime_error("num_track_slots must be positive");
+    params_->freeze();
     B2_CUDA_CALL(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     ParamsView const& p = params_->view();
     StateView& s = view_;

@@ -265,8 +265,12 @@ std::string celer_sim_run(std::string const& input_json)
         throw std::runtime_error("nonpositive secondary_stack_factor");
     if (inp.step_diagnostic && inp.step_diagnostic_bins <= 0)
         throw std::runtime_error("nonpositive step diagnostic 'max' bin");
-    if (inp.track_order != "none" && inp.track_order != "init_charge"
-        && inp.track_order != "unsorted")
+    uint32_t track_order = b200::ORDER_NONE;
+    if (inp.track_order == "none" || inp.track_order == "unsorted")
+        track_order = b200::ORDER_NONE;
+    else if (inp.track_order == "init_charge")
+        track_order = b200::ORDER_INIT_CHARGE;
+    else
     {
         // The dense charged/neutral slot lists give init_charge coherence natively;
         // the reindexing orders are not implemented
@@ -286,6 +290,24 @@ std::string celer_sim_run(std::string const& input_json)
             "'simple_calo' differs from the detector volumes the problem image was exported "
             "with");
     params->rng_seed(inp.seed);
+    // Run options celer-sim applies when it builds the problem (Runner.cc:323-440). The
+    // track order is a property of the loop, not of the tables: it is applied here. The
+    // step limiter and the bremsstrahlung model choice are baked into the exported physics
+    // tables: they must agree with the image.
+    params->track_order(track_order);
+    {
+        double const image_limiter = params->view().phys.fixed_step_limiter;
+        if (inp.step_limiter != image_limiter)
+            throw std::runtime_error("'step_limiter' (" + std::to_string(inp.step_limiter)
+                                     + ") differs from the value the problem image was "
+                                       "exported with ("
+                                     + std::to_string(image_limiter) + ")");
+        if (inp.brem_combined != params->has_action("brems-combined"))
+            throw std::runtime_error(
+                std::string("'brem_combined' is ") + (inp.brem_combined ? "true" : "false")
+                + " but the problem image was exported "
+                + (inp.brem_combined ? "without" : "with") + " the combined bremsstrahlung model");
+    }
 
     // Events (Runner::build_events, Runner.cc:452-500)
     std::vector<uint32_t> particle_ids;

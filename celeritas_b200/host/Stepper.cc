@@ -532,8 +532,9 @@ StepperResult Stepper::operator()(B200Primary const* primaries, uint32_t n)
 
 void Stepper::warm_up()
 {
+    // reference: Stepper::warm_up (Stepper.cc:104-115) requires an empty state
     CoreStateCounters c = state_->sync_counters();
-    if (c.num_active != 0 && c.num_alive != 0)
+    if (c.num_alive != 0 || c.num_initializers != 0 || staging_->count != 0)
         throw std::runtime_error("cannot warm up when state has active tracks");
     (*this)();
 }

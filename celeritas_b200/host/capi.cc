@@ -138,6 +138,11 @@ uint32_t b200_params_model_action_begin(B200Params const* params)
     return params->params->view().phys.model_to_action;
 }
 
+uint32_t b200_params_max_depth(B200Params const* params)
+{
+    return params->params->view().geo.max_depth;
+}
+
 uint32_t b200_params_find_particle(B200Params const* params, int pdg)
 {
     return params->params->find_particle(pdg);

@@ -64,6 +64,7 @@ EXPORTS = [
     'b200_primaries_generate', 'b200_celer_sim_run', 'b200_string_free',
     'b200_params_num_particles', 'b200_run_events_streams', 'b200_step_fused',
     'b200_step_post_tail', 'b200_step_along_select', 'b200_params_num_models', 'b200_params_model_action_begin',
+    'b200_params_max_depth',
 ]
 
 _lib = None
@@ -110,6 +111,8 @@ def load_library():
     L.b200_params_num_models.restype = C.c_uint32
     L.b200_params_model_action_begin.argtypes = [vp]
     L.b200_params_model_action_begin.restype = C.c_uint32
+    L.b200_params_max_depth.argtypes = [vp]
+    L.b200_params_max_depth.restype = C.c_uint32
     L.b200_state_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]
     L.b200_state_destroy.argtypes = [vp]
     L.b200_state_view.argtypes = [vp]
@@ -228,6 +231,10 @@ class Params:
     @property
     def num_particles(self):
         return load_library().b200_params_num_particles(self.h)
+
+    @property
+    def max_depth(self):
+        return load_library().b200_params_max_depth(self.h)
 
     def generate_primaries(self, primary_options):
         """Primaries of a celer-sim `primary_options` dict; returns (primaries, offsets)."""

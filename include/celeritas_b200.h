@@ -129,6 +129,8 @@ uint32_t b200_params_num_particles(B200Params const* params);
 /* Discrete models are the actions [model_action_begin, model_action_begin + num_models) */
 uint32_t b200_params_num_models(B200Params const* params);
 uint32_t b200_params_model_action_begin(B200Params const* params);
+/* Deepest universe nesting of the geometry (OrangeParams::max_depth, src/orange/OrangeParams.hh) */
+uint32_t b200_params_max_depth(B200Params const* params);
 
 /*--- per-stream state -------------------------------------------------------*/
 int b200_state_create(B200Params const* params,

@@ -43,7 +43,9 @@
 #define CELERITAS_CORE_RNG_XORWOW 1
 #define CELERITAS_CORE_RNG CELERITAS_CORE_RNG_XORWOW
 
-#define CELERITAS_MAX_BLOCK_SIZE 0
+// The reference's CMake sets 256 whenever CUDA is on (/root/reference/CMakeLists.txt:94-97);
+// every action kernel is __launch_bounds__(CELERITAS_MAX_BLOCK_SIZE)
+#define CELERITAS_MAX_BLOCK_SIZE 256
 
 inline constexpr char celeritas_build_type[] = "Release";
 inline constexpr char celeritas_hostname[] = "oracle";

@@ -22,6 +22,7 @@
 #include "celeritas/em/model/KleinNishinaModel.hh"
 #include "celeritas/em/model/LivermorePEModel.hh"
 #include "celeritas/em/model/MollerBhabhaModel.hh"
+#include "celeritas/em/model/CombinedBremModel.hh"
 #include "celeritas/em/model/RelativisticBremModel.hh"
 #include "celeritas/em/model/SeltzerBergerModel.hh"
 #include "celeritas/em/params/FluctuationParams.hh"
@@ -480,6 +481,10 @@ void export_physics(HostCRef<PhysicsParamsData> const& p,
     // Hardwired models
     {
         auto const& h = p.hardwired;
+        // Atomic relaxation emits more secondaries per interaction than the fixed per-slot
+        // secondary storage of the B200 state holds
+        CELER_VALIDATE(!h.relaxation_data,
+                       << "atomic relaxation has no B200 export");
         img.put("phys.hardwired",
                 U32{raw(h.photoelectric),
                     raw(h.livermore_pe),
@@ -497,6 +502,51 @@ void export_models(Problem const& prob, b200::Image& img)
     PhysicsParams const& phys = *prob.core->physics();
     U32 model_kind(phys.num_models(), 0);
     std::string labels;
+    auto put_sb = [&img](uint32_t action,
+                         uint32_t electron,
+                         uint32_t positron,
+                         uint32_t gamma,
+                         double electron_mass,
+                         auto const& t) {
+        img.put("model.sb.ids", U32{action, electron, positron, gamma});
+        img.put_scalar<double>("model.sb.electron_mass", electron_mass);
+        U32 rows;
+        for (auto const& el : all(t.elements))
+        {
+            rows.push_back(el.grid.x.begin()->unchecked_get());
+            rows.push_back(el.grid.x.size());
+            rows.push_back(el.grid.y.begin()->unchecked_get());
+            rows.push_back(el.grid.y.size());
+            rows.push_back(el.grid.values.begin()->unchecked_get());
+            rows.push_back(el.argmax.begin()->unchecked_get());
+            rows.push_back(0);
+            rows.push_back(0);
+        }
+        img.put("model.sb.elements", rows);
+        U32 sizes(all(t.sizes).begin(), all(t.sizes).end());
+        img.put("model.sb.sizes", sizes);
+        F64 reals(all(t.reals).begin(), all(t.reals).end());
+        img.put("model.sb.reals", reals);
+    };
+    auto put_rb = [&img](uint32_t action, auto const& d) {
+        img.put("model.rb.ids",
+                U32{action,
+                    raw(d.ids.electron),
+                    raw(d.ids.positron),
+                    raw(d.ids.gamma),
+                    d.enable_lpm ? 1u : 0u});
+        img.put_scalar<double>("model.rb.electron_mass", d.electron_mass.value());
+        F64 ed;
+        for (auto const& e : all(d.elem_data))
+        {
+            ed.push_back(e.fz);
+            ed.push_back(e.factor1);
+            ed.push_back(e.factor2);
+            ed.push_back(e.gamma_factor);
+            ed.push_back(e.epsilon_factor);
+        }
+        img.put("model.rb.elem_data", ed);
+    };
     for (auto mid : range(ModelId{phys.num_models()}))
     {
         auto const& model = *phys.model(mid);
@@ -545,53 +595,31 @@ void export_models(Problem const& prob, b200::Image& img)
         else if (auto* sb = dynamic_cast<SeltzerBergerModel const*>(&model))
         {
             auto const& d = sb->host_ref();
-            img.put("model.sb.ids",
-                    U32{sb->action_id().unchecked_get(),
-                        raw(d.ids.electron),
-                        raw(d.ids.positron),
-                        raw(d.ids.gamma)});
-            img.put_scalar<double>("model.sb.electron_mass",
-                                   d.electron_mass.value());
-            auto const& t = d.differential_xs;
-            U32 rows;
-            for (auto const& el : all(t.elements))
-            {
-                rows.push_back(el.grid.x.begin()->unchecked_get());
-                rows.push_back(el.grid.x.size());
-                rows.push_back(el.grid.y.begin()->unchecked_get());
-                rows.push_back(el.grid.y.size());
-                rows.push_back(el.grid.values.begin()->unchecked_get());
-                rows.push_back(el.argmax.begin()->unchecked_get());
-                rows.push_back(0);
-                rows.push_back(0);
-            }
-            img.put("model.sb.elements", rows);
-            U32 sizes(all(t.sizes).begin(), all(t.sizes).end());
-            img.put("model.sb.sizes", sizes);
-            F64 reals(all(t.reals).begin(), all(t.reals).end());
-            img.put("model.sb.reals", reals);
+            put_sb(sb->action_id().unchecked_get(),
+                   raw(d.ids.electron),
+                   raw(d.ids.positron),
+                   raw(d.ids.gamma),
+                   d.electron_mass.value(),
+                   d.differential_xs);
         }
         else if (auto* rb = dynamic_cast<RelativisticBremModel const*>(&model))
         {
-            auto const& d = rb->host_ref();
-            img.put("model.rb.ids",
-                    U32{rb->action_id().unchecked_get(),
-                        raw(d.ids.electron),
-                        raw(d.ids.positron),
-                        raw(d.ids.gamma),
-                        d.enable_lpm ? 1u : 0u});
-            img.put_scalar<double>("model.rb.electron_mass",
-                                   d.electron_mass.value());
-            F64 ed;
-            for (auto const& e : all(d.elem_data))
-            {
-                ed.push_back(e.fz);
-                ed.push_back(e.factor1);
-                ed.push_back(e.factor2);
-                ed.push_back(e.gamma_factor);
-                ed.push_back(e.epsilon_factor);
-            }
-            img.put("model.rb.elem_data", ed);
+            put_rb(rb->action_id().unchecked_get(), rb->host_ref());
+        }
+        else if (auto* cb = dynamic_cast<CombinedBremModel const*>(&model))
+        {
+            // Seltzer-Berger below 1 GeV, relativistic above, behind ONE action
+            // (em/interactor/CombinedBremInteractor.hh:132-170): both data sets are
+            // exported with no action of their own, plus the combined action id
+            auto const& d = cb->host_ref();
+            put_sb(0xffffffffu,
+                   raw(d.rb_data.ids.electron),
+                   raw(d.rb_data.ids.positron),
+                   raw(d.rb_data.ids.gamma),
+                   d.rb_data.electron_mass.value(),
+                   d.sb_differential_xs);
+            put_rb(0xffffffffu, d.rb_data);
+            img.put_scalar<uint32_t>("model.cb.action", cb->action_id().unchecked_get());
         }
         else if (auto* pe = dynamic_cast<LivermorePEModel const*>(&model))
         {

@@ -129,8 +129,11 @@ def test_diagnostics_match_reference(fuse):
     assert gpu.action_diagnostic().sum() == 0 and gpu.step_diagnostic().sum() == 0
 
 
+@pytest.mark.parametrize('order', ['none', 'init_charge'])
 @pytest.mark.parametrize('merge', [False, True])
-def test_celer_sim_run_matches_reference(merge):
+def test_celer_sim_run_matches_reference(merge, order):
+    """`track_order` is a run option (RunnerInput.hh:123): the SAME image runs with either
+    slot assignment and must match the reference built with that order."""
     import celeritas_b200 as cb
     slots = 4096
     opts = dict(PRIMARY_OPTIONS, num_events=3, primaries_per_event=4, pdg=[11, 22])
@@ -143,12 +146,14 @@ def test_celer_sim_run_matches_reference(merge):
         'initializer_capacity': cfg['initializer_capacity'], 'secondary_stack_factor': 3,
         'simple_calo': cfg['simple_calo'], 'action_diagnostic': True, 'step_diagnostic': True,
         'step_diagnostic_bins': 50, 'merge_events': merge, 'action_times': True,
-        'warm_up': True,
+        'warm_up': True, 'track_order': order,
     }
     out = cb.celer_sim_run(run_input)
     runner = out['result']['runner']
+    assert out['input']['track_order'] == order
 
-    refp = reference_problem('testem3-small', action_diagnostic=True, step_diagnostic_bins=50)
+    refp = reference_problem('testem3-small', action_diagnostic=True, step_diagnostic_bins=50,
+                             track_order=order)
     prim = refp.generate_primaries(opts)
     offsets = [0, len(prim)] if merge else list(range(0, len(prim) + 1, 4))
     ref = refp.stepper(slots)
@@ -205,6 +210,7 @@ def test_celer_sim_max_steps_aborts_like_reference():
         'geometry_file': cfg['geometry_file'], 'primary_options': opts, 'seed': cfg['seed'],
         'num_track_slots': slots, 'initializer_capacity': cfg['initializer_capacity'],
         'secondary_stack_factor': 3, 'max_steps': 25, 'warm_up': False,
+        'track_order': 'none',
     }
     runner = cb.celer_sim_run(run_input)['result']['runner']
     refp = reference_problem('testem3-small')
@@ -234,6 +240,8 @@ def test_celer_sim_input_errors():
             ({'field_options': {'minimum_step': 1}}, "'field_options' cannot be specified"),
             ({'field': [0, 0, 1]}, 'without a uniform-field'),
             ({'_format': 'other'}, 'invalid format'),
+            ({'step_limiter': 0.5}, "'step_limiter'"),
+            ({'brem_combined': True}, "'brem_combined'"),
             ({'simple_calo': ['world']}, 'simple_calo')):
         inp = dict(base)
         for k, v in change.items():

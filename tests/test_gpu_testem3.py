@@ -136,3 +136,20 @@ def test_action_sorted_lists_match_reference_actions():
             break
         cr, cg = ref.step(), gpu.step()
     assert interactions > 500 and checked >= 5
+
+
+@pytest.mark.parametrize('fuse', [0, NEVER_FUSE], ids=['fused', 'per-action'])
+def test_lockstep_combined_brem(fuse):
+    """celer-sim `brem_combined`: CombinedBremInteractor (Seltzer-Berger below 1 GeV,
+    relativistic with LPM above; em/interactor/CombinedBremInteractor.hh:132-170) behind one
+    action. 2 GeV electrons in liquid argon exercise both samplers; whole showers in
+    lock-step, integers and RNG words identical."""
+    import celeritas_b200 as cb
+    from parity import lockstep
+    refp, ref, params, gpu = setup('lar-sphere-combined', 4096, fuse)
+    assert 'brems-combined' in params.action_labels
+    prim = cb.make_primaries(4, particle_id=params.find_particle(11), energy=2000.0,
+                             pos=(0, 0, 0), direction=(1, 0, 0))
+    hist = lockstep(ref, gpu, prim, compare_every=1)
+    assert sum(h['active'] for h in hist) > 10000
+    assert np.allclose(refp.calo(1), gpu.calo(), rtol=1e-9, atol=1e-9)

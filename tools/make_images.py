@@ -69,6 +69,14 @@ PROBLEMS = {
                       'physics_file': 'data/physics/testem3-steel-lar.json',
                       'seed': 20220904, 'initializer_capacity': 1 << 18, 'max_events': 64,
                       'simple_calo': GAPS + ABSORBERS},
+    # celer-sim `brem_combined`: one bremsstrahlung model (Seltzer-Berger below 1 GeV,
+    # relativistic above) instead of two. The reference allows it only with single-element
+    # materials (PhysicsParams.cc:665): liquid-argon sphere in vacuum, full EM
+    'lar-sphere-combined': {'geometry_file': 'data/geometry/lar-sphere.org.json',
+                            'physics_file': 'data/physics/lar-sphere-em.json',
+                            'seed': 20220904, 'initializer_capacity': 1 << 18,
+                            'max_events': 64, 'brem_combined': True,
+                            'simple_calo': ['sphere']},
 }
 
 # BASELINE configs 3/4: CMS-scale stand-in (tools/make_cms_scale.py): four levels, 2916 unit
