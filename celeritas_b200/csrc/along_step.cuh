@@ -231,12 +231,13 @@ B2_D real msc_step_from_geo(real gstep, real true_step, real alpha, real range, 
 
 //! Urban msc step limitation (UrbanMsc::limit_step, UrbanMscSafetyStepLimit.hh,
 //! UrbanMscMinimalStepLimit.hh)
+template<class Geo>
 B2_D void msc_limit_step(ParamsView const& p,
                          StateView const& s,
                          u32 slot,
                          Particle const& particle,
                          PhysTrack const& phys,
-                         GeoTrack& geo)
+                         Geo& geo)
 {
     UrbanMscParams const& msc = p.model.msc;
     PhysParams const& pp = p.phys;
@@ -415,12 +416,13 @@ B2_D real urban_positron_correction(real zeff, real y)
 
 //! Apply msc: true path, angular deflection, lateral displacement
 //! (UrbanMsc::apply_step, em/msc/detail/UrbanMscScatter.hh)
+template<class Geo>
 B2_D void msc_apply_step(ParamsView const& p,
                          StateView const& s,
                          u32 slot,
                          Particle const& particle,
                          PhysTrack const& phys,
-                         GeoTrack& geo)
+                         Geo& geo)
 {
     UrbanMscParams const& msc = p.model.msc;
     PhysParams const& pp = p.phys;
@@ -926,7 +928,8 @@ B2_D void apply_eloss(ParamsView const& p, StateView const& s, u32 slot, PhysTra
 // PROPAGATION / TIME / TRACK UPDATE
 //---------------------------------------------------------------------------//
 //! Straight-line propagation up to `dist` (field/LinearPropagator.hh:58-93)
-B2_D Propagation propagate_linear(GeoTrack& geo, real dist)
+template<class Geo>
+B2_D Propagation propagate_linear(Geo& geo, real dist)
 {
     Propagation result = geo.find_next_step(true, dist);
     if (result.boundary)
@@ -1069,11 +1072,12 @@ B2_D void along_phase_finish(ParamsView const& p, StateView const& s, u32 slot)
 
 //! Whole along-step for one alive track. CHARGED is a compile-time property of the
 //! launch (dense per-charge slot lists), so the neutral kernel carries no msc/eloss code.
-template<bool CHARGED, bool FIELD>
+//! COOP: the warp's 32 lanes all run this track (see GeoTrackT in orange.cuh).
+template<bool CHARGED, bool FIELD, bool COOP = false>
 B2_D void along_step(ParamsView const& p, StateView const& s, u32 slot)
 {
     Particle particle = load_particle(p, s, slot);
-    GeoTrack geo(p, s, slot);
+    GeoTrackT<COOP> geo(p, s, slot);
     PhysTrack phys(p, particle.id, s.material_id[slot]);
     constexpr bool charged = CHARGED;
     constexpr bool use_field = CHARGED && FIELD;

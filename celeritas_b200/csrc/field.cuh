@@ -351,7 +351,8 @@ struct FieldDriver
 };
 
 //! Propagate a charged track in the field up to `step` or the next boundary
-B2_D Propagation propagate_field(ParamsView const& p, Particle const& particle, GeoTrack& geo, real step)
+template<class Geo>
+B2_D Propagation propagate_field(ParamsView const& p, Particle const& particle, Geo& geo, real step)
 {
     FieldParams const& opt = p.model.field;
     FieldDriver driver(opt, particle.charge);

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(BLOCK) k_initialize_tracks(B2_GRID_CONSTANT Pa
     u32 const num_vac = s.counters[CTR_NUM_VACANCIES];
     u32 const num_new = num_init < num_vac ? num_init : num_vac;
     if (tid < num_new)
-        initialize_track(p, s, tid, num_init, num_vac, num_new);
+        initialize_track(p, s, tid, num_init, num_vac, num_new, [&s](u32 k) { return s.vacancies[k]; });
 }
 
 __global__ void k_initialize_finalize(StateView s)

@@ -1121,18 +1121,31 @@ B2_GEO_FN bool geo_initialize(GeoParams const& g,
 B2_GEO_FN void
 geo_move_internal_pos(GeoParams const& g, StateView const& s, u32 slot, real x, real y, real z);
 
-struct GeoTrack
+// COOP = warp-cooperative mode: all 32 lanes of a warp hold the SAME track (same slot, same
+// registers, same control flow) and split the per-face work of the distance and safety
+// searches among them (coop_find_next_step / coop_find_safety below). Everything else is
+// executed redundantly by every lane: loads are broadcasts, stores write the same value to
+// the same address. Used for iterations with fewer tracks than warps (csrc/tail.cu).
+template<bool COOP>
+struct GeoTrackT;
+template<bool COOP>
+B2_D Propagation coop_find_next_step(GeoTrackT<COOP>& t, bool limited, real max_step);
+template<bool COOP>
+B2_D real coop_find_safety(GeoTrackT<COOP>& t);
+
+template<bool COOP>
+struct GeoTrackT
 {
     GeoParams const& g;
     StateView const& s;
     u32 slot;
     bool failed;
 
-    B2_D GeoTrack(ParamsView const& p, StateView const& st, u32 sl)
+    B2_D GeoTrackT(ParamsView const& p, StateView const& st, u32 sl)
         : g(p.geo), s(st), slot(sl), failed(false)
     {
     }
-    B2_D GeoTrack(GeoParams const& gp, StateView const& st, u32 sl)
+    B2_D GeoTrackT(GeoParams const& gp, StateView const& st, u32 sl)
         : g(gp), s(st), slot(sl), failed(false)
     {
     }
@@ -1341,7 +1354,10 @@ struct GeoTrack
     //! Distance to next boundary over all levels (find_next_step[_impl])
     B2_D Propagation find_next_step(bool limited, real max_step)
     {
-        return geo_find_next_step(g, s, slot, limited, max_step);
+        if constexpr (COOP)
+            return coop_find_next_step(*this, limited, max_step);
+        else
+            return geo_find_next_step(g, s, slot, limited, max_step);
     }
     B2_D Propagation find_next_step_impl(bool limited, real max_step)
     {
@@ -1497,7 +1513,13 @@ struct GeoTrack
         clear_next();
     }
 
-    B2_D real find_safety() { return geo_find_safety(g, s, slot); }
+    B2_D real find_safety()
+    {
+        if constexpr (COOP)
+            return coop_find_safety(*this);
+        else
+            return geo_find_safety(g, s, slot);
+    }
     B2_D real find_safety_impl()
     {
         real min_safety = real_inf();
@@ -1510,6 +1532,239 @@ struct GeoTrack
         return min_safety;
     }
 };
+using GeoTrack = GeoTrackT<false>;
+
+//---------------------------------------------------------------------------//
+// WARP-COOPERATIVE DISTANCE AND SAFETY SEARCH
+//
+// The reference walks the universe levels of a track one after the other and, inside each
+// level, the faces of the current volume one after the other
+// (OrangeTrackView::find_next_step_impl, OrangeTrackView.hh; SimpleUnitTracker::
+// intersect_impl / simple_intersect, univ/SimpleUnitTracker.hh:390-507): for a lone track
+// that is (levels x faces) dependent chains of four loads and a quadratic solve. Here the
+// (level, face) pairs of ALL levels are dealt out to the lanes of the warp that holds the
+// track, every lane solves one face, and two warp-wide integer minima pick the winner.
+//
+// Same result as the serial search: at level 0 a root is valid if d <= max_step (limited)
+// or d < real_max; at deeper levels the reference passes the shallower levels' best distance
+// as the limit and takes a deeper intersection only if it is STRICTLY closer, so the result
+// is the lexicographic minimum of (distance, level, face) over the roots that are strictly
+// below that limit; "first of equal" inside a level is the lowest face, across levels the
+// shallowest level. Lanes are numbered in (level, face) order, so the tie-break is the lowest
+// lane. Levels that are rect arrays or volumes with internal surfaces / implicit
+// (background) volumes are ONE item: the lane runs the serial per-universe search for it.
+// More than 32 items: every lane runs the serial search (redundantly).
+//---------------------------------------------------------------------------//
+B2_D u32 coop_lane()
+{
+    return threadIdx.x & 31u;
+}
+
+//! Lane holding the smallest non-negative double among the valid lanes (ties: lowest lane);
+//! 32 if no lane is valid. Two integer warp minima (REDUX) instead of a shuffle tree.
+B2_D u32 coop_argmin(real d, bool valid)
+{
+    constexpr unsigned full = 0xffffffffu;
+    u64 const bits = static_cast<u64>(__double_as_longlong(d));
+    u32 const hi = valid ? static_cast<u32>(bits >> 32) : 0xffffffffu;
+    u32 const min_hi = __reduce_min_sync(full, hi);
+    bool const in_hi = valid && hi == min_hi;
+    u32 const lo = in_hi ? static_cast<u32>(bits) : 0xffffffffu;
+    u32 const min_lo = __reduce_min_sync(full, lo);
+    unsigned const winners = __ballot_sync(full, in_hi && lo == min_lo);
+    return winners ? static_cast<u32>(__ffs(winners) - 1) : 32u;
+}
+
+B2_D real coop_broadcast(real v, u32 lane)
+{
+    return __shfl_sync(0xffffffffu, v, lane);
+}
+
+template<bool COOP>
+B2_D Propagation coop_find_next_step(GeoTrackT<COOP>& t, bool limited, real max_step)
+{
+    GeoParams const& g = t.g;
+    StateView const& s = t.s;
+    u32 const slot = t.slot;
+    if (s.geo_boundary[slot] == 0)
+        return Propagation{0, true, false};  // reentrant: already "at" the next boundary
+
+    u32 const lane = coop_lane();
+    u32 const lev = t.level();
+    // deal the (level, face) items out to the lanes
+    u32 my_level = INVALID, my_item = 0;
+    bool my_whole = false;
+    u32 total = 0;
+    for (u32 l = 0; l <= lev; ++l)
+    {
+        u32 const uid = t.univ(l);
+        u32 count = 1;
+        bool whole = true;
+        if (g.universe_type[uid] == UNIV_SIMPLE)
+        {
+            SimpleUnit const& u = g.simple_units[g.universe_index[uid]];
+            u32 const rec = u.vol_begin + t.vol(l);
+            if (!(g.vol_flags[rec] & (VOL_INTERNAL_SURFACES | VOL_IMPLICIT)))
+            {
+                count = g.vol_face_end[rec] - g.vol_face_begin[rec];
+                whole = false;
+            }
+        }
+        if (lane >= total && lane < total + count)
+        {
+            my_level = l;
+            my_item = lane - total;
+            my_whole = whole;
+        }
+        total += count;
+    }
+    if (total > 32)
+        return t.find_next_step_impl(limited, max_step);
+
+    // one root search per lane
+    real const bound = limited ? max_step : real_inf();
+    real d = real_inf();
+    bool valid = false;
+    u32 w_surface = INVALID;
+    u32 w_sense = 0;
+    if (my_level != INVALID)
+    {
+        LocalState const st = t.local_state(my_level);
+        u32 const uid = t.univ(my_level);
+        if (my_whole)
+        {
+            Intersection const is = (my_level == 0)
+                                        ? univ_intersect(g, uid, st, limited, max_step)
+                                        : univ_intersect(g, uid, st, false, real_inf());
+            d = is.distance;
+            w_surface = is.surface;
+            w_sense = is.sense;
+            valid = is.surface != INVALID && (my_level == 0 || d < bound);
+        }
+        else
+        {
+            SimpleUnit const& u = g.simple_units[g.universe_index[uid]];
+            VolumeRef const vol = get_volume(g, u, st.volume);
+            u32 const on_face
+                = (st.surface != INVALID) ? volume_find_face(g, vol, st.surface) : INVALID;
+            SurfaceRef const sr = get_surface(g, u, volume_surface(g, vol, my_item));
+            bool const on = (my_item == on_face);
+            int const nroots = surface_num_isect(sr.type);
+            if (!(nroots == 1 && on))
+            {
+                Roots const r = surface_intersect(sr, st.pos, st.dir, on);
+                for (int k = 0; k < nroots; ++k)
+                {
+                    real const dk = r.r[k];
+                    bool const ok = (my_level == 0)
+                                        ? (limited ? (dk <= max_step) : (dk < real_max()))
+                                        : (dk < bound);
+                    if (ok && (!valid || dk < d))
+                    {
+                        d = dk;
+                        valid = true;
+                    }
+                }
+            }
+        }
+    }
+    u32 const winner = coop_argmin(d, valid);
+
+    Intersection isect{INVALID, 0, bound};
+    u32 min_level = 0;
+    if (winner < 32)
+    {
+        constexpr unsigned full = 0xffffffffu;
+        isect.distance = coop_broadcast(d, winner);
+        min_level = __shfl_sync(full, my_level, winner);
+        u32 const item = __shfl_sync(full, my_item, winner);
+        bool const whole = __shfl_sync(full, static_cast<int>(my_whole), winner) != 0;
+        u32 const ws = __shfl_sync(full, w_surface, winner);
+        u32 const wn = __shfl_sync(full, w_sense, winner);
+        if (whole)
+        {
+            isect.surface = ws;
+            isect.sense = static_cast<u8>(wn);
+        }
+        else
+        {
+            // surface and current sense of the winning face (every lane, same values)
+            LocalState const st = t.local_state(min_level);
+            SimpleUnit const& u = g.simple_units[g.universe_index[t.univ(min_level)]];
+            VolumeRef const vol = get_volume(g, u, st.volume);
+            u32 const surface = volume_surface(g, vol, item);
+            isect.surface = surface;
+            isect.sense = (surface == st.surface)
+                              ? st.sense
+                              : static_cast<u8>(surface_sense(get_surface(g, u, surface), st.pos)
+                                                >= 0);
+        }
+    }
+    s.geo_next_step[slot] = isect.distance;
+    s.geo_next_surf[slot] = isect.surface;
+    s.geo_next_sense[slot] = isect.sense;
+    if (isect.surface != INVALID)
+        s.geo_next_level[slot] = min_level;
+    return Propagation{isect.distance, isect.surface != INVALID, false};
+}
+
+//! Safety distance over all levels: min over levels of the per-universe safety
+//! (OrangeTrackView::find_safety; SimpleUnitTracker::safety, univ/SimpleUnitTracker.hh)
+template<bool COOP>
+B2_D real coop_find_safety(GeoTrackT<COOP>& t)
+{
+    GeoParams const& g = t.g;
+    u32 const lane = coop_lane();
+    u32 const lev = t.level();
+    u32 my_level = INVALID, my_item = 0;
+    bool my_whole = false;
+    u32 total = 0;
+    for (u32 l = 0; l <= lev; ++l)
+    {
+        u32 const uid = t.univ(l);
+        u32 count = 1;
+        bool whole = true;
+        if (g.universe_type[uid] == UNIV_SIMPLE)
+        {
+            SimpleUnit const& u = g.simple_units[g.universe_index[uid]];
+            u32 const rec = u.vol_begin + t.vol(l);
+            u32 const nf = g.vol_face_end[rec] - g.vol_face_begin[rec];
+            if ((g.vol_flags[rec] & VOL_SIMPLE_SAFETY) && nf > 0)
+            {
+                count = nf;
+                whole = false;
+            }
+        }
+        if (lane >= total && lane < total + count)
+        {
+            my_level = l;
+            my_item = lane - total;
+            my_whole = whole;
+        }
+        total += count;
+    }
+    if (total > 32)
+        return t.find_safety_impl();
+    real d = real_inf();
+    if (my_level != INVALID)
+    {
+        u32 const uid = t.univ(my_level);
+        Real3 const pos = t.pos(my_level);
+        if (my_whole)
+        {
+            d = univ_safety(g, uid, pos, t.vol(my_level));
+        }
+        else
+        {
+            SimpleUnit const& u = g.simple_units[g.universe_index[uid]];
+            VolumeRef const vol = get_volume(g, u, t.vol(my_level));
+            d = surface_safety(get_surface(g, u, volume_surface(g, vol, my_item)), pos);
+        }
+    }
+    // distances are >= 0 or +inf (never NaN: surface_safety maps a NaN normal to +inf)
+    u32 const winner = coop_argmin(d, my_level != INVALID);
+    return winner < 32 ? coop_broadcast(d, winner) : real_inf();
+}
 
 B2_GEO_FN Propagation
 geo_find_next_step(GeoParams const& g, StateView const& s, u32 slot, bool limited, real max_step)

@@ -108,6 +108,14 @@ B2_D u32 thread_id()
     return blockIdx.x * blockDim.x + threadIdx.x;
 }
 
+//! Nanoseconds of the device-wide timer
+B2_D u64 global_timer_ns()
+{
+    u64 t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 //---------------------------------------------------------------------------//
 // The step kernels are bound by the latency of dependent loads of per-slot state
 // (ncu: ~60 % of stall samples are long-scoreboard, spread evenly over ~40 fields;
@@ -205,12 +213,16 @@ B2_D u32 active_slot(StateView const& s, u32 tid)
 // (track/detail/InitTracksExecutor.hh:71-175)
 //---------------------------------------------------------------------------//
 //! Start the tid-th of the num_new = min(num_init, num_vac) tracks that start this step
+//! `vacancy_at(k)` returns the k-th vacant slot in slot order: the sorted vacancy array of
+//! the per-action path, or the per-run prefix search of the device-resident loop (tail.cu)
+template<class VacancyAt>
 B2_D void initialize_track(ParamsView const& p,
                            StateView const& s,
                            u32 tid,
                            u32 num_init,
                            u32 num_vac,
-                           u32 num_new)
+                           u32 num_new,
+                           VacancyAt&& vacancy_at)
 {
     u32 ti = num_init - tid - 1;
     u32 slot;
@@ -228,13 +240,13 @@ B2_D void initialize_track(ParamsView const& p,
         u32 const neutral_rank = s.ti_neutral_prefix[ti] - neutral_before_first;
         bool const is_neutral = p.particle.charge[s.ti_particle_id[ti]] == 0;
         if (is_neutral)
-            slot = s.vacancies[neutral_rank];
+            slot = vacancy_at(neutral_rank);
         else
-            slot = s.vacancies[num_vac - (num_new - num_neutral) + ((ti - first) - neutral_rank)];
+            slot = vacancy_at(num_vac - (num_new - num_neutral) + ((ti - first) - neutral_rank));
     }
     else
     {
-        slot = s.vacancies[num_vac - tid - 1];
+        slot = vacancy_at(num_vac - tid - 1);
     }
 
     // sim
@@ -538,22 +550,21 @@ constexpr u32 DIAG_SMEM_BINS = 1024;
 // caches -- measured floor 213 us per iteration for a single 1 GeV shower, of which the
 // per-action kernels account for ~165 us (profiles/README_r01.md).
 //---------------------------------------------------------------------------//
-template<bool FIELD>
-B2_D void step_fused_track(ParamsView const& p, StateView const& s, u32 tid)
+//! COOP: called by all 32 lanes of a warp with the same `tid` (warp-cooperative navigation,
+//! orange.cuh); everything but the face searches runs redundantly, tallies by lane 0 only.
+template<bool FIELD, bool COOP = false>
+B2_D void step_fused_slot(ParamsView const& p, StateView const& s, u32 slot, bool charged)
 {
-    u32 const slot = active_slot(s, tid);
-    if (slot == INVALID)
-        return;
-    bool const charged = tid < s.counters[CTR_NUM_CHARGED];
+    bool const tally_lane = !COOP || (threadIdx.x & 31u) == 0;
     // pre
     do_pre_step(p, s, slot);
     // along
     if (s.status[slot] == ST_ALIVE)
     {
         if (charged)
-            along_step<true, FIELD>(p, s, slot);
+            along_step<true, FIELD, COOP>(p, s, slot);
         else
-            along_step<false, false>(p, s, slot);
+            along_step<false, false, COOP>(p, s, slot);
     }
     // pre_post, post
     do_discrete_select(p, s, slot);
@@ -561,14 +572,14 @@ B2_D void step_fused_track(ParamsView const& p, StateView const& s, u32 tid)
     do_boundary(p, s, slot);
     do_tracking_cut(p, s, slot);
     u8 const status = s.status[slot];
-    if (s.diag_action_counts && status != ST_INACTIVE)
+    if (tally_lane && s.diag_action_counts && status != ST_INACTIVE)
     {
         atomicAdd(&s.diag_action_counts[s.particle_id[slot] * s.diag_action_bins
                                         + s.post_step_action[slot]],
                   1u);
     }
     // user_post
-    if (s.calo_edep && status != ST_INACTIVE)
+    if (tally_lane && s.calo_edep && status != ST_INACTIVE)
     {
         real edep = s.energy_deposition[slot];
         if (edep != 0)
@@ -578,12 +589,158 @@ B2_D void step_fused_track(ParamsView const& p, StateView const& s, u32 tid)
                 atomicAdd(&s.calo_edep[det], edep);
         }
     }
-    if (s.diag_step_counts && status == ST_KILLED)
+    if (tally_lane && s.diag_step_counts && status == ST_KILLED)
     {
         u32 const nb = s.diag_step_bins;
         u32 const n = s.num_steps[slot];
         atomicAdd(&s.diag_step_counts[s.particle_id[slot] * nb + (n < nb - 1 ? n : nb - 1)], 1u);
     }
+}
+
+template<bool FIELD>
+B2_D void step_fused_track(ParamsView const& p, StateView const& s, u32 tid)
+{
+    u32 const slot = active_slot(s, tid);
+    if (slot == INVALID)
+        return;
+    step_fused_slot<FIELD, false>(p, s, slot, tid < s.counters[CTR_NUM_CHARGED]);
+}
+
+//---------------------------------------------------------------------------//
+// Warp-cooperative step of ONE track (fewer tracks than warps: csrc/tail.cu).
+//
+// All 32 lanes of the warp run the whole step of the same track and share the per-face
+// work of its distance and safety searches (coop_find_next_step, orange.cuh). The lanes
+// are NOT guaranteed to stay in lock-step between those searches, and the step is full of
+// read-modify-write sequences on the track's state (s.num_steps[slot] += 1, the boundary
+// crossing, the RNG words): run on the shared state, a lane that is a few instructions
+// ahead would feed its results to the lanes behind it (measured: tracks crossed a
+// boundary twice). So every lane works on a PRIVATE one-slot copy of the track's state
+// (ShadowSlot, in local memory; the same StateView code runs on it with num_slots = 1,
+// slot = 0) and lane 0 writes the result back. Tallies are atomics on the real arrays, by
+// lane 0 only.
+//---------------------------------------------------------------------------//
+constexpr u32 SHADOW_MAX_DEPTH = 8;
+constexpr u32 SHADOW_MAX_PROCESSES = 8;
+
+struct ShadowSlot
+{
+    real time, step_length, energy, geo_next_step;
+    real geo_pos[3 * SHADOW_MAX_DEPTH], geo_dir[3 * SHADOW_MAX_DEPTH];
+    real interaction_mfp, macro_xs, energy_deposition, dedx_range;
+    real msc_range[3], msc_true_path, msc_geom_path, msc_alpha;
+    real per_process_xs[SHADOW_MAX_PROCESSES];
+    real sec_energy[MAX_SECONDARIES], sec_dir[MAX_SECONDARIES * 3];
+    u32 track_id, parent_id, event_id, num_steps, num_looping_steps;
+    u32 post_step_action, along_step_action, particle_id, material_id;
+    u32 geo_level, geo_surface_level, geo_surf, geo_next_level, geo_next_surf;
+    u32 geo_vol[SHADOW_MAX_DEPTH], geo_univ[SHADOW_MAX_DEPTH];
+    u32 element, sec_particle[MAX_SECONDARIES], rng[6], pre_volume;
+    u8 status, geo_sense, geo_boundary, geo_next_sense, msc_is_displaced;
+};
+
+B2_D bool shadow_supported(StateView const& s)
+{
+    return s.max_depth <= SHADOW_MAX_DEPTH && s.max_processes <= SHADOW_MAX_PROCESSES;
+}
+
+//! The per-slot fields the step reads or writes: X(field, count) with `count` entries of
+//! stride num_slots (level-major / component-major columns)
+#define B2_SHADOW_FIELDS(X, D, P)                                                          \
+    X(time, 1) X(step_length, 1) X(energy, 1) X(geo_next_step, 1) X(geo_pos, 3 * (D))      \
+    X(geo_dir, 3 * (D)) X(interaction_mfp, 1) X(macro_xs, 1) X(energy_deposition, 1)       \
+    X(dedx_range, 1) X(msc_range, 3) X(msc_true_path, 1) X(msc_geom_path, 1)               \
+    X(msc_alpha, 1) X(per_process_xs, (P)) X(sec_energy, MAX_SECONDARIES)                  \
+    X(sec_dir, MAX_SECONDARIES * 3) X(track_id, 1) X(parent_id, 1) X(event_id, 1)          \
+    X(num_steps, 1) X(num_looping_steps, 1) X(post_step_action, 1)                         \
+    X(along_step_action, 1) X(particle_id, 1) X(material_id, 1) X(geo_level, 1)            \
+    X(geo_surface_level, 1) X(geo_surf, 1) X(geo_next_level, 1) X(geo_next_surf, 1)        \
+    X(geo_vol, (D)) X(geo_univ, (D)) X(element, 1) X(sec_particle, MAX_SECONDARIES)        \
+    X(rng, 6) X(status, 1) X(geo_sense, 1) X(geo_boundary, 1) X(geo_next_sense, 1)         \
+    X(msc_is_displaced, 1)
+
+template<class T>
+B2_D T* shadow_ptr(T& x)
+{
+    return &x;
+}
+template<class T, size_t N>
+B2_D T* shadow_ptr(T (&x)[N])
+{
+    return x;
+}
+
+//! View of the private copy: per-slot columns point into `buf`, everything else
+//! (counters, tallies, lists) is the real thing
+B2_D StateView shadow_view(StateView const& s, ShadowSlot& buf)
+{
+    StateView v = s;
+    v.num_slots = 1;
+#define B2_X(field, count) v.field = shadow_ptr(buf.field);
+    B2_SHADOW_FIELDS(B2_X, 0, 0)
+#undef B2_X
+    v.pre_volume = s.pre_volume ? &buf.pre_volume : nullptr;
+    return v;
+}
+
+B2_D void shadow_load(StateView const& s, u32 slot, ShadowSlot& buf)
+{
+    u32 const n = s.num_slots;
+    u32 const D = s.max_depth, P = s.max_processes;
+#define B2_X(field, count)                          \
+    for (u32 i = 0; i < (count); ++i)               \
+        shadow_ptr(buf.field)[i] = s.field[size_t(i) * n + slot];
+    B2_SHADOW_FIELDS(B2_X, D, P)
+#undef B2_X
+    if (s.pre_volume)
+        buf.pre_volume = s.pre_volume[slot];
+}
+
+B2_D void shadow_store(StateView const& s, u32 slot, ShadowSlot const& buf)
+{
+    u32 const n = s.num_slots;
+    u32 const D = s.max_depth, P = s.max_processes;
+#define B2_X(field, count)                          \
+    for (u32 i = 0; i < (count); ++i)               \
+        s.field[size_t(i) * n + slot] = shadow_ptr(const_cast<ShadowSlot&>(buf).field)[i];
+    B2_SHADOW_FIELDS(B2_X, D, P)
+#undef B2_X
+    if (s.pre_volume)
+        s.pre_volume[slot] = buf.pre_volume;
+}
+
+//! Whole step of the tid-th active track by ONE thread on a private copy of its state
+//! (experiment: is it the private copy or the shared searches that makes the cooperative
+//! step faster? see profiles/README_r02.md)
+template<bool FIELD>
+B2_D void step_fused_track_shadow(ParamsView const& p, StateView const& s, u32 tid)
+{
+    u32 const slot = active_slot(s, tid);
+    if (slot == INVALID)
+        return;
+    bool const charged = tid < s.counters[CTR_NUM_CHARGED];
+    ShadowSlot buf;
+    shadow_load(s, slot, buf);
+    StateView const v = shadow_view(s, buf);
+    step_fused_slot<FIELD, false>(p, v, 0, charged);
+    shadow_store(s, slot, buf);
+}
+
+//! Whole step of the tid-th active track by the calling WARP (all 32 lanes)
+template<bool FIELD>
+B2_D void step_fused_track_coop(ParamsView const& p, StateView const& s, u32 tid)
+{
+    u32 const slot = active_slot(s, tid);
+    if (slot == INVALID)
+        return;
+    bool const charged = tid < s.counters[CTR_NUM_CHARGED];
+    ShadowSlot buf;
+    shadow_load(s, slot, buf);
+    StateView const v = shadow_view(s, buf);
+    step_fused_slot<FIELD, true>(p, v, 0, charged);
+    __syncwarp();
+    if ((threadIdx.x & 31u) == 0)
+        shadow_store(s, slot, buf);
 }
 
 
@@ -797,68 +954,43 @@ B2_D void end_pass2_finish(StateView const& s, u32 slot_begin)
 }
 
 
-//! Pass 3 for the 128 slots of (virtual) block `vb` of `nb`, starting at slot_begin
-B2_D void end_pass3_block(ParamsView const& p, StateView const& s, u32 slot_begin, u32 vb, u32 nb)
+//! The reference's pre-step resets the step limit of inactive slots
+//! (PreStepExecutor.hh:47-57); inactive slots are never visited by the dense kernels
+//! here, so it is done once, when the slot is first seen inactive
+B2_D void reset_inactive_slot(StateView const& s, u32 slot)
 {
-    u32 slot = slot_begin + vb * BLOCK + threadIdx.x;
-    // classification of pass 1 (the same launch sequence; nothing changed in between)
-    SlotEnd e = unpack_class(slot < s.num_slots ? s.slot_class[slot] : u8(0));
-    u32 ta, tb;
-    // Everything that does not depend on the scans is loaded BEFORE their barriers, so
-    // that these round trips overlap with the scans instead of queueing up behind them
-    // (the kernel is latency bound: 38 long-scoreboard stall cycles per issue, ncu)
-    u32 const block_vac = s.block_scratch[vb];
-    u32 const block_chg = s.block_scratch[nb + vb];
-    u32 const block_neu = s.block_scratch[2 * nb + vb];
-    u32 const block_sec = s.block_scratch[3 * nb + vb];
-    u32 const block_all = s.block_scratch[4 * nb + vb];
-    u32 const block_neutral_sec = s.block_scratch[5 * nb + vb];
-    u32 const device_error = s.counters[CTR_ERROR];
-    u32 const num_init = s.counters[CTR_NUM_INITIALIZERS];
-    u32 const num_sec_total = s.counters[CTR_NUM_SECONDARIES];
-    u32 event = 0, parent_track = 0;
-    real time = 0;
-    if (e.num_sec_all > 0)
+    if (s.post_step_action[slot] != INVALID || s.along_step_action[slot] != INVALID)
     {
-        event = s.event_id[slot];
-        parent_track = s.track_id[slot];
-        time = s.time[slot];
+        s.step_length[slot] = real_inf();
+        s.post_step_action[slot] = INVALID;
+        s.along_step_action[slot] = INVALID;
     }
-    u32 sa = block_exclusive_scan<BLOCK, u32>(
-        e.is_vacant | (e.charged << 10) | (e.neutral << 20), &ta);
-    u32 sb = block_exclusive_scan<BLOCK, u32>(pack_secondaries(e), &tb);
-    // vacancies[i] = i for the (all vacant) slots below slot_begin
-    u32 vac_off = slot_begin + (sa & 0x3ffu) + block_vac;
-    u32 chg_off = ((sa >> 10) & 0x3ffu) + block_chg;
-    u32 neu_off = ((sa >> 20) & 0x3ffu) + block_neu;
-    u32 sec_off = (sb & 0x3ffu) + block_sec;
-    u32 all_off = ((sb >> 10) & 0x3ffu) + block_all;
-    // neutral initializers created by lower slots in this step (init_charge only)
-    u32 neutral_off = ((sb >> 20) & 0x3ffu) + block_neutral_sec;
-    if (slot >= s.num_slots)
-        return;
-    if (device_error != 0)
-        return;
-    if (e.is_vacant)
-        s.vacancies[vac_off] = slot;
+}
+
+//! End of step for one slot that was NOT inactive during the step: dense-list entry,
+//! secondaries -> initializers (or in-place reuse of a dead parent's slot), killed ->
+//! inactive. The offsets are the slot's exclusive prefix sums in slot order. Returns whether
+//! the slot became inactive (its step limit is reset when it is next seen inactive).
+B2_D bool end_slot_active(ParamsView const& p,
+                          StateView const& s,
+                          u32 slot,
+                          SlotEnd const& e,
+                          u32 chg_off,
+                          u32 neu_off,
+                          u32 sec_off,
+                          u32 all_off,
+                          u32 neutral_off,
+                          u32 num_init,
+                          u32 num_sec_total,
+                          u32 event,
+                          u32 parent_track,
+                          real time)
+{
     if (e.charged)
         s.track_slots[chg_off] = slot;
     if (e.neutral)
         s.track_slots[s.num_slots - 1 - neu_off] = slot;
 
-    if (e.inactive)
-    {
-        // The reference's pre-step resets the step limit of inactive slots
-        // (PreStepExecutor.hh:47-57); inactive slots are never visited by the dense
-        // kernels here, so do it once, when the slot is first seen inactive
-        if (s.post_step_action[slot] != INVALID || s.along_step_action[slot] != INVALID)
-        {
-            s.step_length[slot] = real_inf();
-            s.post_step_action[slot] = INVALID;
-            s.along_step_action[slot] = INVALID;
-        }
-        return;
-    }
 
     // Initializers created this step occupy [num_init - num_sec, num_init)
     // in slot order (exclusive scan of the per-slot counts)
@@ -966,9 +1098,77 @@ B2_D void end_pass3_block(ParamsView const& p, StateView const& s, u32 slot_begi
     }
     // a vacant slot that is not yet inactive holds a killed track
     if (!initialized && e.is_vacant && s.status[slot] == ST_KILLED)
+    {
         s.status[slot] = ST_INACTIVE;
+        return true;
+    }
+    return false;
 }
 
+//! Pass 3 for the 128 slots of (virtual) block `vb` of `nb`, starting at slot_begin
+B2_D void end_pass3_block(ParamsView const& p, StateView const& s, u32 slot_begin, u32 vb, u32 nb)
+{
+    u32 slot = slot_begin + vb * BLOCK + threadIdx.x;
+    // classification of pass 1 (the same launch sequence; nothing changed in between)
+    SlotEnd e = unpack_class(slot < s.num_slots ? s.slot_class[slot] : u8(0));
+    u32 ta, tb;
+    // Everything that does not depend on the scans is loaded BEFORE their barriers, so
+    // that these round trips overlap with the scans instead of queueing up behind them
+    // (the kernel is latency bound: 38 long-scoreboard stall cycles per issue, ncu)
+    u32 const block_vac = s.block_scratch[vb];
+    u32 const block_chg = s.block_scratch[nb + vb];
+    u32 const block_neu = s.block_scratch[2 * nb + vb];
+    u32 const block_sec = s.block_scratch[3 * nb + vb];
+    u32 const block_all = s.block_scratch[4 * nb + vb];
+    u32 const block_neutral_sec = s.block_scratch[5 * nb + vb];
+    u32 const device_error = s.counters[CTR_ERROR];
+    u32 const num_init = s.counters[CTR_NUM_INITIALIZERS];
+    u32 const num_sec_total = s.counters[CTR_NUM_SECONDARIES];
+    u32 event = 0, parent_track = 0;
+    real time = 0;
+    if (e.num_sec_all > 0)
+    {
+        event = s.event_id[slot];
+        parent_track = s.track_id[slot];
+        time = s.time[slot];
+    }
+    u32 sa = block_exclusive_scan<BLOCK, u32>(
+        e.is_vacant | (e.charged << 10) | (e.neutral << 20), &ta);
+    u32 sb = block_exclusive_scan<BLOCK, u32>(pack_secondaries(e), &tb);
+    // vacancies[i] = i for the (all vacant) slots below slot_begin
+    u32 vac_off = slot_begin + (sa & 0x3ffu) + block_vac;
+    u32 chg_off = ((sa >> 10) & 0x3ffu) + block_chg;
+    u32 neu_off = ((sa >> 20) & 0x3ffu) + block_neu;
+    u32 sec_off = (sb & 0x3ffu) + block_sec;
+    u32 all_off = ((sb >> 10) & 0x3ffu) + block_all;
+    // neutral initializers created by lower slots in this step (init_charge only)
+    u32 neutral_off = ((sb >> 20) & 0x3ffu) + block_neutral_sec;
+    if (slot >= s.num_slots)
+        return;
+    if (device_error != 0)
+        return;
+    if (e.is_vacant)
+        s.vacancies[vac_off] = slot;
+    if (e.inactive)
+    {
+        reset_inactive_slot(s, slot);
+        return;
+    }
+    end_slot_active(p,
+                    s,
+                    slot,
+                    e,
+                    chg_off,
+                    neu_off,
+                    sec_off,
+                    all_off,
+                    neutral_off,
+                    num_init,
+                    num_sec_total,
+                    event,
+                    parent_track,
+                    time);
+}
 
 //---------------------------------------------------------------------------//
 // reseed (random/RngReseed.cu:29-74)

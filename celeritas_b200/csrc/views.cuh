@@ -569,6 +569,13 @@ struct StateView
     // tracks take the highest vacancies first, so the busy slots cluster at the top.
     u32 slot_begin;
 
+    // Device-resident step loop (tail.cu): runs of 32 consecutive slots
+    u32* run_vac_prefix;     // [num_slots / 32 + 1] vacancies below each run
+    u32* run_vac_mask;       // [num_slots / 32] bit i: slot 32 * run + i is vacant
+    u64* run_scan;           // [2 * num_slots / 32] per-run exclusive prefixes inside a super-block
+    u32* tail_reset_list;    // [2][num_slots] slots that became inactive (ping-pong)
+    u32* tail_ctrl;          // [2] entries in each reset list
+
     // Interacting tracks of the current step sorted by model (null: interactions run
     // over the whole active list). Filled by the discrete-select launch.
     u32* interact_list;   // [model][slot]

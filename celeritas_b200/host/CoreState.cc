@@ -3,6 +3,8 @@
 //---------------------------------------------------------------------------//
 #include "CoreState.hh"
 
+#include "../../include/celeritas_b200.h"
+
 #include <atomic>
 #include <cstring>
 #include <numeric>
@@ -142,6 +144,30 @@ CoreState::CoreState(std::shared_ptr<CoreParams const> params,
         s.interact_list = arena_.alloc<u32>(size_t(p.phys.num_models) * n);
         s.interact_count = arena_.alloc<u32>(16);
     }
+    // Device-resident step loop (csrc/tail.cu); needs whole runs of 32 slots
+    if (n % 32 == 0)
+    {
+        uint32_t const nruns = n / 32;
+        s.run_vac_prefix = arena_.alloc<u32>(size_t(nruns) + 1);
+        s.run_vac_mask = arena_.alloc<u32>(nruns);
+        s.run_scan = arena_.alloc<u64>(size_t(2) * nruns);
+        s.tail_reset_list = arena_.alloc<u32>(size_t(2) * n);
+        s.tail_ctrl = arena_.alloc<u32>(2);
+        size_t const ring_bytes
+            = size_t(tail_ring_capacity) * B200_TAIL_RING_WORDS * sizeof(uint32_t);
+        B2_CUDA_CALL(cudaHostAlloc(
+            reinterpret_cast<void**>(&h_tail_ring_), ring_bytes, cudaHostAllocMapped));
+        B2_CUDA_CALL(cudaHostAlloc(reinterpret_cast<void**>(&h_tail_done_),
+                                   2 * sizeof(uint32_t),
+                                   cudaHostAllocMapped));
+        std::memset(h_tail_ring_, 0, ring_bytes);
+        std::memset(h_tail_done_, 0, 2 * sizeof(uint32_t));
+        void* mapped = nullptr;
+        B2_CUDA_CALL(cudaHostGetDevicePointer(&mapped, h_tail_ring_, 0));
+        d_tail_ring_ = static_cast<uint32_t*>(mapped);
+        B2_CUDA_CALL(cudaHostGetDevicePointer(&mapped, h_tail_done_, 0));
+        d_tail_done_ = static_cast<uint32_t*>(mapped);
+    }
     B2_CUDA_CALL(cudaHostAlloc(reinterpret_cast<void**>(&h_counters_),
                                (CTR_SIZE + 1) * sizeof(uint32_t),
                                cudaHostAllocMapped));
@@ -158,6 +184,10 @@ CoreState::~CoreState()
 {
     if (h_counters_)
         cudaFreeHost(h_counters_);
+    if (h_tail_ring_)
+        cudaFreeHost(h_tail_ring_);
+    if (h_tail_done_)
+        cudaFreeHost(h_tail_done_);
     if (stream_)
         cudaStreamDestroy(stream_);
 }
@@ -200,6 +230,23 @@ CoreStateCounters CoreState::wait_counters()
     }
     std::atomic_thread_fence(std::memory_order_acquire);
     return this->unpack_counters();
+}
+
+CoreStateCounters CoreState::unpack_tail_entry(uint32_t index)
+{
+    uint32_t const* e = h_tail_ring_ + size_t(index) * B200_TAIL_RING_WORDS;
+    CoreStateCounters c;
+    c.num_generated = e[0];
+    c.num_initializers = e[1];
+    c.num_vacancies = e[2];
+    c.num_active = e[3];
+    c.num_secondaries = e[4];
+    c.num_alive = e[5];
+    c.num_charged = e[6];
+    c.num_neutral = e[7];
+    c.first_busy_block = e[8];
+    last_error_ = e[9];
+    return c;
 }
 
 CoreStateCounters CoreState::unpack_counters()

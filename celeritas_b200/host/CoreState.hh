@@ -89,6 +89,17 @@ class CoreState
 
     size_t device_bytes() const { return arena_.bytes(); }
 
+    //!@{
+    //! Device-resident step loop (csrc/tail.cu): mapped host ring of per-iteration counters
+    static constexpr uint32_t tail_ring_capacity = 1024;
+    uint32_t* tail_ring_device() const { return d_tail_ring_; }
+    uint32_t* tail_done_device() const { return d_tail_done_; }
+    uint32_t const* tail_ring_host() const { return h_tail_ring_; }
+    uint32_t volatile* tail_done_host() const { return h_tail_done_; }
+    //! Counters of one ring entry, as sync_counters() would have returned them
+    CoreStateCounters unpack_tail_entry(uint32_t index);
+    //!@}
+
   private:
     std::shared_ptr<CoreParams const> params_;
     uint32_t stream_id_;
@@ -96,6 +107,10 @@ class CoreState
     DeviceArena arena_;
     b200::StateView view_{};
     uint32_t* h_counters_{nullptr};  // pinned, mapped: [CTR_SIZE + 1]
+    uint32_t* h_tail_ring_{nullptr};  // pinned, mapped: [tail_ring_capacity][RING_WORDS]
+    uint32_t* h_tail_done_{nullptr};  // pinned, mapped: [2]
+    uint32_t* d_tail_ring_{nullptr};
+    uint32_t* d_tail_done_{nullptr};
     uint32_t iteration_seq_{0};
     CoreStateCounters unpack_counters();
     uint32_t last_error_{0};

@@ -4,6 +4,8 @@
 #include "Stepper.hh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <set>
@@ -233,6 +235,12 @@ ActionSequence::ActionSequence(CoreParams const& params, Options options)
         fuse_threshold_ = static_cast<uint32_t>(std::strtoul(env, nullptr, 10));
     if (fuse_threshold_ == 0xffffffffu)
         fusable_ = false;
+    // The device-resident loop runs the same fused step: same precondition
+    tail_threshold_ = options.tail_threshold ? options.tail_threshold : default_tail_threshold;
+    if (char const* env = std::getenv("B200_TAIL_THRESHOLD"))
+        tail_threshold_ = static_cast<uint32_t>(std::strtoul(env, nullptr, 10));
+    if (tail_threshold_ == 0xffffffffu || !fusable_)
+        tail_threshold_ = 0;
 
     // The run [geo-boundary, tracking-cut, action-diagnostic?, tally?, step-diagnostic?] of
     // consecutive built-in actions is one launch (b200_step_post_tail) when nothing else
@@ -493,16 +501,9 @@ void Stepper::step_async()
     actions_->step(*params_, state);
 }
 
-StepperResult Stepper::operator()()
+StepperResult Stepper::finish_iteration(CoreStateCounters const& c)
 {
-    this->step_async();
-    // With per-action timing the event pairs must have completed: full synchronisation.
-    // Otherwise take the counters as soon as the end-of-step scan has published them.
-    CoreStateCounters c = (actions_->action_times() || std::getenv("B200_FULL_SYNC"))
-                              ? state_->sync_counters()
-                              : state_->wait_counters();
     last_ = c;
-    actions_->collect_times();
     if (uint32_t err = state_->last_device_error())
     {
         if (err == B200_ERR_INITIALIZER_CAPACITY)
@@ -522,6 +523,152 @@ StepperResult Stepper::operator()()
         state_->single_event(INVALID);
     }
     return r;
+}
+
+StepperResult Stepper::operator()()
+{
+    this->step_async();
+    // With per-action timing the event pairs must have completed: full synchronisation.
+    // Otherwise take the counters as soon as the end-of-step scan has published them.
+    CoreStateCounters c = (actions_->action_times() || std::getenv("B200_FULL_SYNC"))
+                              ? state_->sync_counters()
+                              : state_->wait_counters();
+    actions_->collect_times();
+    return this->finish_iteration(c);
+}
+
+//---------------------------------------------------------------------------//
+// Device-resident loop (csrc/tail.cu)
+//---------------------------------------------------------------------------//
+bool Stepper::tail_eligible() const
+{
+    uint32_t const threshold = actions_->tail_threshold();
+    if (threshold == 0 || actions_->action_times() || staging_->count != 0)
+        return false;
+    if (!state_->tail_ring_device())
+        return false;
+    if (last_.num_alive == 0 && last_.num_initializers == 0)
+        return false;
+    // tracks in the next iteration: the ones alive plus the queued ones that find a slot
+    uint64_t const next_active
+        = uint64_t(last_.num_alive) + std::min(last_.num_initializers, last_.num_vacancies);
+    return next_active <= threshold;
+}
+
+uint32_t Stepper::run_tail(uint32_t max_iterations,
+                           std::vector<StepperResult>* results,
+                           std::vector<double>* seconds)
+{
+    using Clock = std::chrono::steady_clock;
+    CoreState& state = *state_;
+    if (tail_blocks_ == 0)
+    {
+        int max_blocks = 0;
+        check_rc(b200_tail_max_blocks(pv(*params_), &max_blocks), "tail_max_blocks");
+        int device = 0, sms = 0;
+        B2_CUDA_CALL(cudaGetDevice(&device));
+        B2_CUDA_CALL(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        // One block on every other SM by default: the loop is latency bound (a few tracks),
+        // and while it is resident a second stream's kernels keep the rest of the GPU
+        // (measured with two streams, profiles/README_r02.md: CMS-scale pass 379 ms without
+        // the loop, 381 ms with 148 blocks, 352 ms with 74, 354 ms with 32)
+        int blocks = std::min(max_blocks, std::max(1, sms / 2));
+        if (char const* env = std::getenv("B200_TAIL_BLOCKS"))
+            blocks = std::min<int>(max_blocks, std::max<int>(1, std::atoi(env)));
+        if (blocks <= 0)
+            throw std::runtime_error("the device-resident loop does not fit on this device");
+        tail_blocks_ = static_cast<uint32_t>(blocks);
+    }
+    uint32_t const chunk = std::min<uint32_t>(max_iterations, CoreState::tail_ring_capacity);
+    uint32_t const exit_active
+        = std::min<uint64_t>(uint64_t(2) * actions_->tail_threshold(), state.size());
+    uint32_t volatile* done = state.tail_done_host();
+    done[0] = 0xffffffffu;
+    done[1] = 0xffffffffu;
+    auto const start = Clock::now();
+    check_rc(b200_step_tail_loop(pv(*params_),
+                                 sv(state),
+                                 tail_blocks_,
+                                 chunk,
+                                 exit_active,
+                                 state.tail_ring_device(),
+                                 state.tail_done_device(),
+                                 state.stream()),
+             "step_tail_loop");
+    B2_CUDA_CALL(cudaStreamSynchronize(state.stream()));
+    double const elapsed = std::chrono::duration<double>(Clock::now() - start).count();
+    uint32_t const n = done[0];
+    if (n == 0xffffffffu)
+        throw std::runtime_error("the device-resident loop did not report back");
+    ++tail_launches_;
+    tail_iterations_ += n;
+    uint32_t const* ring = state.tail_ring_host();
+    auto stamp = [ring](uint32_t i) {
+        uint32_t const* e = ring + size_t(i) * B200_TAIL_RING_WORDS;
+        return uint64_t(e[10]) | (uint64_t(e[11]) << 32);
+    };
+    if (char const* dump = std::getenv("B200_TAIL_DUMP"))
+    {
+        // phase durations of every iteration (profiling aid): active, A, B, C1, C2 [ns]
+        if (FILE* f = std::fopen(dump, "a"))
+        {
+            for (uint32_t i = 0; i < n; ++i)
+            {
+                uint32_t const* e = ring + size_t(i) * B200_TAIL_RING_WORDS;
+                uint64_t total = i > 0 ? stamp(i) - stamp(i - 1) : 0;
+                std::fprintf(f, "%u %u %u %u %u %llu\n", e[3], e[12], e[13], e[14], e[15],
+                             static_cast<unsigned long long>(total));
+            }
+            std::fclose(f);
+        }
+    }
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        CoreStateCounters c = state.unpack_tail_entry(i);
+        results->push_back(this->finish_iteration(c));
+        if (seconds)
+        {
+            // device timer between consecutive end-of-step scans; the first iteration gets
+            // what is left of the launch's host-side duration
+            double dt = i > 0 ? double(stamp(i) - stamp(i - 1)) * 1e-9
+                              : std::max(0.0, elapsed - double(stamp(n - 1) - stamp(0)) * 1e-9);
+            seconds->push_back(dt);
+        }
+    }
+    return n;
+}
+
+uint32_t Stepper::advance(uint32_t max_iterations,
+                          std::vector<StepperResult>* results,
+                          std::vector<double>* seconds)
+{
+    using Clock = std::chrono::steady_clock;
+    if (!results)
+        throw std::runtime_error("advance needs a result vector");
+    uint32_t done = 0;
+    while (done < max_iterations)
+    {
+        if (this->tail_eligible())
+        {
+            uint32_t const n = this->run_tail(max_iterations - done, results, seconds);
+            done += n;
+            if (n > 0)
+            {
+                if (!results->back())
+                    break;
+                continue;
+            }
+        }
+        auto const start = Clock::now();
+        StepperResult r = (*this)();
+        results->push_back(r);
+        if (seconds)
+            seconds->push_back(std::chrono::duration<double>(Clock::now() - start).count());
+        ++done;
+        if (!r)
+            break;
+    }
+    return done;
 }
 
 StepperResult Stepper::operator()(B200Primary const* primaries, uint32_t n)

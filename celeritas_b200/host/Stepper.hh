@@ -71,7 +71,14 @@ class ActionSequence
         //! Iterations with at most this many active tracks run pre..user_post as one
         //! fused launch (0: default, 0xffffffff: never)
         uint32_t fuse_threshold{0};
+        //! Stepper::advance runs iterations with at most this many active tracks inside
+        //! the device-resident loop (0: default, 0xffffffff: never)
+        uint32_t tail_threshold{0};
     };
+    //! Default of Options::tail_threshold
+    //! (measured, profiles/README_r02.md: above a few hundred tracks the loop's end of step
+    //! costs what the host round trip does)
+    static constexpr uint32_t default_tail_threshold = 256;
     //! Default of Options::fuse_threshold (measured: profiles/README_r01.md)
     static constexpr uint32_t default_fuse_threshold = 65536;
     //! Build the B200 adapters for every step action in the problem's table
@@ -88,6 +95,8 @@ class ActionSequence
     //! Whether small iterations can take the fused path, and up to how many tracks
     bool fusable() const { return fusable_; }
     uint32_t fuse_threshold() const { return fuse_threshold_; }
+    //! Active-track bound of the device-resident loop (0: the loop is off)
+    uint32_t tail_threshold() const { return tail_threshold_; }
 
     //! Per-action device timing with CUDA events on the state's stream
     //! (reference option: StepperInput::action_times, ActionSequence.cc:99-121)
@@ -105,6 +114,7 @@ class ActionSequence
     bool action_times_{false};
     bool fusable_{false};
     uint32_t fuse_threshold_{0};
+    uint32_t tail_threshold_{0};
     size_t tail_begin_{0}, tail_end_{0};  // [begin, end) of the boundary..diagnostics run
     size_t along_select_{0};  // index of the along-step action when the select follows it
     std::vector<double> accum_time_;
@@ -154,6 +164,18 @@ class Stepper
     CoreState& state() { return *state_; }
     CoreParams const& params() const { return *params_; }
 
+    //! Up to `max_iterations` iterations without new primaries, stopping early when no track
+    //! is left: Stepper::operator()() repeated. While few tracks are left the iterations run
+    //! inside the device-resident loop (b200_step_tail_loop: no host round trip between
+    //! them); results and state are the same either way. Appends one StepperResult (and,
+    //! if asked, one duration in seconds) per iteration; returns the number taken.
+    uint32_t advance(uint32_t max_iterations,
+                     std::vector<StepperResult>* results,
+                     std::vector<double>* seconds = nullptr);
+    //! Iterations taken inside the device-resident loop / launches of it so far
+    uint64_t tail_iterations() const { return tail_iterations_; }
+    uint64_t tail_launches() const { return tail_launches_; }
+
     //! Enqueue one iteration without reading anything back
     void step_async();
     //! Stage primaries for the next iteration (host buffers)
@@ -169,5 +191,14 @@ class Stepper
     std::unique_ptr<Staging> staging_;
     std::set<uint32_t> events_in_flight_;
     CoreStateCounters last_{};  // counters at the end of the previous iteration
+    uint32_t tail_blocks_{0};   // cooperative grid of the device-resident loop (0: unknown)
+    uint64_t tail_iterations_{0};
+    uint64_t tail_launches_{0};
+
+    bool tail_eligible() const;
+    uint32_t run_tail(uint32_t max_iterations,
+                      std::vector<StepperResult>* results,
+                      std::vector<double>* seconds);
+    StepperResult finish_iteration(CoreStateCounters const& c);
 };
 }  // namespace celeritas_b200

@@ -20,8 +20,7 @@ TransporterResult Transporter::operator()(B200Primary const* primaries, uint32_t
     using Clock = std::chrono::steady_clock;
     TransporterResult result;
     Stepper& step = *stepper_;
-    auto last_time = Clock::now();
-    auto append = [&](StepperResult const& c) {
+    auto append = [&](StepperResult const& c, double seconds) {
         if (input_.store_track_counts)
         {
             result.generated.push_back(c.generated);
@@ -30,28 +29,41 @@ TransporterResult Transporter::operator()(B200Primary const* primaries, uint32_t
             result.alive.push_back(c.alive);
         }
         if (input_.store_step_times)
-        {
-            auto now = Clock::now();
-            result.step_times.push_back(std::chrono::duration<double>(now - last_time).count());
-            last_time = now;
-        }
+            result.step_times.push_back(seconds);
         ++result.num_step_iterations;
         result.num_steps += c.active;
         result.max_queued = std::max<uint64_t>(result.max_queued, c.queued);
     };
 
     uint64_t remaining_steps = input_.max_steps;
+    auto const start = Clock::now();
     StepperResult counts = step(primaries, n);
-    append(counts);
+    append(counts, std::chrono::duration<double>(Clock::now() - start).count());
+    std::vector<StepperResult> batch;
+    std::vector<double> batch_seconds;
     while (counts)
     {
-        if (input_.max_steps != 0 && --remaining_steps == 0)
+        // The reference's loop, `if (max_steps && --remaining_steps == 0) break;` before
+        // every further iteration: at most remaining_steps - 1 more may run
+        if (input_.max_steps != 0 && remaining_steps <= 1)
         {
             // Exceeded the step count: abort the transport loop
             break;
         }
-        counts = step();
-        append(counts);
+        uint64_t const budget = input_.max_steps != 0 ? remaining_steps - 1 : 0xffffffffull;
+        batch.clear();
+        batch_seconds.clear();
+        // Stepper::advance is operator()() repeated; iterations with few tracks run inside
+        // the device-resident loop, without a host round trip in between
+        uint32_t const taken
+            = step.advance(static_cast<uint32_t>(std::min<uint64_t>(budget, 0xffffffffull)),
+                           &batch,
+                           input_.store_step_times ? &batch_seconds : nullptr);
+        if (input_.max_steps != 0)
+            remaining_steps -= taken;
+        for (uint32_t i = 0; i < taken; ++i)
+            append(batch[i], input_.store_step_times ? batch_seconds[i] : 0.0);
+        counts = batch.back();
     }
     result.num_tracks = step.state().num_tracks();
     result.num_aborted = uint64_t(counts.alive) + counts.queued;

@@ -208,6 +208,7 @@ int b200_stepper_create_opts(B200Params const* params,
         inp.actions.action_diagnostic = options->action_diagnostic != 0;
         inp.actions.step_diagnostic_bins = options->step_diagnostic_bins;
         inp.actions.fuse_threshold = options->fuse_threshold;
+        inp.actions.tail_threshold = options->tail_threshold;
         s->stepper = std::make_shared<Stepper>(std::move(inp));
         s->state_handle.state = &s->stepper->state();
         s->launches_at_create = b200_launch_count();
@@ -287,6 +288,33 @@ int b200_stepper_step(B200Stepper* stepper,
             result->alive = r.alive;
         }
     });
+}
+
+int b200_stepper_advance(B200Stepper* stepper,
+                         uint32_t max_iterations,
+                         B200StepperResult* results,
+                         uint32_t* num_done)
+{
+    if (!stepper || !results || !num_done)
+        return B200_ERR_INVALID_ARGUMENT;
+    *num_done = 0;
+    return guarded([&] {
+        std::vector<StepperResult> batch;
+        uint32_t const n = stepper->stepper->advance(max_iterations, &batch);
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            results[i].generated = batch[i].generated;
+            results[i].queued = batch[i].queued;
+            results[i].active = batch[i].active;
+            results[i].alive = batch[i].alive;
+        }
+        *num_done = n;
+    });
+}
+
+uint64_t b200_stepper_tail_iterations(B200Stepper const* stepper)
+{
+    return stepper->stepper->tail_iterations();
 }
 
 int b200_stepper_warm_up(B200Stepper* stepper)

@@ -37,7 +37,8 @@ class RunResult(C.Structure):
 class StepperOptions(C.Structure):
     _fields_ = [('stream_id', C.c_uint32), ('num_track_slots', C.c_uint32),
                 ('action_times', C.c_int), ('action_diagnostic', C.c_int),
-                ('step_diagnostic_bins', C.c_uint32), ('fuse_threshold', C.c_uint32)]
+                ('step_diagnostic_bins', C.c_uint32), ('fuse_threshold', C.c_uint32),
+                ('tail_threshold', C.c_uint32)]
 
 
 # Every symbol declared in include/celeritas_b200.h
@@ -64,7 +65,8 @@ EXPORTS = [
     'b200_primaries_generate', 'b200_celer_sim_run', 'b200_string_free',
     'b200_params_num_particles', 'b200_run_events_streams', 'b200_step_fused',
     'b200_step_post_tail', 'b200_step_along_select', 'b200_params_num_models', 'b200_params_model_action_begin',
-    'b200_params_max_depth',
+    'b200_params_max_depth', 'b200_step_tail_loop', 'b200_tail_max_blocks',
+    'b200_stepper_advance', 'b200_stepper_tail_iterations',
 ]
 
 _lib = None
@@ -133,6 +135,10 @@ def load_library():
     L.b200_stepper_num_step_actions.restype = C.c_uint32
     L.b200_stepper_step_action_label.argtypes = [vp, C.c_uint32]
     L.b200_stepper_step_action_label.restype = C.c_char_p
+    L.b200_stepper_advance.argtypes = [vp, C.c_uint32, C.POINTER(StepperResult),
+                                       C.POINTER(C.c_uint32)]
+    L.b200_stepper_tail_iterations.argtypes = [vp]
+    L.b200_stepper_tail_iterations.restype = C.c_uint64
     L.b200_stepper_launch_count.argtypes = [vp]
     L.b200_stepper_launch_count.restype = C.c_uint64
     L.b200_stepper_set_action_times.argtypes = [vp, C.c_int]
@@ -274,13 +280,15 @@ class Stepper:
     """One stream's stepping loop (reference: Stepper<MemSpace::device>)."""
 
     def __init__(self, params, num_track_slots, stream_id=0, action_times=False,
-                 action_diagnostic=False, step_diagnostic_bins=0, fuse_threshold=0):
+                 action_diagnostic=False, step_diagnostic_bins=0, fuse_threshold=0,
+                 tail_threshold=0):
         L = load_library()
         self.params = params
         self.n = num_track_slots
         h = C.c_void_p()
         opts = StepperOptions(stream_id, num_track_slots, int(action_times),
-                              int(action_diagnostic), step_diagnostic_bins, fuse_threshold)
+                              int(action_diagnostic), step_diagnostic_bins, fuse_threshold,
+                              tail_threshold)
         _check(L.b200_stepper_create_opts(params.h, C.byref(opts), C.byref(h)))
         self.h = h
 
@@ -326,6 +334,20 @@ class Stepper:
         else:
             _check(L.b200_stepper_step(self.h, None, 0, C.byref(r)))
         return dict(generated=r.generated, queued=r.queued, active=r.active, alive=r.alive)
+
+    def advance(self, max_iterations):
+        """Up to max_iterations iterations without primaries (device-resident loop while few
+        tracks are left); returns the list of per-iteration counts."""
+        L = load_library()
+        res = (StepperResult * max_iterations)()
+        n = C.c_uint32()
+        _check(L.b200_stepper_advance(self.h, max_iterations, res, C.byref(n)))
+        return [dict(generated=r.generated, queued=r.queued, active=r.active, alive=r.alive)
+                for r in res[:n.value]]
+
+    @property
+    def tail_iterations(self):
+        return int(load_library().b200_stepper_tail_iterations(self.h))
 
     def warm_up(self):
         _check(load_library().b200_stepper_warm_up(self.h))

@@ -100,6 +100,10 @@ typedef struct B200StepperOptions
     /* Iterations with at most this many active tracks run pre-step..tally as one fused
      * launch (b200_step_fused). 0: library default; 0xffffffff: never fuse. */
     uint32_t fuse_threshold;
+    /* b200_stepper_advance and b200_run_events run iterations with at most this many active
+     * tracks inside the device-resident loop (b200_step_tail_loop). 0: library default;
+     * 0xffffffff: never (one host round trip per iteration, as the reference). */
+    uint32_t tail_threshold;
 } B200StepperOptions;
 
 /* Opaque views holding device pointers (layout: celeritas_b200/csrc/views.cuh). */
@@ -180,6 +184,33 @@ int b200_step_post_tail(B200ParamsView const*, B200StateView const*, cudaStream_
 int b200_step_along_select(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_step_action_diagnostic(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_step_step_diagnostic(B200ParamsView const*, B200StateView const*, cudaStream_t);
+/* Device-resident step loop for small iterations: up to `max_iterations` WHOLE step
+ * iterations (start tracks, the fused step, extend-from-secondaries) in ONE cooperative
+ * launch of `num_blocks` blocks, i.e. Stepper::operator() (global/Stepper.cc:124-140)
+ * repeated without returning to the host. The loop leaves when no track is left, when the
+ * next iteration could hold more than `exit_active` tracks, on a device error, or after
+ * max_iterations. `ring` ([max_iterations][B200_TAIL_RING_WORDS]) and `done` ([2]) are
+ * device pointers to MAPPED HOST memory: the counters of every iteration (generated,
+ * initializers, vacancies, active, secondaries, alive, charged, neutral, first busy block,
+ * error, device timer lo/hi) and {iterations done, exit reason (B200TailExit)}. */
+#define B200_TAIL_RING_WORDS 16
+typedef enum B200TailExit
+{
+    B200_TAIL_EXIT_DONE = 0,
+    B200_TAIL_EXIT_MAX_ITERATIONS = 1,
+    B200_TAIL_EXIT_TOO_MANY = 2,
+    B200_TAIL_EXIT_ERROR = 3
+} B200TailExit;
+int b200_step_tail_loop(B200ParamsView const*,
+                        B200StateView const*,
+                        uint32_t num_blocks,
+                        uint32_t max_iterations,
+                        uint32_t exit_active,
+                        uint32_t* ring,
+                        uint32_t* done,
+                        cudaStream_t);
+/* Largest grid of the loop's kernel that is resident at once on the current device */
+int b200_tail_max_blocks(B200ParamsView const*, int* num_blocks);
 int b200_reseed(B200ParamsView const*, B200StateView const*, uint64_t event_id, cudaStream_t);
 int b200_reset_generated(B200StateView const*, cudaStream_t);
 int b200_kill_active(B200ParamsView const*, B200StateView const*, cudaStream_t);
@@ -241,6 +272,17 @@ int b200_stepper_step(B200Stepper* stepper,
                       B200Primary const* primaries,
                       uint32_t num_primaries,
                       B200StepperResult* result);
+/* Up to `max_iterations` step iterations without primaries. While few tracks are left
+ * they run inside the device-resident loop (b200_step_tail_loop), otherwise one by one as
+ * b200_stepper_step does; either way results[i] is iteration i's StepperResult and the
+ * state afterwards is the same. Stops early when no track is left. *num_done <=
+ * max_iterations iterations were taken. */
+int b200_stepper_advance(B200Stepper* stepper,
+                         uint32_t max_iterations,
+                         B200StepperResult* results,
+                         uint32_t* num_done);
+/* Iterations that ran inside the device-resident loop since the stepper was created */
+uint64_t b200_stepper_tail_iterations(B200Stepper const* stepper);
 int b200_stepper_warm_up(B200Stepper* stepper);
 int b200_stepper_reseed(B200Stepper* stepper, uint64_t event_id);
 int b200_stepper_kill_active(B200Stepper* stepper);
