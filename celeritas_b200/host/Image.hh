@@ -120,49 +120,62 @@ class Image
 
     std::map<std::string, ImageEntry> const& entries() const { return entries_; }
 
+    //! The image as one contiguous byte string (the file layout above)
+    std::vector<unsigned char> serialize() const
+    {
+        std::vector<unsigned char> out;
+        auto wr = [&out](void const* src, size_t n) {
+            auto const* b = static_cast<unsigned char const*>(src);
+            out.insert(out.end(), b, b + n);
+        };
+        wr(magic(), 8);
+        uint32_t n = entries_.size();
+        wr(&n, 4);
+        for (auto const& kv : entries_)
+        {
+            uint32_t len = kv.first.size();
+            wr(&len, 4);
+            wr(kv.first.data(), len);
+            uint32_t dt = static_cast<uint32_t>(kv.second.dtype);
+            wr(&dt, 4);
+            wr(&kv.second.count, 8);
+            wr(kv.second.bytes.data(), kv.second.bytes.size());
+            static char const zeros[8] = {0};
+            wr(zeros, (8 - kv.second.bytes.size() % 8) % 8);
+        }
+        return out;
+    }
+
     void write(std::string const& path) const
     {
         FILE* f = std::fopen(path.c_str(), "wb");
         if (!f)
             throw std::runtime_error("cannot open '" + path + "' for writing");
-        std::fwrite(magic(), 1, 8, f);
-        uint32_t n = entries_.size();
-        std::fwrite(&n, 4, 1, f);
-        for (auto const& kv : entries_)
-        {
-            uint32_t len = kv.first.size();
-            std::fwrite(&len, 4, 1, f);
-            std::fwrite(kv.first.data(), 1, len, f);
-            uint32_t dt = static_cast<uint32_t>(kv.second.dtype);
-            std::fwrite(&dt, 4, 1, f);
-            std::fwrite(&kv.second.count, 8, 1, f);
-            std::fwrite(kv.second.bytes.data(), 1, kv.second.bytes.size(), f);
-            static char const zeros[8] = {0};
-            size_t pad = (8 - kv.second.bytes.size() % 8) % 8;
-            std::fwrite(zeros, 1, pad, f);
-        }
+        std::vector<unsigned char> const bytes = this->serialize();
+        size_t const written = std::fwrite(bytes.data(), 1, bytes.size(), f);
         std::fclose(f);
+        if (written != bytes.size())
+            throw std::runtime_error("short write to '" + path + "'");
     }
 
-    static Image read(std::string const& path)
+    //! Parse an image held in memory (`what` names it in error messages)
+    static Image parse(void const* data, size_t size, std::string const& what = "image in memory")
     {
-        FILE* f = std::fopen(path.c_str(), "rb");
-        if (!f)
-            throw std::runtime_error("cannot open image '" + path + "'");
+        auto const* cur = static_cast<unsigned char const*>(data);
+        auto const* const end = cur + size;
         auto rd = [&](void* dst, size_t n) {
-            if (n && std::fread(dst, 1, n, f) != n)
-            {
-                std::fclose(f);
-                throw std::runtime_error("truncated image '" + path + "'");
-            }
+            if (n > static_cast<size_t>(end - cur))
+                throw std::runtime_error("truncated image '" + what + "'");
+            if (n)
+                std::memcpy(dst, cur, n);
+            cur += n;
         };
+        if (!data)
+            throw std::runtime_error("null image");
         char m[8];
         rd(m, 8);
         if (std::memcmp(m, magic(), 8) != 0)
-        {
-            std::fclose(f);
-            throw std::runtime_error("'" + path + "' is not a B2IMG v1 file");
-        }
+            throw std::runtime_error("'" + what + "' is not a B2IMG v1 file");
         uint32_t n;
         rd(&n, 4);
         Image img;
@@ -170,6 +183,8 @@ class Image
         {
             uint32_t len;
             rd(&len, 4);
+            if (len > static_cast<size_t>(end - cur))
+                throw std::runtime_error("truncated image '" + what + "'");
             std::string name(len, '\0');
             rd(&name[0], len);
             uint32_t dt;
@@ -177,14 +192,30 @@ class Image
             ImageEntry e;
             e.dtype = static_cast<DType>(dt);
             rd(&e.count, 8);
-            e.bytes.resize(e.count * dtype_size(e.dtype));
+            size_t const esize = dtype_size(e.dtype);
+            if (e.count > static_cast<size_t>(end - cur) / esize)
+                throw std::runtime_error("truncated image '" + what + "'");
+            e.bytes.resize(e.count * esize);
             rd(e.bytes.data(), e.bytes.size());
             char pad[8];
             rd(pad, (8 - e.bytes.size() % 8) % 8);
             img.entries_[name] = std::move(e);
         }
-        std::fclose(f);
         return img;
+    }
+
+    static Image read(std::string const& path)
+    {
+        FILE* f = std::fopen(path.c_str(), "rb");
+        if (!f)
+            throw std::runtime_error("cannot open image '" + path + "'");
+        std::vector<unsigned char> bytes;
+        unsigned char buf[1 << 16];
+        size_t got;
+        while ((got = std::fread(buf, 1, sizeof(buf), f)) > 0)
+            bytes.insert(bytes.end(), buf, buf + got);
+        std::fclose(f);
+        return parse(bytes.data(), bytes.size(), path);
     }
 
   private:

@@ -447,6 +447,12 @@ void Stepper::insert(B200Primary const* primaries, uint32_t n)
 
 void Stepper::step_async()
 {
+    this->begin_iteration();
+    actions_->step(*params_, *state_);
+}
+
+void Stepper::begin_iteration()
+{
     CoreState& state = *state_;
     cudaStream_t stream = state.stream();
     Staging& st = *staging_;
@@ -498,7 +504,11 @@ void Stepper::step_async()
                  "extend_from_primaries");
         st.count = 0;
     }
-    actions_->step(*params_, state);
+}
+
+StepperResult Stepper::end_iteration()
+{
+    return this->finish_iteration(state_->wait_counters());
 }
 
 StepperResult Stepper::finish_iteration(CoreStateCounters const& c)

@@ -181,6 +181,17 @@ class Stepper
     //! Stage primaries for the next iteration (host buffers)
     void insert(B200Primary const* primaries, uint32_t n);
 
+    //!@{
+    //! One iteration driven by an EXTERNAL action sequence (the reference's own
+    //! ActionSequence calling one b200_step_* launcher per action):
+    //! begin_iteration sizes the iteration's grids from the previous counters and moves
+    //! staged primaries into the initializer queue (extend-from-primaries); the caller then
+    //! launches the step actions on state().stream(); end_iteration waits for the counters
+    //! that extend-from-secondaries publishes and returns the iteration's result.
+    void begin_iteration();
+    StepperResult end_iteration();
+    //!@}
+
   private:
     std::shared_ptr<CoreParams const> params_;
     std::shared_ptr<ActionSequence> actions_;

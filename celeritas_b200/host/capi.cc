@@ -86,6 +86,23 @@ int b200_params_create_from_image(char const* image_path, B200Params** out)
     });
 }
 
+int b200_params_create_from_memory(void const* image, size_t size, B200Params** out)
+{
+    if (!image || !out)
+        return B200_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (b200_device_count() == 0)
+    {
+        g_error = "no CUDA device available (this library has no CPU path)";
+        return B200_ERR_NO_DEVICE;
+    }
+    return guarded([&] {
+        auto p = std::make_unique<B200Params>();
+        p->params = CoreParams::from_image(b200::Image::parse(image, size));
+        *out = p.release();
+    });
+}
+
 void b200_params_destroy(B200Params* params)
 {
     delete params;
@@ -288,6 +305,41 @@ int b200_stepper_step(B200Stepper* stepper,
             result->alive = r.alive;
         }
     });
+}
+
+int b200_stepper_insert(B200Stepper* stepper, B200Primary const* primaries, uint32_t num_primaries)
+{
+    if (!stepper || (num_primaries && !primaries))
+        return B200_ERR_INVALID_ARGUMENT;
+    return guarded([&] { stepper->stepper->insert(primaries, num_primaries); });
+}
+
+int b200_stepper_begin_iteration(B200Stepper* stepper)
+{
+    if (!stepper)
+        return B200_ERR_INVALID_ARGUMENT;
+    return guarded([&] { stepper->stepper->begin_iteration(); });
+}
+
+int b200_stepper_end_iteration(B200Stepper* stepper, B200StepperResult* result)
+{
+    if (!stepper)
+        return B200_ERR_INVALID_ARGUMENT;
+    return guarded([&] {
+        StepperResult r = stepper->stepper->end_iteration();
+        if (result)
+        {
+            result->generated = r.generated;
+            result->queued = r.queued;
+            result->active = r.active;
+            result->alive = r.alive;
+        }
+    });
+}
+
+cudaStream_t b200_stepper_stream(B200Stepper* stepper)
+{
+    return stepper ? stepper->stepper->state().stream() : nullptr;
 }
 
 int b200_stepper_advance(B200Stepper* stepper,

@@ -67,6 +67,8 @@ EXPORTS = [
     'b200_step_post_tail', 'b200_step_along_select', 'b200_params_num_models', 'b200_params_model_action_begin',
     'b200_params_max_depth', 'b200_step_tail_loop', 'b200_tail_max_blocks',
     'b200_stepper_advance', 'b200_stepper_tail_iterations',
+    'b200_params_create_from_memory', 'b200_stepper_insert', 'b200_stepper_begin_iteration',
+    'b200_stepper_end_iteration', 'b200_stepper_stream',
 ]
 
 _lib = None
@@ -92,7 +94,13 @@ def load_library():
     L.b200_last_error.restype = C.c_char_p
     L.b200_device_count.restype = C.c_int
     L.b200_params_create_from_image.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.b200_params_create_from_memory.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(vp)]
     L.b200_params_destroy.argtypes = [vp]
+    L.b200_stepper_insert.argtypes = [vp, vp, C.c_uint32]
+    L.b200_stepper_begin_iteration.argtypes = [vp]
+    L.b200_stepper_end_iteration.argtypes = [vp, C.POINTER(StepperResult)]
+    L.b200_stepper_stream.argtypes = [vp]
+    L.b200_stepper_stream.restype = vp
     L.b200_params_view.restype = vp
     L.b200_params_view.argtypes = [vp]
     L.b200_params_num_actions.argtypes = [vp]
@@ -200,10 +208,15 @@ FIELDS = {
 class Params:
     """Problem parameters in HBM (reference: CoreParams)."""
 
-    def __init__(self, image_path):
+    def __init__(self, image_path=None, image_bytes=None):
         L = load_library()
         h = C.c_void_p()
-        _check(L.b200_params_create_from_image(os.fspath(image_path).encode(), C.byref(h)))
+        if image_bytes is not None:
+            # hand-off in memory (b200_params_create_from_memory)
+            buf = bytes(image_bytes)
+            _check(L.b200_params_create_from_memory(buf, C.c_size_t(len(buf)), C.byref(h)))
+        else:
+            _check(L.b200_params_create_from_image(os.fspath(image_path).encode(), C.byref(h)))
         self.h = h
         self.image_path = image_path
 

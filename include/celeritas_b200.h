@@ -120,6 +120,10 @@ int b200_device_count(void);
 /*--- problem parameters ---------------------------------------------------*/
 /* Load a flattened problem image (celeritas_b200/host/Image.hh) into HBM. */
 int b200_params_create_from_image(char const* image_path, B200Params** out);
+/* The same from an image held in host memory (Image::serialize): the hand-off from a live
+ * CoreParams::host_ref() on the reference side (src/celeritas/global/CoreParams.hh:155-172)
+ * without a file in between; the bytes are not referenced after the call returns. */
+int b200_params_create_from_memory(void const* image, size_t size, B200Params** out);
 void b200_params_destroy(B200Params* params);
 B200ParamsView const* b200_params_view(B200Params const* params);
 /* Problem metadata */
@@ -281,6 +285,18 @@ int b200_stepper_advance(B200Stepper* stepper,
                          uint32_t max_iterations,
                          B200StepperResult* results,
                          uint32_t* num_done);
+/* One iteration driven by an EXTERNAL action sequence: the reference's own ActionSequence
+ * (src/celeritas/global/ActionSequence.cc:77-138) calling one adapter per action
+ * (celeritas_b200/adapter/B200Actions.cc). insert = ExtendFromPrimariesAction::insert
+ * (track/ExtendFromPrimariesAction.cc:103-131), stages host primaries; begin_iteration sizes
+ * the iteration's launches from the previous counters and runs extend-from-primaries; the
+ * caller then calls the b200_step_* launchers with b200_stepper_state()'s view on
+ * b200_stepper_stream(); end_iteration (after b200_step_extend_from_secondaries) returns the
+ * iteration's counters as soon as the device has published them. */
+int b200_stepper_insert(B200Stepper* stepper, B200Primary const* primaries, uint32_t num_primaries);
+int b200_stepper_begin_iteration(B200Stepper* stepper);
+int b200_stepper_end_iteration(B200Stepper* stepper, B200StepperResult* result);
+cudaStream_t b200_stepper_stream(B200Stepper* stepper);
 /* Iterations that ran inside the device-resident loop since the stepper was created */
 uint64_t b200_stepper_tail_iterations(B200Stepper const* stepper);
 int b200_stepper_warm_up(B200Stepper* stepper);

@@ -777,7 +777,24 @@ void export_models(Problem const& prob, b200::Image& img)
 }  // namespace
 
 //---------------------------------------------------------------------------//
+namespace
+{
+b200::Image build_image(Problem const& prob);
+}
+
 void export_image(Problem const& prob, std::string const& path)
+{
+    build_image(prob).write(path);
+}
+
+std::vector<unsigned char> export_image_bytes(Problem const& prob)
+{
+    return build_image(prob).serialize();
+}
+
+namespace
+{
+b200::Image build_image(Problem const& prob)
 {
     b200::Image img;
     img.put_string("config", prob.config.dump());
@@ -790,8 +807,7 @@ void export_image(Problem const& prob, std::string const& path)
         for (auto v : range(VolumeId{prob.geo->volumes().size()}))
             labels += prob.geo->volumes().at(v).name + "\n";
         img.put_string("geo.volume_labels", labels);
-        img.write(path);
-        return;
+        return img;
     }
     CoreParams const& core = *prob.core;
     auto const& ref = core.host_ref();
@@ -929,6 +945,7 @@ void export_image(Problem const& prob, std::string const& path)
         img.put_string("calo.volumes", names);
     }
 
-    img.write(path);
+    return img;
 }
+}  // namespace
 }  // namespace celerref

@@ -56,4 +56,6 @@ std::unique_ptr<Problem> build_problem(nlohmann::json const& config);
 
 // Write the flattened problem image consumed by the B200 loader
 void export_image(Problem const& p, std::string const& path);
+// The same image as one byte string (b200_params_create_from_memory)
+std::vector<unsigned char> export_image_bytes(Problem const& p);
 }  // namespace celerref

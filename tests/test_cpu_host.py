@@ -171,3 +171,27 @@ def test_cms_scale_geometry_is_reproducible():
     # every material-bearing volume of the geometry is named in the physics file
     phys = json.load(open(os.path.join(REPO, 'data', 'physics', 'cms-scale-steel-lar.json')))
     assert {v['name'] for v in phys['volumes']} == set(mats)
+
+
+def test_compiled_dropin_uses_only_the_declared_cabi():
+    """oracle/_ref/libcelerref_dropin.so (the adapter classes of celeritas_b200/adapter compiled
+    against the reference's headers) reaches the B200 library through symbols that
+    include/celeritas_b200.h declares and nothing else; and from memory, not through a file."""
+    lib = os.path.join(REPO, 'oracle', '_ref', 'libcelerref_dropin.so')
+    if not os.path.exists(lib):
+        pytest.skip('drop-in not built (make -C oracle dropin needs /root/reference)')
+    out = subprocess.run(['nm', '-D', '--undefined-only', lib], capture_output=True, text=True,
+                         check=True).stdout
+    used = set(re.findall(r'\bU (b200_[a-z0-9_]+)', out))
+    header = open(os.path.join(REPO, 'include', 'celeritas_b200.h')).read()
+    declared = set(re.findall(r'\b(b200_[a-z0-9_]+)\s*\(', header))
+    assert used and used <= declared, used - declared
+    assert 'b200_params_create_from_memory' in used
+    assert 'b200_params_create_from_image' not in used
+    for launcher in ('b200_step_pre_step', 'b200_step_along_step', 'b200_step_interact',
+                     'b200_step_extend_from_secondaries', 'b200_stepper_begin_iteration'):
+        assert launcher in used
+    # and it is the reference's interfaces it implements
+    out = subprocess.run(['nm', '-DC', lib], capture_output=True, text=True, check=True).stdout
+    assert 'celeritas::ActionSequence::step' in out
+    assert 'celeritas_b200_adapter::B200StepAction' in out
