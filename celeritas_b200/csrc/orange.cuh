@@ -15,12 +15,29 @@
 //---------------------------------------------------------------------------//
 #pragma once
 
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+
 #include "views.cuh"
 
 namespace b200
 {
+// Volumes with at most this many faces AND intersections take the register path: face senses
+// in one u32, candidate intersections in small per-thread arrays.
 constexpr int ORANGE_MAX_FACES = 32;
 constexpr int ORANGE_MAX_ISECT = 32;
+// Larger volumes (background volumes whose faces are all the surfaces of their unit, CMS-scale
+// mother volumes with hundreds of faces) take the "big volume" path below: no per-thread
+// arrays sized by the face count, only the sense words (1 bit per face). The reference sizes
+// per-track global scratch from max_faces / max_intersections at run time
+// (orange/OrangeData.hh:348-544, OrangeTrackView.hh:1042-1067); here the only limit is:
+constexpr int ORANGE_BIG_MAX_FACES = 4096;
+constexpr int ORANGE_BIG_SENSE_WORDS = ORANGE_BIG_MAX_FACES / 32;
+// Lanes of a warp that reach the big-volume search together share the work (1) or every lane
+// searches on its own (0: measurement knob, same results)
+#ifndef B2_ORANGE_BIG_COOP
+#    define B2_ORANGE_BIG_COOP 1
+#endif
 
 struct Propagation
 {
@@ -517,6 +534,93 @@ B2_D u32 calc_senses(GeoParams const& g,
     return senses;
 }
 
+//! RPN logic over face senses held as words (bit f of word f / 32: face f is outside)
+B2_D bool eval_logic_words(GeoParams const& g, VolumeRef const& v, u32 const* words)
+{
+    u32 stack = 0;
+    for (u32 i = v.logic_begin; i < v.logic_end; ++i)
+    {
+        u32 tok = g.logic_ints[i];
+        if (tok < LOGIC_BEGIN)
+        {
+            stack = (stack << 1) | ((words[tok >> 5] >> (tok & 31u)) & 1u);
+        }
+        else if (tok == LOGIC_TRUE)
+        {
+            stack = (stack << 1) | 1u;
+        }
+        else if (tok == LOGIC_OR)
+        {
+            stack = (stack >> 1) | (stack & 1u);
+        }
+        else if (tok == LOGIC_AND)
+        {
+            u32 t = stack & 1u;
+            stack = (stack >> 1) & (t | ~u32(1));
+        }
+        else if (tok == LOGIC_NOT)
+        {
+            stack ^= 1u;
+        }
+    }
+    return stack & 1u;
+}
+
+//! Point-in-volume test for a volume of any size (SenseCalculator + LogicEvaluator). `face`
+//! names a face whose sense is known (or INVALID) and receives the first face found to be
+//! exactly "on"; `probe` (or INVALID) is a face whose sense is returned in `probe_sense`.
+B2_NOINLINE inline bool volume_contains_big(GeoParams const& g,
+                                            SimpleUnit const& u,
+                                            VolumeRef const& v,
+                                            Real3 const& pos,
+                                            OnFace& face,
+                                            u32 probe,
+                                            u8& probe_sense)
+{
+    u32 words[ORANGE_BIG_SENSE_WORDS];
+    u32 const nwords = (v.num_faces + 31u) >> 5;
+    for (u32 w = 0; w < nwords; ++w)
+        words[w] = 0;
+    for (u32 f = 0; f < v.num_faces; ++f)
+    {
+        u32 cur;
+        if (f != face.face)
+        {
+            int ss = surface_sense(get_surface(g, u, volume_surface(g, v, f)), pos);
+            cur = ss >= 0;
+            if (face.face == INVALID && ss == 0)
+            {
+                face.face = f;
+                face.sense = cur;
+            }
+        }
+        else
+        {
+            cur = face.sense;
+        }
+        words[f >> 5] |= cur << (f & 31u);
+    }
+    if (probe != INVALID)
+        probe_sense = (words[probe >> 5] >> (probe & 31u)) & 1u;
+    return eval_logic_words(g, v, words);
+}
+
+//! Point-in-volume test, any volume size
+B2_D bool volume_contains(GeoParams const& g,
+                          SimpleUnit const& u,
+                          VolumeRef const& v,
+                          Real3 const& pos,
+                          OnFace& face)
+{
+    if (v.num_faces <= u32(ORANGE_MAX_FACES))
+    {
+        u32 senses = calc_senses(g, u, v, pos, face);
+        return eval_logic(g, v, senses);
+    }
+    u8 unused = 0;
+    return volume_contains_big(g, u, v, pos, face, INVALID, unused);
+}
+
 //---------------------------------------------------------------------------//
 // BIH TRAVERSAL (reference detail/BIHTraverser.hh:103-295)
 //---------------------------------------------------------------------------//
@@ -627,9 +731,9 @@ B2_D Initialization unit_initialize(GeoParams const& g, SimpleUnit const& u, Rea
     auto is_inside = [&](u32 id) -> bool {
         VolumeRef vol = get_volume(g, u, id);
         OnFace face{INVALID, 0};
-        u32 senses = calc_senses(g, u, vol, pos, face);
+        bool const inside = volume_contains(g, u, vol, pos, face);
         on_surface = (face.face != INVALID);
-        return eval_logic(g, vol, senses);
+        return inside;
     };
     u32 id = bih_find_volume(g, u, pos, is_inside);
     if (on_surface)
@@ -648,8 +752,7 @@ B2_D Initialization unit_cross_boundary(GeoParams const& g, SimpleUnit const& u,
             return false;
         VolumeRef vol = get_volume(g, u, id);
         OnFace face{volume_find_face(g, vol, st.surface), st.sense};
-        u32 senses = calc_senses(g, u, vol, st.pos, face);
-        if (eval_logic(g, vol, senses))
+        if (volume_contains(g, u, vol, st.pos, face))
         {
             on_surf = (face.face != INVALID) ? volume_surface(g, vol, face.face) : INVALID;
             on_sense = face.sense;
@@ -677,6 +780,245 @@ B2_D Initialization unit_cross_boundary(GeoParams const& g, SimpleUnit const& u,
     return Initialization{u.background, st.surface, st.sense};
 }
 
+//---------------------------------------------------------------------------//
+// BIG VOLUMES: WARP-COOPERATIVE DISTANCE SEARCH
+//
+// SimpleUnitTracker::intersect_impl (univ/SimpleUnitTracker.hh:390-455) fills per-track
+// scratch arrays with every valid intersection of every face, sorts them by distance, and
+// walks them in order (complex_intersect :506-560, background_intersect :585-640). For a
+// volume with hundreds of faces that is hundreds of dependent quadric solves in one thread
+// plus a sort through global memory. Here the lanes of a warp that arrive at the search
+// together (any subset: cooperative_groups::coalesced_threads) serve one another's tracks in
+// turn: for each track the group deals the FACES out to its lanes (face f -> lane f mod n),
+// every lane solves its faces, and the group reduces to the next crossing in
+// (distance, face, root) order. The ordered walk of the reference becomes "extract the next
+// minimum, strictly after the previous one": no intersection array, no sort, no scratch
+// memory; a walk normally ends after one or two crossings. Sense words are built the same
+// way (one OR-reduction per 32 faces), and a background volume's neighbour tests are dealt
+// out by neighbour. Results do not depend on which lanes happen to cooperate: every
+// per-face value is computed by the same instruction sequence, the reductions are exact
+// integer minima, and ties are broken by (face, root), the order of the reference's
+// intersection array.
+//---------------------------------------------------------------------------//
+namespace cg = cooperative_groups;
+
+//! A group of one lane: the same search without cooperation
+struct SoloGroup
+{
+    B2_D u32 size() const { return 1; }
+    B2_D u32 thread_rank() const { return 0; }
+};
+B2_D u64 group_min(SoloGroup const&, u64 v) { return v; }
+B2_D u32 group_min(SoloGroup const&, u32 v) { return v; }
+B2_D u32 group_or(SoloGroup const&, u32 v) { return v; }
+B2_D u64 group_min(cg::coalesced_group const& grp, u64 v)
+{
+    return cg::reduce(grp, v, cg::less<u64>());
+}
+B2_D u32 group_min(cg::coalesced_group const& grp, u32 v)
+{
+    return cg::reduce(grp, v, cg::less<u32>());
+}
+B2_D u32 group_or(cg::coalesced_group const& grp, u32 v)
+{
+    return cg::reduce(grp, v, cg::bit_or<u32>());
+}
+
+//! One track's search by all lanes of `grp` (every argument is uniform over the group)
+template<class Group>
+B2_D Intersection big_volume_search(Group const& grp,
+                                    GeoParams const& g,
+                                    SimpleUnit const& u,
+                                    LocalState const& st,
+                                    bool limited,
+                                    real max_dist)
+{
+    u32 const n = grp.size();
+    u32 const rank = grp.thread_rank();
+    VolumeRef const vol = get_volume(g, u, st.volume);
+    u32 const on_face = (st.surface != INVALID) ? volume_find_face(g, vol, st.surface) : INVALID;
+    constexpr u64 none = ~u64(0);
+
+    // Next valid crossing strictly after (prev_bits, prev_key) in (distance, face, root)
+    // order. Valid distances are positive, so their bit patterns order like the doubles.
+    auto next_crossing = [&](u64 prev_bits, u32 prev_key, u64& out_bits, u32& out_key) {
+        u64 best_bits = none;
+        u32 best_key = INVALID;
+        for (u32 f = rank; f < vol.num_faces; f += n)
+        {
+            SurfaceRef const sr = get_surface(g, u, volume_surface(g, vol, f));
+            bool const on = (f == on_face);
+            int const nroots = surface_num_isect(sr.type);
+            if (nroots == 1 && on)
+                continue;
+            Roots const r = surface_intersect(sr, st.pos, st.dir, on);
+            for (int k = 0; k < nroots; ++k)
+            {
+                real const d = r.r[k];
+                bool const valid = limited ? (d <= max_dist) : (d < real_max());
+                if (!valid)
+                    continue;
+                u64 const bits = static_cast<u64>(__double_as_longlong(d));
+                u32 const key = 2u * f + u32(k);
+                bool const after = bits > prev_bits || (bits == prev_bits && key > prev_key);
+                bool const better = bits < best_bits || (bits == best_bits && key < best_key);
+                if (after && better)
+                {
+                    best_bits = bits;
+                    best_key = key;
+                }
+            }
+        }
+        out_bits = group_min(grp, best_bits);
+        out_key = group_min(grp, best_bits == out_bits ? best_key : INVALID);
+        return out_bits != none;
+    };
+
+    Intersection result{INVALID, 0, real_inf()};
+    u64 bits = 0;
+    u32 key = 0;
+    if (!(vol.flags & (VOL_INTERNAL_SURFACES | VOL_IMPLICIT)))
+    {
+        // simple_intersect: the nearest crossing leaves the volume
+        if (next_crossing(0, 0, bits, key))
+        {
+            u32 const surface = volume_surface(g, vol, key >> 1);
+            result.surface = surface;
+            result.sense = (surface == st.surface)
+                               ? st.sense
+                               : static_cast<u8>(surface_sense(get_surface(g, u, surface), st.pos)
+                                                 >= 0);
+            result.distance = __longlong_as_double(static_cast<long long>(bits));
+        }
+    }
+    else if (vol.flags & VOL_INTERNAL_SURFACES)
+    {
+        // complex_intersect: cross surfaces in order until the logic says "outside"
+        u32 words[ORANGE_BIG_SENSE_WORDS];
+        u32 const nwords = (vol.num_faces + 31u) >> 5;
+        for (u32 w = 0; w < nwords; ++w)
+        {
+            u32 mine = 0;
+            u32 const end = (32u * w + 32u < vol.num_faces) ? 32u * w + 32u : vol.num_faces;
+            for (u32 f = 32u * w + rank; f < end; f += n)
+            {
+                u32 const cur
+                    = (f == on_face)
+                          ? u32(st.sense)
+                          : u32(surface_sense(get_surface(g, u, volume_surface(g, vol, f)), st.pos)
+                                >= 0);
+                mine |= cur << (f & 31u);
+            }
+            words[w] = group_or(grp, mine);
+        }
+        while (next_crossing(bits, key, bits, key))
+        {
+            u32 const f = key >> 1;
+            words[f >> 5] ^= 1u << (f & 31u);
+            u32 const new_sense = (words[f >> 5] >> (f & 31u)) & 1u;
+            if (!eval_logic_words(g, vol, words))
+            {
+                result.surface = volume_surface(g, vol, f);
+                result.sense = static_cast<u8>(new_sense ^ 1u);
+                result.distance = __longlong_as_double(static_cast<long long>(bits));
+                break;
+            }
+        }
+    }
+    else
+    {
+        // background_intersect: the first crossing that enters a neighbouring volume
+        real bump = g.tol_abs;
+        for (int ax = 0; ax < 3; ++ax)
+        {
+            real t = g.tol_rel * fabs(st.pos[ax]);
+            bump = t > bump ? t : bump;
+        }
+        while (result.surface == INVALID && next_crossing(bits, key, bits, key))
+        {
+            real const dist = __longlong_as_double(static_cast<long long>(bits));
+            u32 const surface = volume_surface(g, vol, key >> 1);
+            Real3 pos = st.pos;
+            axpy(dist + bump, st.dir, pos);
+            u32 const conn = u.conn_begin + surface;
+            u32 const nb = g.conn_begin[conn], ne = g.conn_end[conn];
+            // neighbours dealt out to the lanes; the first one (in connectivity order)
+            // that contains the bumped point wins
+            u32 found = INVALID;
+            for (u32 i = nb + rank; i < ne && found == INVALID; i += n)
+            {
+                u32 const vid = g.local_volume_ids[i];
+                VolumeRef const nv = get_volume(g, u, vid);
+                u32 const nf = volume_find_face(g, nv, surface);
+                OnFace face{INVALID, 0};
+                u8 sense = 0;
+                bool inside;
+                if (nv.num_faces <= u32(ORANGE_MAX_FACES))
+                {
+                    u32 const senses = calc_senses(g, u, nv, pos, face);
+                    sense = (senses >> nf) & 1u;
+                    inside = eval_logic(g, nv, senses);
+                }
+                else
+                {
+                    inside = volume_contains_big(g, u, nv, pos, face, nf, sense);
+                }
+                if (inside)
+                    found = ((i - nb) << 1) | u32(sense);
+            }
+            found = group_min(grp, found);
+            if (found != INVALID)
+            {
+                result.distance = dist;
+                result.surface = surface;
+                result.sense = static_cast<u8>((found & 1u) ^ 1u);
+            }
+        }
+    }
+    if (limited && result.surface == INVALID)
+        result.distance = max_dist;
+    return result;
+}
+
+//! Distance to boundary in a volume too large for the register path. Out of line: the step
+//! kernels' register budgets are set by the small-volume path.
+B2_NOINLINE inline Intersection unit_intersect_big(GeoParams const& g,
+                                                   SimpleUnit const& u,
+                                                   LocalState const& st,
+                                                   bool limited,
+                                                   real max_dist)
+{
+#if B2_ORANGE_BIG_COOP
+    // Every lane that is here right now has a big-volume search of its own to do: do them
+    // one after the other, all lanes together
+    cg::coalesced_group const grp = cg::coalesced_threads();
+    u32 const my_unit = static_cast<u32>(&u - g.simple_units);
+    Intersection mine{INVALID, 0, real_inf()};
+    for (u32 leader = 0; leader < grp.size(); ++leader)
+    {
+        LocalState q;
+        for (int k = 0; k < 3; ++k)
+        {
+            q.pos[k] = grp.shfl(st.pos[k], leader);
+            q.dir[k] = grp.shfl(st.dir[k], leader);
+        }
+        q.volume = grp.shfl(st.volume, leader);
+        q.surface = grp.shfl(st.surface, leader);
+        q.sense = static_cast<u8>(grp.shfl(u32(st.sense), leader));
+        u32 const q_unit = grp.shfl(my_unit, leader);
+        bool const q_limited = grp.shfl(u32(limited), leader) != 0;
+        real const q_max = grp.shfl(max_dist, leader);
+        Intersection const r
+            = big_volume_search(grp, g, g.simple_units[q_unit], q, q_limited, q_max);
+        if (grp.thread_rank() == leader)
+            mine = r;
+    }
+    return mine;
+#else
+    return big_volume_search(SoloGroup{}, g, u, st, limited, max_dist);
+#endif
+}
+
 //! Distance to the boundary of the current volume. max_dist < 0 = unlimited.
 B2_D Intersection unit_intersect(GeoParams const& g,
                                  SimpleUnit const& u,
@@ -685,6 +1027,8 @@ B2_D Intersection unit_intersect(GeoParams const& g,
                                  real max_dist)
 {
     VolumeRef vol = get_volume(g, u, st.volume);
+    if (vol.num_faces > u32(ORANGE_MAX_FACES) || vol.max_isect > u32(ORANGE_MAX_ISECT))
+        return unit_intersect_big(g, u, st, limited, max_dist);
     u32 on_face = (st.surface != INVALID) ? volume_find_face(g, vol, st.surface) : INVALID;
     bool const simple = !(vol.flags & (VOL_INTERNAL_SURFACES | VOL_IMPLICIT));
 

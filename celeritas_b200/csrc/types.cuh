@@ -105,6 +105,14 @@ enum TrackOrder : u32
 {
     ORDER_NONE = 0,
     ORDER_INIT_CHARGE = 1,
+    ORDER_REINDEX_SHUFFLE = 2,  // not supported (a libstdc++ std::shuffle of the slot map)
+    // reindex_*: SortTracksAction (track/SortTracksAction.cc:46-131) keeps a permutation of
+    // all track slots sorted by a key, see csrc/kernels_sort.cu
+    ORDER_REINDEX_STATUS = 3,
+    ORDER_REINDEX_PARTICLE_TYPE = 4,
+    ORDER_REINDEX_ALONG_STEP_ACTION = 5,
+    ORDER_REINDEX_STEP_LIMIT_ACTION = 6,
+    ORDER_REINDEX_BOTH_ACTION = 7,
     ORDER_SIZE_
 };
 

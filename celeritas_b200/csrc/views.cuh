@@ -576,6 +576,15 @@ struct StateView
     u32* tail_reset_list;    // [2][num_slots] slots that became inactive (ping-pong)
     u32* tail_ctrl;          // [2] entries in each reset list
 
+    // TrackOrder::reindex_* (SortTracksAction): permutation of ALL track slots sorted by the
+    // order's key (null for the other orders), rebuilt by every sort action, and the first
+    // index of every key: keys are action ids (num_sort_keys = number of actions), particle
+    // ids, or 0 = active / 1 = inactive; slots without a key (inactive) sort last
+    u32* sort_slots;         // [slot]
+    u32* sort_offsets;       // [num_sort_keys + 2]
+    u32* sort_block_counts;  // [num_sort_keys + 1][sort blocks]
+    u32 num_sort_keys;
+
     // Interacting tracks of the current step sorted by model (null: interactions run
     // over the whole active list). Filled by the discrete-select launch.
     u32* interact_list;   // [model][slot]

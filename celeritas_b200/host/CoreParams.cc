@@ -113,7 +113,7 @@ void CoreParams::load(Image const& img)
         init_capacity_ = init.at(0);
         max_events_ = init.at(1);
         view_.scalars.track_order = init.at(2);
-        if (init.at(2) >= ORDER_SIZE_)
+        if (init.at(2) >= ORDER_SIZE_ || init.at(2) == ORDER_REINDEX_SHUFFLE)
             throw std::runtime_error("unsupported track_order in image");
     }
 
@@ -124,10 +124,13 @@ void CoreParams::load(Image const& img)
         g.max_depth = sc.at(0);
         g.max_faces = sc.at(1);
         g.max_intersections = sc.at(2);
-        if (g.max_faces > ORANGE_MAX_FACES || g.max_intersections > ORANGE_MAX_ISECT)
+        // Volumes beyond ORANGE_MAX_FACES / ORANGE_MAX_ISECT take the big-volume path
+        // (csrc/orange.cuh), whose only limit is the size of its sense-word array
+        if (g.max_faces > ORANGE_BIG_MAX_FACES)
         {
             throw std::runtime_error(
-                "geometry exceeds compiled face/intersection limits: max_faces="
+                "geometry exceeds the face limit of the big-volume path ("
+                + std::to_string(ORANGE_BIG_MAX_FACES) + "): max_faces="
                 + std::to_string(g.max_faces)
                 + " max_intersections=" + std::to_string(g.max_intersections));
         }
@@ -549,8 +552,17 @@ void CoreParams::max_events(uint32_t num_events)
 
 void CoreParams::track_order(uint32_t order)
 {
-    if (order >= ORDER_SIZE_)
+    if (order >= ORDER_SIZE_ || order == ORDER_REINDEX_SHUFFLE)
         throw std::runtime_error("unsupported track_order");
+    // The reindex orders come with SortTracksAction entries in the action table
+    // (CoreParams.cc:253-284 of the reference): they are a property of the exported image
+    if (order != view_.scalars.track_order
+        && (order >= ORDER_REINDEX_STATUS || view_.scalars.track_order >= ORDER_REINDEX_STATUS))
+    {
+        throw std::runtime_error(
+            "track_order differs from the order the problem image was exported with, and one "
+            "of them sorts tracks (its sort actions are part of the image's action table)");
+    }
     if (order != view_.scalars.track_order)
         require_unfrozen(frozen_, "track_order");
     view_.scalars.track_order = order;

@@ -144,6 +144,19 @@ CoreState::CoreState(std::shared_ptr<CoreParams const> params,
         s.interact_list = arena_.alloc<u32>(size_t(p.phys.num_models) * n);
         s.interact_count = arena_.alloc<u32>(16);
     }
+    // TrackOrder::reindex_*: the sorted slot permutation (csrc/kernels_sort.cu)
+    if (p.scalars.track_order >= ORDER_REINDEX_STATUS)
+    {
+        uint32_t const nkeys = std::max<uint32_t>(
+            std::max<uint32_t>(uint32_t(params_->actions().size()), p.particle.num_particles), 1u);
+        uint32_t const sort_blocks = (n + 255) / 256;
+        std::vector<uint32_t> seq(n);
+        std::iota(seq.begin(), seq.end(), 0u);
+        s.sort_slots = const_cast<u32*>(arena_.upload(seq));
+        s.sort_offsets = arena_.alloc<u32>(size_t(nkeys) + 2);
+        s.sort_block_counts = arena_.alloc<u32>((size_t(nkeys) + 1) * sort_blocks);
+        s.num_sort_keys = nkeys;
+    }
     // Device-resident step loop (csrc/tail.cu); needs whole runs of 32 slots
     if (n % 32 == 0)
     {
@@ -358,6 +371,15 @@ void CoreState::get_field(std::string const& f, void* out)
                     o[i] = soff[univ[size_t(slevel[i]) * n + i]] + surf[i];
             }
         }
+    }
+    else if (f == "sort_slots" || f == "sort_offsets")
+    {
+        if (!s.sort_slots)
+            throw std::runtime_error("the track order of this problem does not sort tracks");
+        if (f == "sort_slots")
+            copy(s.sort_slots, size_t(4) * n);
+        else
+            copy(s.sort_offsets, size_t(4) * (s.num_sort_keys + 2));
     }
     else if (f == "interact_count")
     {

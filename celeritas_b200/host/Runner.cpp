@@ -270,10 +270,19 @@ std::string celer_sim_run(std::string const& input_json)
         track_order = b200::ORDER_NONE;
     else if (inp.track_order == "init_charge")
         track_order = b200::ORDER_INIT_CHARGE;
+    else if (inp.track_order == "reindex_status")
+        track_order = b200::ORDER_REINDEX_STATUS;
+    else if (inp.track_order == "reindex_particle_type")
+        track_order = b200::ORDER_REINDEX_PARTICLE_TYPE;
+    else if (inp.track_order == "reindex_along_step_action")
+        track_order = b200::ORDER_REINDEX_ALONG_STEP_ACTION;
+    else if (inp.track_order == "reindex_step_limit_action")
+        track_order = b200::ORDER_REINDEX_STEP_LIMIT_ACTION;
+    else if (inp.track_order == "reindex_both_action")
+        track_order = b200::ORDER_REINDEX_BOTH_ACTION;
     else
     {
-        // The dense charged/neutral slot lists give init_charge coherence natively;
-        // the reindexing orders are not implemented
+        // reindex_shuffle is a std::shuffle of the slot map at construction: not reproduced
         throw std::runtime_error("track_order '" + inp.track_order + "' is not supported");
     }
 

@@ -101,6 +101,7 @@ ActionSequence::ActionSequence(CoreParams const& params, Options options)
     uint32_t const model_end = model_begin + view.phys.num_models;
     bool have_interact = false;
     bool have_tally = false;
+    bool have_sort = false;
 
     // Full action table: the problem's actions, then the diagnostics in the order
     // celer-sim registers them (app/celer-sim/Runner.cc:616-633), then user actions
@@ -163,6 +164,24 @@ ActionSequence::ActionSequence(CoreParams const& params, Options options)
         else if (a.label == "physics-discrete-select")
         {
             act = std::make_shared<KernelAction>(a.id, a.label, order, &b200_step_discrete_select);
+        }
+        else if (a.label.rfind("sort-tracks-", 0) == 0)
+        {
+            // TrackOrder::reindex_*: labels of SortTracksAction::label()
+            // (track/SortTracksAction.cc:83-98)
+            uint32_t key = INVALID;
+            if (a.label == "sort-tracks-status")
+                key = ORDER_REINDEX_STATUS;
+            else if (a.label == "sort-tracks-start")
+                key = ORDER_REINDEX_PARTICLE_TYPE;
+            else if (a.label == "sort-tracks-along-step")
+                key = ORDER_REINDEX_ALONG_STEP_ACTION;
+            else if (a.label == "sort-tracks-post-step")
+                key = ORDER_REINDEX_STEP_LIMIT_ACTION;
+            else
+                throw std::runtime_error("unknown sort action '" + a.label + "'");
+            act = std::make_shared<SortTracksAction>(a.id, a.label, order, key);
+            have_sort = true;
         }
         else if (a.id >= model_begin && a.id < model_end)
         {
@@ -230,6 +249,9 @@ ActionSequence::ActionSequence(CoreParams const& params, Options options)
         if (user->order() >= Order::pre && user->order() <= Order::user_post)
             fusable_ = false;
     }
+    // A sort action has to see the state between two groups of the fused launch
+    if (have_sort)
+        fusable_ = false;
     fuse_threshold_ = options.fuse_threshold ? options.fuse_threshold : default_fuse_threshold;
     if (char const* env = std::getenv("B200_FUSE_THRESHOLD"))
         fuse_threshold_ = static_cast<uint32_t>(std::strtoul(env, nullptr, 10));
@@ -284,6 +306,12 @@ ActionSequence::ActionSequence(CoreParams const& params, Options options)
     // profiles/README_r01.md), so it is opt-in
     if (!std::getenv("B200_ALONG_SELECT"))
         along_select_ = actions_.size();
+}
+
+void SortTracksAction::step(CoreParams const& params, CoreState& state) const
+{
+    check_rc(b200_step_sort_tracks(pv(params), sv(state), track_order_, state.stream()),
+             label_.c_str());
 }
 
 ActionSequence::~ActionSequence()

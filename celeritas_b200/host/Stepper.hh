@@ -58,6 +58,28 @@ class KernelAction final : public StepActionInterface
     Launcher launch_;
 };
 
+//! Sort or partition the track-slot permutation (reference: SortTracksAction,
+//! track/SortTracksAction.cc:46-131); one per TrackOrder::reindex_* key
+class SortTracksAction final : public StepActionInterface
+{
+  public:
+    SortTracksAction(uint32_t id, std::string label, StepActionOrder order, uint32_t track_order)
+        : id_(id), label_(std::move(label)), order_(order), track_order_(track_order)
+    {
+    }
+    uint32_t action_id() const override { return id_; }
+    std::string const& label() const override { return label_; }
+    StepActionOrder order() const override { return order_; }
+    uint32_t track_order() const { return track_order_; }
+    void step(CoreParams const& params, CoreState& state) const override;
+
+  private:
+    uint32_t id_;
+    std::string label_;
+    StepActionOrder order_;
+    uint32_t track_order_;
+};
+
 class ActionSequence
 {
   public:

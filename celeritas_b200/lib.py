@@ -68,7 +68,7 @@ EXPORTS = [
     'b200_params_max_depth', 'b200_step_tail_loop', 'b200_tail_max_blocks',
     'b200_stepper_advance', 'b200_stepper_tail_iterations',
     'b200_params_create_from_memory', 'b200_stepper_insert', 'b200_stepper_begin_iteration',
-    'b200_stepper_end_iteration', 'b200_stepper_stream',
+    'b200_stepper_end_iteration', 'b200_stepper_stream', 'b200_step_sort_tracks',
 ]
 
 _lib = None
@@ -101,6 +101,7 @@ def load_library():
     L.b200_stepper_end_iteration.argtypes = [vp, C.POINTER(StepperResult)]
     L.b200_stepper_stream.argtypes = [vp]
     L.b200_stepper_stream.restype = vp
+    L.b200_step_sort_tracks.argtypes = [vp, vp, C.c_uint32, vp]
     L.b200_params_view.restype = vp
     L.b200_params_view.argtypes = [vp]
     L.b200_params_num_actions.argtypes = [vp]
@@ -202,6 +203,7 @@ FIELDS = {
     'interaction_mfp': ('<f8', 1), 'macro_xs': ('<f8', 1), 'energy_deposition': ('<f8', 1),
     'dedx_range': ('<f8', 1), 'rng': ('<u4', 6), 'pos': ('<f8', 3), 'dir': ('<f8', 3),
     'volume_id': ('<u4', 1), 'surface_id': ('<u4', 1), 'geo_level': ('<u4', 1),
+    'sort_slots': ('<u4', 1),
 }
 
 
@@ -396,6 +398,16 @@ class Stepper:
         dt, w = FIELDS[field]
         out = np.zeros((self.n, w) if w > 1 else self.n, dtype=dt)
         _check(L.b200_state_get(L.b200_stepper_state(self.h), field.encode(), out.ctypes.data))
+        return out
+
+    def sort_offsets(self):
+        """First index of every sort key in get('sort_slots') after the last sort action
+        (TrackOrder::reindex_*); entry [number of keys + 1] is the number of slots."""
+        L = load_library()
+        n = max(L.b200_params_num_actions(self.params.h),
+                L.b200_params_num_particles(self.params.h), 1) + 2
+        out = np.zeros(n, dtype=np.uint32)
+        _check(L.b200_state_get(L.b200_stepper_state(self.h), b'sort_offsets', out.ctypes.data))
         return out
 
     def interaction_lists(self):

@@ -172,6 +172,14 @@ int b200_step_boundary(B200ParamsView const*, B200StateView const*, cudaStream_t
 int b200_step_tracking_cut(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_step_tally(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_step_extend_from_secondaries(B200ParamsView const*, B200StateView const*, cudaStream_t);
+/* SortTracksAction::step (src/celeritas/track/SortTracksAction.cc:100-131) for problems whose
+ * track order is one of TrackOrder::reindex_* (src/celeritas/Types.hh:151-171): rebuilds the
+ * permutation of all track slots sorted by the key of `track_order` (3 = reindex_status,
+ * 4 = reindex_particle_type, 5 = reindex_along_step_action, 6 = reindex_step_limit_action; the
+ * reference's enum values) and the first index of every key (action_thread_offsets,
+ * back-filled). Read back with b200_state_get "sort_slots" / "sort_offsets". */
+int b200_step_sort_tracks(B200ParamsView const*, B200StateView const*, uint32_t track_order,
+                          cudaStream_t);
 /* ActionDiagnostic (user/detail/ActionDiagnosticExecutor.hh:30-65, order post) and
  * StepDiagnostic (user/detail/StepDiagnosticExecutor.hh:28-60, order user_post); the
  * state must have been created with the diagnostic enabled (B200StepperOptions). */

@@ -6,6 +6,7 @@
 #include "Problem.hh"
 
 #include <fstream>
+#include <map>
 
 #include "corecel/io/Logger.hh"
 #include "corecel/io/OutputRegistry.hh"
@@ -545,10 +546,17 @@ std::unique_ptr<Problem> build_problem(json const& config)
         input.capacity = cfg.value("initializer_capacity", 4096u);
         input.max_events = cfg.value("max_events", 4096u);
         std::string order = cfg.value("track_order", std::string("none"));
-        input.track_order = order == "init_charge" ? TrackOrder::init_charge
-                                                   : TrackOrder::none;
-        CELER_VALIDATE(order == "none" || order == "init_charge",
-                       << "unsupported track_order " << order);
+        static std::map<std::string, TrackOrder> const orders{
+            {"none", TrackOrder::none},
+            {"init_charge", TrackOrder::init_charge},
+            {"reindex_status", TrackOrder::reindex_status},
+            {"reindex_particle_type", TrackOrder::reindex_particle_type},
+            {"reindex_along_step_action", TrackOrder::reindex_along_step_action},
+            {"reindex_step_limit_action", TrackOrder::reindex_step_limit_action},
+            {"reindex_both_action", TrackOrder::reindex_both_action}};
+        auto found = orders.find(order);
+        CELER_VALIDATE(found != orders.end(), << "unsupported track_order " << order);
+        input.track_order = found->second;
         params.init = std::make_shared<TrackInitParams>(std::move(input));
     }
     p->core = std::make_shared<CoreParams>(std::move(params));

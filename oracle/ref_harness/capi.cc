@@ -245,6 +245,9 @@ int celerref_state_get(void* stepper, char const* field, void* out)
                 o32[i] = state.sim.post_step_action[ts].unchecked_get();
             else if (f == "along_step_action")
                 o32[i] = state.sim.along_step_action[ts].unchecked_get();
+            else if (f == "track_slots")
+                // thread -> slot permutation kept by SortTracksAction (TrackOrder::reindex_*)
+                o32[i] = state.track_slots[ThreadId{i}];
             else if (f == "particle_id")
                 o32[i] = state.particles.particle_id[ts].unchecked_get();
             else if (f == "energy")

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 GEOMETRIES = ['two-boxes', 'testem3-flat', 'testem3', 'simple-cms', 'five-volumes', 'universes',
               'rect-array', 'nested-rect-arrays', 'hex-array', 'three-spheres', 'testem15',
-              'lar-sphere', 'four-steel-slabs', 'one-steel-sphere', 'cms-scale']
+              'lar-sphere', 'four-steel-slabs', 'one-steel-sphere', 'cms-scale', 'many-faces']
 
 
 def ray_set(name, n, seed):

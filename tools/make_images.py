@@ -94,12 +94,19 @@ PROBLEMS['simple-cms-em-field-initcharge'] = dict(PROBLEMS['simple-cms-em-field'
 PROBLEMS['cms-scale-small'] = dict(PROBLEMS['cms-scale'], initializer_capacity=1 << 18,
                                    max_events=64, track_order='none')
 
+# Volumes beyond the register path's 32 faces / intersections (tools/make_many_faces.py): a
+# 113-face background volume filled with liquid argon, a 40-plane polyhedron, a box with 30
+# holes as one internal-surface volume; full EM
+PROBLEMS['many-faces'] = {'geometry_file': 'data/geometry/many-faces.org.json',
+                          'physics_file': 'data/physics/many-faces-steel-lar.json',
+                          'seed': 20220904, 'initializer_capacity': 1 << 18, 'max_events': 64,
+                          'simple_calo': ['mother', 'polyhedron', 'cheese']}
 
 # Geometry-only images for the navigation (ray-trace) parity tests: the ORANGE test
 # geometries of the reference (test/orange/data, test/geocel/data)
 for _g in ('two-boxes', 'testem3-flat', 'testem3', 'simple-cms', 'five-volumes', 'universes',
            'rect-array', 'nested-rect-arrays', 'hex-array', 'three-spheres', 'testem15',
-           'lar-sphere', 'four-steel-slabs', 'one-steel-sphere', 'cms-scale'):
+           'lar-sphere', 'four-steel-slabs', 'one-steel-sphere', 'cms-scale', 'many-faces'):
     PROBLEMS['geo-' + _g] = {'problem': 'geometry',
                              'geometry_file': 'data/geometry/%s.org.json' % _g}
 
