@@ -91,6 +91,89 @@ __global__ void __launch_bounds__(BLOCK, B2_PRE_MIN_BLOCKS) k_pre_step(B2_GRID_C
     }
 }
 
+#if B2_SMEM_GRIDS
+//---------------------------------------------------------------------------//
+// Experiment (north-star (c): "physics tables staged in shared memory or via TMA"): the
+// pre-step as a PERSISTENT kernel whose blocks first copy the value-grid tables (values and
+// node energies of every cross-section / energy-loss / range grid: 2 x 23 kB for the TestEm3
+// problem) into shared memory with two 1-D bulk copies (cp.async.bulk, completion on an
+// mbarrier) and then walk the active list; every XsCalculator / RangeCalculator lookup of
+// do_pre_step then reads shared memory instead of L1/L2. Measured against the plain kernel
+// in profiles/README_r02.md.
+//---------------------------------------------------------------------------//
+constexpr u32 STAGED_BLOCK = 256;
+
+B2_D u32 smem_addr(void const* ptr)
+{
+    return static_cast<u32>(__cvta_generic_to_shared(ptr));
+}
+
+__global__ void __launch_bounds__(STAGED_BLOCK, 2)
+    k_pre_step_staged(B2_GRID_CONSTANT ParamsView const p,
+                      B2_GRID_CONSTANT StateView const s,
+                      u32 reals_bytes,
+                      u32 energy_bytes)
+{
+    extern __shared__ __align__(128) unsigned char staged[];
+    __shared__ __align__(8) u64 bar;
+    real* const sm_reals = reinterpret_cast<real*>(staged);
+    real* const sm_energy = reinterpret_cast<real*>(staged + reals_bytes);
+    if (threadIdx.x == 0)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bar)),
+                     "r"(reals_bytes + energy_bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_addr(sm_reals)),
+            "l"(static_cast<real const*>(p.phys.reals)), "r"(reals_bytes), "r"(smem_addr(&bar))
+            : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_addr(sm_energy)),
+            "l"(static_cast<real const*>(p.phys.grid_energy)), "r"(energy_bytes),
+            "r"(smem_addr(&bar))
+            : "memory");
+    }
+    // wait for phase 0 of the barrier
+    {
+        u32 done = 0;
+        while (!done)
+        {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                "selp.u32 %0, 1, 0, p;\n"
+                "}\n"
+                : "=r"(done)
+                : "r"(smem_addr(&bar)), "r"(0u)
+                : "memory");
+        }
+    }
+    // the same problem description with the two table columns redirected to shared memory
+    ParamsView q = p;
+    q.phys.reals = RO<real>(sm_reals);
+    q.phys.grid_energy = RO<real>(sm_energy);
+    u32 const nact = s.counters[CTR_NUM_CHARGED] + s.counters[CTR_NUM_NEUTRAL];
+    for (u32 tid = thread_id(); tid < nact; tid += gridDim.x * STAGED_BLOCK)
+    {
+        u32 const slot = active_slot(s, tid);
+        if (slot != INVALID)
+        {
+            prefetch_pre_step_state(s, slot);
+            do_pre_step(q, s, slot);
+        }
+    }
+}
+#endif
+
 
 
 
@@ -468,6 +551,33 @@ int b200_step_initialize_tracks(B200ParamsView const* params,
 int b200_step_pre_step(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
 {
     StateView const& s = SV(state);
+#if B2_SMEM_GRIDS
+    {
+        // table sizes [bytes], rounded up to the 16-byte granularity of a bulk copy
+        // (the loader pads both columns, CoreParams.cc)
+        ParamsView const& p = PV(params);
+        u32 const reals_bytes = (p.phys_reals_count * 8u + 15u) & ~15u;
+        u32 const energy_bytes = (p.phys_energy_count * 8u + 15u) & ~15u;
+        static int sms = 0;
+        if (sms == 0)
+        {
+            int device = 0;
+            cudaGetDevice(&device);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+            cudaFuncSetAttribute(k_pre_step_staged, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 100 * 1024);
+        }
+        if (reals_bytes + energy_bytes <= 100 * 1024)
+        {
+            u32 const want = (active_hint(s) + STAGED_BLOCK - 1) / STAGED_BLOCK;
+            u32 const grid = want < u32(2 * sms) ? (want ? want : 1u) : u32(2 * sms);
+            k_pre_step_staged<<<grid, STAGED_BLOCK, reals_bytes + energy_bytes, stream>>>(
+                p, s, reals_bytes, energy_bytes);
+            B2_COUNT(1);
+            return check_launch();
+        }
+    }
+#endif
     k_pre_step<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s);
     B2_COUNT(1);
     return check_launch();

@@ -31,7 +31,10 @@ constexpr int ORANGE_MAX_ISECT = 32;
 // arrays sized by the face count, only the sense words (1 bit per face). The reference sizes
 // per-track global scratch from max_faces / max_intersections at run time
 // (orange/OrangeData.hh:348-544, OrangeTrackView.hh:1042-1067); here the only limit is:
-constexpr int ORANGE_BIG_MAX_FACES = 4096;
+// (1024 faces = 128 B of sense words per search; keep the step kernels' stack frames small:
+// with 4096 faces the frames grew to 2-3.6 kB and the driver started resizing its local-memory
+// pool between launches: 92 -> 153 ms per TestEm3 pass, profiles/README_r02.md)
+constexpr int ORANGE_BIG_MAX_FACES = 1024;
 constexpr int ORANGE_BIG_SENSE_WORDS = ORANGE_BIG_MAX_FACES / 32;
 // Lanes of a warp that reach the big-volume search together share the work (1) or every lane
 // searches on its own (0: measurement knob, same results)
@@ -617,8 +620,12 @@ B2_D bool volume_contains(GeoParams const& g,
         u32 senses = calc_senses(g, u, v, pos, face);
         return eval_logic(g, v, senses);
     }
+#ifndef B2_DBG_NO_BIG_CONTAINS
     u8 unused = 0;
     return volume_contains_big(g, u, v, pos, face, INVALID, unused);
+#else
+    return false;
+#endif
 }
 
 //---------------------------------------------------------------------------//
@@ -788,10 +795,10 @@ B2_D Initialization unit_cross_boundary(GeoParams const& g, SimpleUnit const& u,
 // walks them in order (complex_intersect :506-560, background_intersect :585-640). For a
 // volume with hundreds of faces that is hundreds of dependent quadric solves in one thread
 // plus a sort through global memory. Here the lanes of a warp that arrive at the search
-// together (any subset: cooperative_groups::coalesced_threads) serve one another's tracks in
-// turn: for each track the group deals the FACES out to its lanes (face f -> lane f mod n),
-// every lane solves its faces, and the group reduces to the next crossing in
-// (distance, face, root) order. The ordered walk of the reference becomes "extract the next
+// together AND hold the same track (cooperative_groups: coalesced_threads, partitioned by
+// query; see unit_intersect_big for which lanes those are and why not more) share the search:
+// the group deals the FACES out to its lanes (face f -> lane f mod n), every lane solves its
+// faces, and the group reduces to the next crossing in (distance, face, root) order. The ordered walk of the reference becomes "extract the next
 // minimum, strictly after the previous one": no intersection array, no sort, no scratch
 // memory; a walk normally ends after one or two crossings. Sense words are built the same
 // way (one OR-reduction per 32 faces), and a background volume's neighbour tests are dealt
@@ -831,7 +838,8 @@ B2_D Intersection big_volume_search(Group const& grp,
                                     SimpleUnit const& u,
                                     LocalState const& st,
                                     bool limited,
-                                    real max_dist)
+                                    real max_dist,
+                                    u32* words)
 {
     u32 const n = grp.size();
     u32 const rank = grp.thread_rank();
@@ -894,7 +902,7 @@ B2_D Intersection big_volume_search(Group const& grp,
     else if (vol.flags & VOL_INTERNAL_SURFACES)
     {
         // complex_intersect: cross surfaces in order until the logic says "outside"
-        u32 words[ORANGE_BIG_SENSE_WORDS];
+        // (`words`: ORANGE_BIG_SENSE_WORDS of caller-provided scratch)
         u32 const nwords = (vol.num_faces + 31u) >> 5;
         for (u32 w = 0; w < nwords; ++w)
         {
@@ -982,41 +990,53 @@ B2_D Intersection big_volume_search(Group const& grp,
 
 //! Distance to boundary in a volume too large for the register path. Out of line: the step
 //! kernels' register budgets are set by the small-volume path.
+//!
+//! Which lanes cooperate: the ones that hold the SAME query, i.e. the lanes of a warp that
+//! carries one track in all its lanes (the device-resident loop's one-warp-per-track mode,
+//! csrc/tail.cu). Lanes with different tracks each search on their own, side by side.
+//! Measured on this geometry class (profiles/README_r02.md, "big volumes"): serving the
+//! different tracks of a full warp one after the other with 32-way parallelism has the same
+//! critical path as 32 lanes searching side by side plus the reductions, and is 2.3 x slower
+//! (k_geo_trace, 113-face volume: 92.7 ms against 39.7 ms for 262 144 rays); borrowing lanes
+//! only pays when they would otherwise repeat the same work.
 B2_NOINLINE inline Intersection unit_intersect_big(GeoParams const& g,
                                                    SimpleUnit const& u,
                                                    LocalState const& st,
                                                    bool limited,
                                                    real max_dist)
 {
+    u32 words[ORANGE_BIG_SENSE_WORDS];
 #if B2_ORANGE_BIG_COOP
-    // Every lane that is here right now has a big-volume search of its own to do: do them
-    // one after the other, all lanes together
-    cg::coalesced_group const grp = cg::coalesced_threads();
-    u32 const my_unit = static_cast<u32>(&u - g.simple_units);
-    Intersection mine{INVALID, 0, real_inf()};
-    for (u32 leader = 0; leader < grp.size(); ++leader)
+    // Partition the lanes that are here by (a hash of) their query
+    cg::coalesced_group const here = cg::coalesced_threads();
+    u64 h = static_cast<u64>(__double_as_longlong(st.pos[0]));
+    h = h * 0x9e3779b97f4a7c15ull + static_cast<u64>(__double_as_longlong(st.pos[1]));
+    h = h * 0x9e3779b97f4a7c15ull + static_cast<u64>(__double_as_longlong(st.pos[2]));
+    h = h * 0x9e3779b97f4a7c15ull + static_cast<u64>(__double_as_longlong(st.dir[0]));
+    h = h * 0x9e3779b97f4a7c15ull + static_cast<u64>(__double_as_longlong(st.dir[1]));
+    h = h * 0x9e3779b97f4a7c15ull + static_cast<u64>(__double_as_longlong(max_dist));
+    h = h * 0x9e3779b97f4a7c15ull + (u64(st.volume) << 32 | u64(st.surface));
+    cg::coalesced_group const grp = cg::labeled_partition(here, static_cast<u32>(h ^ (h >> 32)));
+    if (grp.size() > 1)
     {
-        LocalState q;
+        // every member must hold exactly the query of the first one (hash collisions)
+        u32 const my_unit = static_cast<u32>(&u - g.simple_units);
+        bool same = true;
         for (int k = 0; k < 3; ++k)
         {
-            q.pos[k] = grp.shfl(st.pos[k], leader);
-            q.dir[k] = grp.shfl(st.dir[k], leader);
+            same = same && grp.shfl(st.pos[k], 0) == st.pos[k]
+                   && grp.shfl(st.dir[k], 0) == st.dir[k];
         }
-        q.volume = grp.shfl(st.volume, leader);
-        q.surface = grp.shfl(st.surface, leader);
-        q.sense = static_cast<u8>(grp.shfl(u32(st.sense), leader));
-        u32 const q_unit = grp.shfl(my_unit, leader);
-        bool const q_limited = grp.shfl(u32(limited), leader) != 0;
-        real const q_max = grp.shfl(max_dist, leader);
-        Intersection const r
-            = big_volume_search(grp, g, g.simple_units[q_unit], q, q_limited, q_max);
-        if (grp.thread_rank() == leader)
-            mine = r;
+        same = same && grp.shfl(st.volume, 0) == st.volume
+               && grp.shfl(st.surface, 0) == st.surface
+               && grp.shfl(u32(st.sense), 0) == u32(st.sense) && grp.shfl(my_unit, 0) == my_unit
+               && grp.shfl(u32(limited), 0) == u32(limited)
+               && (grp.shfl(max_dist, 0) == max_dist || !limited);
+        if (grp.all(same))
+            return big_volume_search(grp, g, u, st, limited, max_dist, words);
     }
-    return mine;
-#else
-    return big_volume_search(SoloGroup{}, g, u, st, limited, max_dist);
 #endif
+    return big_volume_search(SoloGroup{}, g, u, st, limited, max_dist, words);
 }
 
 //! Distance to the boundary of the current volume. max_dist < 0 = unlimited.
@@ -1027,8 +1047,10 @@ B2_D Intersection unit_intersect(GeoParams const& g,
                                  real max_dist)
 {
     VolumeRef vol = get_volume(g, u, st.volume);
+#ifndef B2_DBG_NO_BIG_INTERSECT
     if (vol.num_faces > u32(ORANGE_MAX_FACES) || vol.max_isect > u32(ORANGE_MAX_ISECT))
         return unit_intersect_big(g, u, st, limited, max_dist);
+#endif
     u32 on_face = (st.surface != INVALID) ? volume_find_face(g, vol, st.surface) : INVALID;
     bool const simple = !(vol.flags & (VOL_INTERNAL_SURFACES | VOL_IMPLICIT));
 
@@ -1496,33 +1518,44 @@ struct GeoTrackT
 
     // --- per-level accessors
     B2_D u32 lidx(u32 level) const { return level * s.num_slots + slot; }
+    // Layout of geo_pos / geo_dir (24 B per level and slot either way):
+    //   B2_POSDIR_PACKED 0  three columns [3][level][slot]
+    //   B2_POSDIR_PACKED 1  double2 {x, y}[level][slot] followed by z[level][slot]
+    B2_D static Real3 load3(real const* base, u32 n, u32 i)
+    {
+#if B2_POSDIR_PACKED
+        double2 const xy = reinterpret_cast<double2 const*>(base)[i];
+        return make_real3(xy.x, xy.y, base[2 * size_t(n) + i]);
+#else
+        return make_real3(base[i], base[n + i], base[2 * n + i]);
+#endif
+    }
+    B2_D static void store3(real* base, u32 n, u32 i, Real3 const& v)
+    {
+#if B2_POSDIR_PACKED
+        reinterpret_cast<double2*>(base)[i] = make_double2(v[0], v[1]);
+        base[2 * size_t(n) + i] = v[2];
+#else
+        base[i] = v[0];
+        base[n + i] = v[1];
+        base[2 * n + i] = v[2];
+#endif
+    }
     B2_D Real3 pos(u32 level) const
     {
-        u32 n = s.num_slots * s.max_depth;
-        u32 i = lidx(level);
-        return make_real3(s.geo_pos[i], s.geo_pos[n + i], s.geo_pos[2 * n + i]);
+        return load3(s.geo_pos, s.num_slots * s.max_depth, lidx(level));
     }
     B2_D Real3 dir(u32 level) const
     {
-        u32 n = s.num_slots * s.max_depth;
-        u32 i = lidx(level);
-        return make_real3(s.geo_dir[i], s.geo_dir[n + i], s.geo_dir[2 * n + i]);
+        return load3(s.geo_dir, s.num_slots * s.max_depth, lidx(level));
     }
     B2_D void set_pos(u32 level, Real3 const& v) const
     {
-        u32 n = s.num_slots * s.max_depth;
-        u32 i = lidx(level);
-        s.geo_pos[i] = v[0];
-        s.geo_pos[n + i] = v[1];
-        s.geo_pos[2 * n + i] = v[2];
+        store3(s.geo_pos, s.num_slots * s.max_depth, lidx(level), v);
     }
     B2_D void set_dir(u32 level, Real3 const& v) const
     {
-        u32 n = s.num_slots * s.max_depth;
-        u32 i = lidx(level);
-        s.geo_dir[i] = v[0];
-        s.geo_dir[n + i] = v[1];
-        s.geo_dir[2 * n + i] = v[2];
+        store3(s.geo_dir, s.num_slots * s.max_depth, lidx(level), v);
     }
     B2_D u32 vol(u32 level) const { return s.geo_vol[lidx(level)]; }
     B2_D u32 univ(u32 level) const { return s.geo_univ[lidx(level)]; }
@@ -1649,11 +1682,8 @@ struct GeoTrackT
             {
                 u32 src = l * s.num_slots + other;
                 u32 dst = lidx(l);
-                for (int k = 0; k < 3; ++k)
-                {
-                    s.geo_pos[k * n + dst] = s.geo_pos[k * n + src];
-                    s.geo_dir[k * n + dst] = s.geo_dir[k * n + src];
-                }
+                store3(s.geo_pos, n, dst, load3(s.geo_pos, n, src));
+                store3(s.geo_dir, n, dst, load3(s.geo_dir, n, src));
                 s.geo_vol[dst] = s.geo_vol[src];
                 s.geo_univ[dst] = s.geo_univ[src];
             }

@@ -22,20 +22,41 @@ struct Rng
     u32 x[5];
     u32 d;
 
+    // Layout of StateView::rng (24 B per slot either way):
+    //   B2_RNG_PACKED 0  six columns [6][slot]: six 4-byte accesses per slot
+    //   B2_RNG_PACKED 1  uint4 {x0..x3}[slot] followed by uint2 {x4, weyl}[slot]: one 16-byte
+    //                    and one 8-byte access per slot (2 sectors per slot instead of 6 when
+    //                    the slots of a warp are scattered)
     B2_D void load(StateView const& s, u32 slot)
     {
+#if B2_RNG_PACKED
+        uint4 const a = reinterpret_cast<uint4 const*>(s.rng)[slot];
+        uint2 const b = reinterpret_cast<uint2 const*>(s.rng + size_t(4) * s.num_slots)[slot];
+        x[0] = a.x;
+        x[1] = a.y;
+        x[2] = a.z;
+        x[3] = a.w;
+        x[4] = b.x;
+        d = b.y;
+#else
 #pragma unroll
         for (int k = 0; k < 5; ++k)
             x[k] = s.rng[k * s.num_slots + slot];
         d = s.rng[5 * s.num_slots + slot];
+#endif
     }
 
     B2_D void store(StateView const& s, u32 slot) const
     {
+#if B2_RNG_PACKED
+        reinterpret_cast<uint4*>(s.rng)[slot] = make_uint4(x[0], x[1], x[2], x[3]);
+        reinterpret_cast<uint2*>(s.rng + size_t(4) * s.num_slots)[slot] = make_uint2(x[4], d);
+#else
 #pragma unroll
         for (int k = 0; k < 5; ++k)
             s.rng[k * s.num_slots + slot] = x[k];
         s.rng[5 * s.num_slots + slot] = d;
+#endif
     }
 
     B2_D void next()

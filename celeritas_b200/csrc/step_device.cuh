@@ -134,6 +134,19 @@ B2_D void prefetch_l2(void const* ptr)
 #endif
 }
 
+//! L2 prefetch of a slot's RNG state (layout: Rng::load)
+B2_D void prefetch_rng(StateView const& s, u32 slot)
+{
+#if B2_RNG_PACKED
+    prefetch_l2(s.rng + 4 * size_t(slot));
+    prefetch_l2(s.rng + 4 * size_t(s.num_slots) + 2 * size_t(slot));
+#else
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        prefetch_l2(s.rng + size_t(k) * s.num_slots + slot);
+#endif
+}
+
 template<bool CHARGED>
 B2_D void prefetch_along_step_state(StateView const& s, u32 slot)
 {
@@ -149,12 +162,19 @@ B2_D void prefetch_along_step_state(StateView const& s, u32 slot)
     prefetch_l2(s.num_steps + slot);
     // geometry (level 0; deeper levels are rare and follow on demand)
     u32 const ng = n * s.max_depth;
+#if B2_POSDIR_PACKED
+    prefetch_l2(s.geo_pos + 2 * size_t(slot));
+    prefetch_l2(s.geo_pos + 2 * size_t(ng) + slot);
+    prefetch_l2(s.geo_dir + 2 * size_t(slot));
+    prefetch_l2(s.geo_dir + 2 * size_t(ng) + slot);
+#else
 #pragma unroll
     for (int k = 0; k < 3; ++k)
     {
         prefetch_l2(s.geo_pos + k * ng + slot);
         prefetch_l2(s.geo_dir + k * ng + slot);
     }
+#endif
     prefetch_l2(s.geo_vol + slot);
     prefetch_l2(s.geo_univ + slot);
     prefetch_l2(s.geo_level + slot);
@@ -169,9 +189,7 @@ B2_D void prefetch_along_step_state(StateView const& s, u32 slot)
 #pragma unroll
         for (int k = 0; k < 3; ++k)
             prefetch_l2(s.msc_range + k * n + slot);
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-            prefetch_l2(s.rng + k * n + slot);
+        prefetch_rng(s, slot);
     }
 }
 
@@ -185,9 +203,7 @@ B2_D void prefetch_pre_step_state(StateView const& s, u32 slot)
     prefetch_l2(s.geo_level + slot);
     prefetch_l2(s.geo_vol + slot);
     prefetch_l2(s.geo_univ + slot);
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
-        prefetch_l2(s.rng + k * n + slot);
+    prefetch_rng(s, slot);
 }
 
 //! i-th active slot: charged from the front, neutral from the back
@@ -641,6 +657,9 @@ struct ShadowSlot
 
 B2_D bool shadow_supported(StateView const& s)
 {
+    // the copy loops below assume one column per component (stride num_slots)
+    if (B2_RNG_PACKED || B2_POSDIR_PACKED)
+        return false;
     return s.max_depth <= SHADOW_MAX_DEPTH && s.max_processes <= SHADOW_MAX_PROCESSES;
 }
 

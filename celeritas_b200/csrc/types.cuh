@@ -35,17 +35,37 @@ constexpr u32 INVALID = 0xffffffffu;
 #ifndef B2_OUTLINE_LEVEL
 #    define B2_OUTLINE_LEVEL 0
 #endif
+// Kernel parameters are ALWAYS __grid_constant__: the big-volume geometry path (orange.cuh)
+// is out of line at every level and takes `GeoParams const&`; without the qualifier every
+// thread copied the whole ParamsView (1.6 kB) to its stack at kernel entry (TestEm3 pass
+// 92 -> 153 ms, profiles/README_r02.md).
+#define B2_GRID_CONSTANT __grid_constant__
 #if B2_OUTLINE_LEVEL >= 1
 #    define B2_UNIV_FN B2_NOINLINE inline
-#    define B2_GRID_CONSTANT __grid_constant__
 #else
 #    define B2_UNIV_FN B2_D
-#    define B2_GRID_CONSTANT
 #endif
 #if B2_OUTLINE_LEVEL >= 2
 #    define B2_GEO_FN B2_NOINLINE inline
 #else
 #    define B2_GEO_FN B2_D
+#endif
+
+// State-layout experiments (north-star (e): "coalesced, vectorised HBM gathers"), measured in
+// profiles/README_r02.md; both change only how the same bytes are arranged
+#ifndef B2_RNG_PACKED
+#    define B2_RNG_PACKED 0
+#endif
+#ifndef B2_POSDIR_PACKED
+#    define B2_POSDIR_PACKED 0
+#endif
+// Pre-step with the value-grid tables staged in shared memory (kernels.cu); needs plain loads
+// for the table columns (B2_RO_LDG=0: the non-coherent path cannot address shared memory)
+#ifndef B2_SMEM_GRIDS
+#    define B2_SMEM_GRIDS 0
+#endif
+#if B2_SMEM_GRIDS && !defined(B2_RO_LDG)
+#    define B2_RO_LDG 0
 #endif
 
 // Read-only column of the problem description (ParamsView). Element loads go through

@@ -443,6 +443,9 @@ struct CoreScalars
 
 struct ParamsView
 {
+    // element counts of phys.reals / phys.grid_energy (table staging, kernels.cu)
+    u32 phys_reals_count;
+    u32 phys_energy_count;
     CoreScalars scalars;
     GeoParams geo;
     MatParams mat;

@@ -266,7 +266,14 @@ void CoreParams::load(Image const& img)
         p.grid_log_delta = F64("phys.grid_log_delta");
         p.grid_prime = U32("phys.grid_prime");
         p.grid_value_offset = U32("phys.grid_value_offset");
-        p.reals = F64("phys.reals");
+        {
+            // padded to whole 16-byte units: a bulk copy to shared memory moves multiples of 16
+            auto reals = img.get<double>("phys.reals");
+            view_.phys_reals_count = reals.size();
+            if (reals.size() % 2)
+                reals.push_back(0);
+            p.reals = arena_.upload(reals);
+        }
         {
             NodeEnergyPool pool;
             auto size = img.get<uint32_t>("phys.grid_size");
@@ -276,6 +283,9 @@ void CoreParams::load(Image const& img)
             for (size_t g = 0; g < size.size(); ++g)
                 offsets[g] = pool.get(front[g], delta[g], size[g]);
             p.grid_energy_offset = arena_.upload(offsets);
+            view_.phys_energy_count = pool.values.size();
+            if (pool.values.size() % 2)
+                pool.values.push_back(0);
             p.grid_energy = arena_.upload(pool.values);
         }
         p.pp_num = U32("phys.pp_num");

@@ -14,6 +14,19 @@ using namespace b200;
 
 namespace celeritas_b200
 {
+namespace
+{
+//! Position of word k (x0..x4, weyl) of slot i in StateView::rng (layout: csrc/rng.cuh)
+inline size_t rng_index(int k, size_t i, size_t n)
+{
+#if B2_RNG_PACKED
+    return k < 4 ? 4 * i + k : 4 * n + 2 * i + (k - 4);
+#else
+    return size_t(k) * n + i;
+#endif
+}
+}  // namespace
+
 CoreState::CoreState(std::shared_ptr<CoreParams const> params,
                      uint32_t stream_id,
                      uint32_t num_track_slots)
@@ -87,9 +100,8 @@ CoreState::CoreState(std::shared_ptr<CoreParams const> params,
         std::vector<uint32_t> soa(size_t(6) * n);
         for (uint32_t i = 0; i < n; ++i)
         {
-            for (int k = 0; k < 5; ++k)
-                soa[size_t(k) * n + i] = sample(rng);
-            soa[size_t(5) * n + i] = sample(rng);
+            for (int k = 0; k < 6; ++k)
+                soa[rng_index(k, i, n)] = sample(rng);
         }
         s.rng = const_cast<u32*>(arena_.upload(soa));
     }
@@ -322,7 +334,7 @@ void CoreState::get_field(std::string const& f, void* out)
         auto* o = static_cast<uint32_t*>(out);
         for (size_t i = 0; i < n; ++i)
             for (int k = 0; k < 6; ++k)
-                o[6 * i + k] = soa[k * n + i];
+                o[6 * i + k] = soa[rng_index(k, i, n)];
     }
     else if (f == "pos" || f == "dir")
     {
@@ -336,7 +348,14 @@ void CoreState::get_field(std::string const& f, void* out)
         auto* o = static_cast<double*>(out);
         for (size_t i = 0; i < n; ++i)
             for (int k = 0; k < 3; ++k)
-                o[3 * i + k] = status[i] == ST_INACTIVE ? 0 : soa[k * stride + i];
+            {
+#if B2_POSDIR_PACKED
+                size_t const at = k < 2 ? 2 * i + k : 2 * stride + i;
+#else
+                size_t const at = k * stride + i;
+#endif
+                o[3 * i + k] = status[i] == ST_INACTIVE ? 0 : soa[at];
+            }
     }
     else if (f == "volume_id" || f == "surface_id")
     {
