@@ -31,9 +31,7 @@ constexpr int ORANGE_MAX_ISECT = 32;
 // arrays sized by the face count, only the sense words (1 bit per face). The reference sizes
 // per-track global scratch from max_faces / max_intersections at run time
 // (orange/OrangeData.hh:348-544, OrangeTrackView.hh:1042-1067); here the only limit is:
-// (1024 faces = 128 B of sense words per search; keep the step kernels' stack frames small:
-// with 4096 faces the frames grew to 2-3.6 kB and the driver started resizing its local-memory
-// pool between launches: 92 -> 153 ms per TestEm3 pass, profiles/README_r02.md)
+// (1024 faces = 128 B of sense words in the stack frame of the out-of-line search)
 constexpr int ORANGE_BIG_MAX_FACES = 1024;
 constexpr int ORANGE_BIG_SENSE_WORDS = ORANGE_BIG_MAX_FACES / 32;
 // Lanes of a warp that reach the big-volume search together share the work (1) or every lane
@@ -620,12 +618,8 @@ B2_D bool volume_contains(GeoParams const& g,
         u32 senses = calc_senses(g, u, v, pos, face);
         return eval_logic(g, v, senses);
     }
-#ifndef B2_DBG_NO_BIG_CONTAINS
     u8 unused = 0;
     return volume_contains_big(g, u, v, pos, face, INVALID, unused);
-#else
-    return false;
-#endif
 }
 
 //---------------------------------------------------------------------------//
@@ -1047,10 +1041,8 @@ B2_D Intersection unit_intersect(GeoParams const& g,
                                  real max_dist)
 {
     VolumeRef vol = get_volume(g, u, st.volume);
-#ifndef B2_DBG_NO_BIG_INTERSECT
     if (vol.num_faces > u32(ORANGE_MAX_FACES) || vol.max_isect > u32(ORANGE_MAX_ISECT))
         return unit_intersect_big(g, u, st, limited, max_dist);
-#endif
     u32 on_face = (st.surface != INVALID) ? volume_find_face(g, vol, st.surface) : INVALID;
     bool const simple = !(vol.flags & (VOL_INTERNAL_SURFACES | VOL_IMPLICIT));
 

@@ -651,14 +651,16 @@ struct ShadowSlot
     u32 post_step_action, along_step_action, particle_id, material_id;
     u32 geo_level, geo_surface_level, geo_surf, geo_next_level, geo_next_surf;
     u32 geo_vol[SHADOW_MAX_DEPTH], geo_univ[SHADOW_MAX_DEPTH];
-    u32 element, sec_particle[MAX_SECONDARIES], rng[6], pre_volume;
+    u32 element, sec_particle[MAX_SECONDARIES], pre_volume;
+    alignas(16) u32 rng[8];  // six words, laid out as Rng::load expects for num_slots = 1
     u8 status, geo_sense, geo_boundary, geo_next_sense, msc_is_displaced;
 };
 
 B2_D bool shadow_supported(StateView const& s)
 {
-    // the copy loops below assume one column per component (stride num_slots)
-    if (B2_RNG_PACKED || B2_POSDIR_PACKED)
+    // the copy loops below assume one column per component (stride num_slots); the RNG
+    // words go through Rng::load / store
+    if (B2_POSDIR_PACKED)
         return false;
     return s.max_depth <= SHADOW_MAX_DEPTH && s.max_processes <= SHADOW_MAX_PROCESSES;
 }
@@ -675,7 +677,7 @@ B2_D bool shadow_supported(StateView const& s)
     X(along_step_action, 1) X(particle_id, 1) X(material_id, 1) X(geo_level, 1)            \
     X(geo_surface_level, 1) X(geo_surf, 1) X(geo_next_level, 1) X(geo_next_surf, 1)        \
     X(geo_vol, (D)) X(geo_univ, (D)) X(element, 1) X(sec_particle, MAX_SECONDARIES)        \
-    X(rng, 6) X(status, 1) X(geo_sense, 1) X(geo_boundary, 1) X(geo_next_sense, 1)         \
+    X(status, 1) X(geo_sense, 1) X(geo_boundary, 1) X(geo_next_sense, 1)         \
     X(msc_is_displaced, 1)
 
 template<class T>
@@ -698,6 +700,7 @@ B2_D StateView shadow_view(StateView const& s, ShadowSlot& buf)
 #define B2_X(field, count) v.field = shadow_ptr(buf.field);
     B2_SHADOW_FIELDS(B2_X, 0, 0)
 #undef B2_X
+    v.rng = buf.rng;
     v.pre_volume = s.pre_volume ? &buf.pre_volume : nullptr;
     return v;
 }
@@ -711,6 +714,14 @@ B2_D void shadow_load(StateView const& s, u32 slot, ShadowSlot& buf)
         shadow_ptr(buf.field)[i] = s.field[size_t(i) * n + slot];
     B2_SHADOW_FIELDS(B2_X, D, P)
 #undef B2_X
+    {
+        // with one slot both RNG layouts are the six words in order
+        Rng r;
+        r.load(s, slot);
+        for (int k = 0; k < 5; ++k)
+            buf.rng[k] = r.x[k];
+        buf.rng[5] = r.d;
+    }
     if (s.pre_volume)
         buf.pre_volume = s.pre_volume[slot];
 }
@@ -724,6 +735,13 @@ B2_D void shadow_store(StateView const& s, u32 slot, ShadowSlot const& buf)
         s.field[size_t(i) * n + slot] = shadow_ptr(const_cast<ShadowSlot&>(buf).field)[i];
     B2_SHADOW_FIELDS(B2_X, D, P)
 #undef B2_X
+    {
+        Rng r;
+        for (int k = 0; k < 5; ++k)
+            r.x[k] = buf.rng[k];
+        r.d = buf.rng[5];
+        r.store(s, slot);
+    }
     if (s.pre_volume)
         s.pre_volume[slot] = buf.pre_volume;
 }

@@ -53,8 +53,11 @@ constexpr u32 INVALID = 0xffffffffu;
 
 // State-layout experiments (north-star (e): "coalesced, vectorised HBM gathers"), measured in
 // profiles/README_r02.md; both change only how the same bytes are arranged
+// Measured (TestEm3 bench, A/B in one gpurun call): packed RNG words 8.56e8 -> 8.71e8
+// track-steps/s (charged along-step 222 -> 211 us, pre-step 71.7 -> 69.0 us at the saturated
+// iteration): ON. Packed position/direction on top of it: 8.70e8, no change: OFF.
 #ifndef B2_RNG_PACKED
-#    define B2_RNG_PACKED 0
+#    define B2_RNG_PACKED 1
 #endif
 #ifndef B2_POSDIR_PACKED
 #    define B2_POSDIR_PACKED 0
