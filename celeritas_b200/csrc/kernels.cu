@@ -634,10 +634,15 @@ int b200_step_tracking_cut(B200ParamsView const* params,
 int b200_step_tally(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
 {
     StateView const& s = SV(state);
-    if (!s.calo_edep)
-        return 0;
-    k_tally<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s, s.num_detectors);
-    B2_COUNT(1);
+    // StepGatherAction<post> (user/detail/StepGatherAction.cc:70-99): SimpleCalo's tally,
+    // then the step/hit output for the callbacks that want whole steps
+    if (s.calo_edep)
+    {
+        k_tally<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s, s.num_detectors);
+        B2_COUNT(1);
+    }
+    if (s.hit_pre)
+        return b200_step_gather_hits(params, state, stream);
     return check_launch();
 }
 
@@ -647,6 +652,8 @@ int b200_step_post_tail(B200ParamsView const* params, B200StateView const* state
     StateView const& s = SV(state);
     k_post_tail<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s);
     B2_COUNT(1);
+    if (s.hit_pre)
+        return b200_step_gather_hits(params, state, stream);
     return check_launch();
 }
 

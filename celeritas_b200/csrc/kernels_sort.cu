@@ -22,6 +22,7 @@
 // (tests/test_gpu_track_order.py).
 //---------------------------------------------------------------------------//
 #include "launch_util.cuh"
+#include "orange.cuh"
 
 namespace b200
 {
@@ -34,6 +35,19 @@ B2_D u32 sort_key(StateView const& s, u32 slot, u32 order, u32 nkeys)
     u32 key;
     switch (order)
     {
+        case SORT_KEY_HITS: {
+            // StepGatherExecutor<post> (user/detail/StepGatherExecutor.hh:60-115): a step is
+            // recorded if the track stepped, started the step in a sensitive volume and
+            // (optionally) deposited energy
+            if (s.status[slot] == ST_INACTIVE)
+                return 1u;
+            u32 const vol = s.pre_volume[slot];
+            if (vol == INVALID || s.hit_detector_of_volume[vol] == INVALID)
+                return 1u;
+            if (s.hit_nonzero_edep && s.energy_deposition[slot] == 0)
+                return 1u;
+            return 0u;
+        }
         case ORDER_REINDEX_STATUS:
             // thrust::partition(IsNotInactive): active slots first
             return s.status[slot] != ST_INACTIVE ? 0u : 1u;
@@ -131,9 +145,63 @@ __global__ void __launch_bounds__(SORT_BLOCK)
         s.sort_slots[base + before + rank_in_warp] = slot;
     }
 }
+//! Compact hit records in slot order: record i is slot sort_slots[i], i < sort_offsets[1]
+//! (the reference: thrust::copy_if of the slots with a detector + gather_step_kernel,
+//! user/DetectorSteps.cu:36-93, 150-200)
+__global__ void __launch_bounds__(SORT_BLOCK)
+    k_hits_gather(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
+{
+    u32 const count = s.sort_offsets[1];
+    u32 const i = blockIdx.x * SORT_BLOCK + threadIdx.x;
+    if (i == 0)
+        *s.hit_count = count;
+    if (i >= count)
+        return;
+    size_t const n = s.num_slots;
+    u32 const slot = s.sort_slots[i];
+    s.hit_u32[i] = s.hit_detector_of_volume[s.pre_volume[slot]];
+    s.hit_u32[n + i] = s.track_id[slot];
+    s.hit_u32[2 * n + i] = s.event_id[slot];
+    s.hit_u32[3 * n + i] = s.parent_id[slot];
+    s.hit_u32[4 * n + i] = s.num_steps[slot];
+    s.hit_u32[5 * n + i] = s.particle_id[slot];
+    s.hit_f64[i] = s.step_length[slot];
+    s.hit_f64[n + i] = s.energy_deposition[slot];
+    for (u32 k = 0; k < 8; ++k)
+        s.hit_f64[(2 + k) * n + i] = s.hit_pre[k * n + slot];
+    GeoTrack geo(p, s, slot);
+    Real3 const pos = geo.pos(), dir = geo.dir();
+    s.hit_f64[10 * n + i] = s.time[slot];
+    for (u32 k = 0; k < 3; ++k)
+    {
+        s.hit_f64[(11 + k) * n + i] = pos[k];
+        s.hit_f64[(14 + k) * n + i] = dir[k];
+    }
+    s.hit_f64[17 * n + i] = s.energy[slot];
+}
 }  // namespace b200
 
 using namespace b200;
+
+//! Step/hit output of the step that just ran (order user_post, after the tallies): stable
+//! partition of the slots by "is a hit", then the gather. No-op without sensitive volumes.
+extern "C" int b200_step_gather_hits(B200ParamsView const* params,
+                                     B200StateView const* state,
+                                     cudaStream_t stream)
+{
+    StateView const& s = SV(state);
+    if (!s.hit_pre)
+        return 0;
+    if (!s.sort_slots || !s.sort_offsets || !s.sort_block_counts || !s.pre_volume)
+        return B200_ERR_INVALID_ARGUMENT;
+    u32 const nblocks = (s.num_slots + SORT_BLOCK - 1) / SORT_BLOCK;
+    k_sort_count<<<nblocks, SORT_BLOCK, 0, stream>>>(s, SORT_KEY_HITS, 1);
+    k_sort_scan<<<1, 1024, 0, stream>>>(s, 1, nblocks);
+    k_sort_scatter<<<nblocks, SORT_BLOCK, 0, stream>>>(s, SORT_KEY_HITS, 1);
+    k_hits_gather<<<nblocks, SORT_BLOCK, 0, stream>>>(PV(params), s);
+    B2_COUNT(4);
+    return check_launch();
+}
 
 extern "C" int b200_step_sort_tracks(B200ParamsView const* params,
                                      B200StateView const* state,

@@ -373,6 +373,20 @@ B2_D void do_pre_step(ParamsView const& p, StateView const& s, u32 slot)
     {
         GeoTrack geo(p, s, slot);
         s.pre_volume[slot] = geo.volume_id();
+        if (s.hit_pre)
+        {
+            // StepGatherExecutor<pre> (user/detail/StepGatherExecutor.hh:117-149): the
+            // pre-step point of every track that steps
+            size_t const n = s.num_slots;
+            Real3 const pos = geo.pos(), dir = geo.dir();
+            s.hit_pre[slot] = s.time[slot];
+            for (int k = 0; k < 3; ++k)
+            {
+                s.hit_pre[(1 + k) * n + slot] = pos[k];
+                s.hit_pre[(4 + k) * n + slot] = dir[k];
+            }
+            s.hit_pre[7 * n + slot] = s.energy[slot];
+        }
     }
     if (status == ST_ERRORED)
         return;

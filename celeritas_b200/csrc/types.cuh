@@ -136,7 +136,9 @@ enum TrackOrder : u32
     ORDER_REINDEX_ALONG_STEP_ACTION = 5,
     ORDER_REINDEX_STEP_LIMIT_ACTION = 6,
     ORDER_REINDEX_BOTH_ACTION = 7,
-    ORDER_SIZE_
+    ORDER_SIZE_,
+    // not a track order: key of the stable partition that compacts the step/hit output
+    SORT_KEY_HITS = 100
 };
 
 struct Real3

@@ -599,6 +599,16 @@ struct StateView
     real* calo_edep;                     // [detector] accumulated energy deposition [MeV]
     u32 num_detectors;
 
+    // Step/hit output (reference: StepCollector + DetectorSteps, user/DetectorSteps.cu): null
+    // when the problem has no sensitive volumes. Pre-step point per slot, and the compact hit
+    // records of the last step in slot order (csrc/kernels_sort.cu: k_hits_gather)
+    u32 const* hit_detector_of_volume;  // [volume] detector id or INVALID
+    u32 hit_nonzero_edep;               // drop steps without energy deposition
+    real* hit_pre;   // [8][slot]: time, pos xyz, dir xyz, energy at the pre-step point
+    u32* hit_u32;    // [6][slot]: detector, track, event, parent, track step count, particle
+    real* hit_f64;   // [18][slot]: step length, edep, pre {time, pos, dir, energy}, post {..}
+    u32* hit_count;  // [1] records written by the last step
+
     // step counters accumulated on device: {track-steps, step iterations}
     u64* step_counters;
 

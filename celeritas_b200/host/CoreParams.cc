@@ -86,8 +86,120 @@ bool CoreParams::has_action(std::string const& label) const
     return false;
 }
 
+namespace
+{
+//! The image is input: a truncated, stale or hand-edited file must fail at load, not turn
+//! into out-of-bounds reads inside the kernels. Checks the index columns against the columns
+//! they point into (INVALID = 0xffffffff is allowed where the format uses it as "none").
+void validate_image(Image const& img)
+{
+    auto fail = [](std::string const& what) {
+        throw std::runtime_error("inconsistent problem image: " + what);
+    };
+    auto u32 = [&](char const* n) { return img.get<uint32_t>(n); };
+    auto below = [&](char const* name, std::vector<uint32_t> const& v, size_t limit,
+                     bool allow_invalid) {
+        for (uint32_t x : v)
+            if (!(x < limit || (allow_invalid && x == 0xffffffffu)))
+                fail(std::string(name) + " holds " + std::to_string(x) + " (limit "
+                     + std::to_string(limit) + ")");
+    };
+    auto same = [&](char const* a, size_t na, char const* b, size_t nb) {
+        if (na != nb)
+            fail(std::string(a) + " and " + b + " differ in length (" + std::to_string(na)
+                 + ", " + std::to_string(nb) + ")");
+    };
+    auto ranges = [&](char const* name, std::vector<uint32_t> const& b,
+                      std::vector<uint32_t> const& e, size_t limit) {
+        same(name, b.size(), name, e.size());
+        for (size_t i = 0; i < b.size(); ++i)
+            if (b[i] > e[i] || e[i] > limit)
+                fail(std::string(name) + " range " + std::to_string(i) + " = ["
+                     + std::to_string(b[i]) + ", " + std::to_string(e[i]) + ") exceeds "
+                     + std::to_string(limit));
+    };
+
+    //// geometry
+    {
+        size_t const nsurf_ids = u32("geo.local_surface_ids").size();
+        size_t const nvol_ids = u32("geo.local_volume_ids").size();
+        size_t const nlogic = u32("geo.logic_ints").size();
+        size_t const nreals = img.get<double>("geo.reals").size();
+        auto utype = img.get<uint8_t>("geo.universe_type");
+        same("geo.universe_type", utype.size(), "geo.universe_index", u32("geo.universe_index").size());
+        if (u32("geo.universe_surface_offset").size() != utype.size() + 1
+            || u32("geo.universe_volume_offset").size() != utype.size() + 1)
+            fail("geo.universe_*_offset must have one entry per universe plus one");
+        ranges("geo.vol_face", u32("geo.vol_face_begin"), u32("geo.vol_face_end"), nsurf_ids);
+        ranges("geo.vol_logic", u32("geo.vol_logic_begin"), u32("geo.vol_logic_end"), nlogic);
+        ranges("geo.conn", u32("geo.conn_begin"), u32("geo.conn_end"), nvol_ids);
+        below("geo.real_ids", u32("geo.real_ids"), nreals, false);
+        same("geo.real_ids", u32("geo.real_ids").size(), "geo.surface_types",
+             img.get<uint8_t>("geo.surface_types").size());
+        size_t const nvol = u32("geo.vol_flags").size();
+        same("geo.vol_flags", nvol, "geo.vol_face_begin", u32("geo.vol_face_begin").size());
+        same("geo.vol_flags", nvol, "geo.vol_daughter", u32("geo.vol_daughter").size());
+        size_t const ndaughters = u32("geo.daughter_universe").size();
+        below("geo.vol_daughter", u32("geo.vol_daughter"), ndaughters, true);
+        below("geo.daughter_universe", u32("geo.daughter_universe"), utype.size(), false);
+        same("geo.daughter_universe", ndaughters, "geo.daughter_transform",
+             u32("geo.daughter_transform").size());
+        below("geo.daughter_transform", u32("geo.daughter_transform"),
+              u32("geo.transform_offset").size(), false);
+        if (u32("geo.simple_units").size() % 16 != 0 || u32("geo.rect_arrays").size() % 16 != 0)
+            fail("geo.simple_units / geo.rect_arrays must be rows of 16");
+        if (img.get<float>("geo.bih_bboxes").size() % 6 != 0)
+            fail("geo.bih_bboxes must be rows of 6");
+    }
+    if (!img.has("phys.dims"))
+        return;
+
+    //// materials, physics tables
+    {
+        size_t const nelem = u32("mat.element_z").size();
+        below("mat.elcomp_element", u32("mat.elcomp_element"), nelem, false);
+        ranges("mat.material_elcomp", u32("mat.material_elcomp_begin"),
+               u32("mat.material_elcomp_end"), u32("mat.elcomp_element").size());
+        size_t const nmat = u32("mat.material_elcomp_begin").size();
+        below("geomat.volume_material", u32("geomat.volume_material"), nmat, true);
+
+        auto dims = u32("phys.dims");
+        if (dims.size() < 4)
+            fail("phys.dims");
+        size_t const npart = dims[0], maxproc = dims[1], nmatp = dims[2], nmodels = dims[3];
+        if (nmatp != nmat)
+            fail("phys.dims and mat.* disagree on the number of materials");
+        auto gsize = u32("phys.grid_size");
+        auto goff = u32("phys.grid_value_offset");
+        size_t const ngrid = gsize.size();
+        size_t const nreals = img.get<double>("phys.reals").size();
+        same("phys.grid_size", ngrid, "phys.grid_value_offset", goff.size());
+        same("phys.grid_size", ngrid, "phys.grid_prime", u32("phys.grid_prime").size());
+        same("phys.grid_size", ngrid, "phys.grid_log_front",
+             img.get<double>("phys.grid_log_front").size());
+        same("phys.grid_size", ngrid, "phys.grid_log_delta",
+             img.get<double>("phys.grid_log_delta").size());
+        for (size_t g = 0; g < ngrid; ++g)
+            if (gsize[g] < 2 || size_t(goff[g]) + gsize[g] > nreals)
+                fail("phys grid " + std::to_string(g) + " exceeds phys.reals");
+        if (u32("phys.pp_grid").size() != 3 * npart * maxproc * nmat)
+            fail("phys.pp_grid must be [3][particle][process][material]");
+        below("phys.pp_grid", u32("phys.pp_grid"), ngrid, true);
+        below("phys.elsel_grid", u32("phys.elsel_grid"), ngrid, true);
+        if (u32("phys.pp_process").size() != npart * maxproc
+            || u32("phys.pp_model_begin").size() != npart * maxproc
+            || u32("phys.pp_num").size() != npart)
+            fail("phys.pp_* must be [particle][process]");
+        below("phys.pp_num", u32("phys.pp_num"), maxproc + 1, false);
+        below("phys.pmid_model", u32("phys.pmid_model"), nmodels, false);
+        below("phys.pm_pmid", u32("phys.pm_pmid"), u32("phys.pmid_model").size(), false);
+    }
+}
+}  // namespace
+
 void CoreParams::load(Image const& img)
 {
+    validate_image(img);
     auto U32 = [&](char const* n) { return arena_.upload(img.get<uint32_t>(n)); };
     auto F64 = [&](char const* n) { return arena_.upload(img.get<double>(n)); };
     auto F32 = [&](char const* n) { return arena_.upload(img.get<float>(n)); };
@@ -527,6 +639,30 @@ void CoreParams::load(Image const& img)
             }
             d_detector_of_volume_ = arena_.upload(det);
         }
+    }
+    //// STEP / HIT OUTPUT ////
+    if (img.has("hits.volumes"))
+    {
+        hit_volumes_ = split_lines(img.get_string("hits.volumes"));
+        hits_nonzero_edep_ = img.get_scalar<uint32_t>("hits.nonzero_edep") != 0;
+        std::vector<uint32_t> det(volume_labels_.size(), INVALID);
+        for (uint32_t d = 0; d < hit_volumes_.size(); ++d)
+        {
+            uint32_t found = 0;
+            for (uint32_t v = 0; v < volume_labels_.size(); ++v)
+            {
+                if (volume_labels_[v] == hit_volumes_[d])
+                {
+                    det[v] = d;
+                    ++found;
+                }
+            }
+            if (found != 1)
+                throw std::runtime_error("sensitive volume '" + hit_volumes_[d]
+                                         + "' is not a unique volume of the geometry");
+        }
+        if (!hit_volumes_.empty())
+            d_hit_detector_of_volume_ = arena_.upload(det);
     }
 }
 

@@ -61,6 +61,10 @@ class CoreParams
     //! Device table: global volume id -> detector id (empty if no detectors)
     uint32_t const* detector_of_volume() const { return d_detector_of_volume_; }
     uint32_t num_detectors() const { return detector_volumes_.size(); }
+    //! Sensitive volumes of the step/hit output (detector id = position) and their map
+    std::vector<std::string> const& hit_volumes() const { return hit_volumes_; }
+    uint32_t const* hit_detector_of_volume() const { return d_hit_detector_of_volume_; }
+    bool hits_nonzero_edep() const { return hits_nonzero_edep_; }
 
     uint32_t init_capacity() const { return init_capacity_; }
     uint32_t max_events() const { return max_events_; }
@@ -104,6 +108,9 @@ class CoreParams
     std::vector<double> particle_charge_;
     std::vector<std::string> detector_volumes_;
     uint32_t const* d_detector_of_volume_{nullptr};
+    std::vector<std::string> hit_volumes_;
+    uint32_t const* d_hit_detector_of_volume_{nullptr};
+    bool hits_nonzero_edep_{false};
     uint32_t init_capacity_{0};
     uint32_t max_events_{0};
     mutable bool frozen_{false};

@@ -156,8 +156,22 @@ CoreState::CoreState(std::shared_ptr<CoreParams const> params,
         s.interact_list = arena_.alloc<u32>(size_t(p.phys.num_models) * n);
         s.interact_count = arena_.alloc<u32>(16);
     }
-    // TrackOrder::reindex_*: the sorted slot permutation (csrc/kernels_sort.cu)
-    if (p.scalars.track_order >= ORDER_REINDEX_STATUS)
+    // Step/hit output
+    bool const hits = params_->hit_detector_of_volume() != nullptr;
+    if (hits)
+    {
+        if (!s.pre_volume)
+            s.pre_volume = arena_.alloc_fill<u32>(n, 0xff);
+        s.hit_detector_of_volume = params_->hit_detector_of_volume();
+        s.hit_nonzero_edep = params_->hits_nonzero_edep() ? 1u : 0u;
+        s.hit_pre = arena_.alloc<real>(size_t(8) * n);
+        s.hit_u32 = arena_.alloc<u32>(size_t(6) * n);
+        s.hit_f64 = arena_.alloc<real>(size_t(18) * n);
+        s.hit_count = arena_.alloc<u32>(1);
+    }
+    // TrackOrder::reindex_* and the hit compaction: the sorted slot permutation
+    // (csrc/kernels_sort.cu)
+    if (p.scalars.track_order >= ORDER_REINDEX_STATUS || hits)
     {
         uint32_t const nkeys = std::max<uint32_t>(
             std::max<uint32_t>(uint32_t(params_->actions().size()), p.particle.num_particles), 1u);
@@ -423,6 +437,63 @@ void CoreState::get_field(std::string const& f, void* out)
     {
         throw std::runtime_error("unknown state field '" + f + "'");
     }
+}
+
+uint32_t CoreState::hits_count()
+{
+    if (!view_.hit_count)
+        throw std::runtime_error("the problem has no sensitive volumes (hits.volumes)");
+    B2_CUDA_CALL(cudaStreamSynchronize(stream_));
+    uint32_t n = 0;
+    B2_CUDA_CALL(cudaMemcpy(&n, view_.hit_count, sizeof(n), cudaMemcpyDeviceToHost));
+    return n;
+}
+
+void CoreState::hits_get(std::string const& field, void* out)
+{
+    uint32_t const count = this->hits_count();
+    if (count == 0)
+        return;
+    size_t const n = view_.num_slots;
+    static char const* const u32_fields[]
+        = {"detector", "track_id", "event_id", "parent_id", "track_step_count", "particle"};
+    for (size_t k = 0; k < 6; ++k)
+    {
+        if (field == u32_fields[k])
+        {
+            B2_CUDA_CALL(cudaMemcpy(out, view_.hit_u32 + k * n, size_t(4) * count,
+                                    cudaMemcpyDeviceToHost));
+            return;
+        }
+    }
+    // double columns: 0 step_length, 1 edep, pre {2 time, 3-5 pos, 6-8 dir, 9 energy},
+    // post {10 time, 11-13 pos, 14-16 dir, 17 energy}
+    auto scalar = [&](size_t column) {
+        B2_CUDA_CALL(cudaMemcpy(out, view_.hit_f64 + column * n, size_t(8) * count,
+                                cudaMemcpyDeviceToHost));
+    };
+    auto vec3 = [&](size_t column) {
+        std::vector<double> soa(size_t(3) * count);
+        for (size_t k = 0; k < 3; ++k)
+            B2_CUDA_CALL(cudaMemcpy(soa.data() + k * count, view_.hit_f64 + (column + k) * n,
+                                    size_t(8) * count, cudaMemcpyDeviceToHost));
+        auto* o = static_cast<double*>(out);
+        for (size_t i = 0; i < count; ++i)
+            for (size_t k = 0; k < 3; ++k)
+                o[3 * i + k] = soa[k * count + i];
+    };
+    if (field == "step_length") scalar(0);
+    else if (field == "energy_deposition") scalar(1);
+    else if (field == "pre_time") scalar(2);
+    else if (field == "pre_pos") vec3(3);
+    else if (field == "pre_dir") vec3(6);
+    else if (field == "pre_energy") scalar(9);
+    else if (field == "post_time") scalar(10);
+    else if (field == "post_pos") vec3(11);
+    else if (field == "post_dir") vec3(14);
+    else if (field == "post_energy") scalar(17);
+    else
+        throw std::runtime_error("unknown hit field '" + field + "'");
 }
 
 void CoreState::calo_get(double* out)

@@ -72,6 +72,9 @@ class CoreState
 
     //! Copy a named per-slot field to host memory
     void get_field(std::string const& name, void* out);
+    //! Step/hit output of the last step iteration (csrc/kernels_sort.cu: k_hits_gather)
+    uint32_t hits_count();
+    void hits_get(std::string const& field, void* out);
     void calo_get(double* out);
     void calo_clear();
 

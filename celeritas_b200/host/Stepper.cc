@@ -249,8 +249,9 @@ ActionSequence::ActionSequence(CoreParams const& params, Options options)
         if (user->order() >= Order::pre && user->order() <= Order::user_post)
             fusable_ = false;
     }
-    // A sort action has to see the state between two groups of the fused launch
-    if (have_sort)
+    // A sort action has to see the state between two groups of the fused launch; the
+    // step/hit output is gathered after every iteration by the tally launch
+    if (have_sort || params.hit_detector_of_volume())
         fusable_ = false;
     fuse_threshold_ = options.fuse_threshold ? options.fuse_threshold : default_fuse_threshold;
     if (char const* env = std::getenv("B200_FUSE_THRESHOLD"))

@@ -364,6 +364,20 @@ int b200_stepper_advance(B200Stepper* stepper,
     });
 }
 
+int b200_stepper_hits_count(B200Stepper* stepper, uint32_t* count)
+{
+    if (!stepper || !count)
+        return B200_ERR_INVALID_ARGUMENT;
+    return guarded([&] { *count = stepper->stepper->state().hits_count(); });
+}
+
+int b200_stepper_hits_get(B200Stepper* stepper, char const* field, void* out)
+{
+    if (!stepper || !field || !out)
+        return B200_ERR_INVALID_ARGUMENT;
+    return guarded([&] { stepper->stepper->state().hits_get(field, out); });
+}
+
 uint64_t b200_stepper_tail_iterations(B200Stepper const* stepper)
 {
     return stepper->stepper->tail_iterations();

@@ -69,6 +69,7 @@ EXPORTS = [
     'b200_stepper_advance', 'b200_stepper_tail_iterations',
     'b200_params_create_from_memory', 'b200_stepper_insert', 'b200_stepper_begin_iteration',
     'b200_stepper_end_iteration', 'b200_stepper_stream', 'b200_step_sort_tracks',
+    'b200_step_gather_hits', 'b200_stepper_hits_count', 'b200_stepper_hits_get',
 ]
 
 _lib = None
@@ -102,6 +103,8 @@ def load_library():
     L.b200_stepper_stream.argtypes = [vp]
     L.b200_stepper_stream.restype = vp
     L.b200_step_sort_tracks.argtypes = [vp, vp, C.c_uint32, vp]
+    L.b200_stepper_hits_count.argtypes = [vp, C.POINTER(C.c_uint32)]
+    L.b200_stepper_hits_get.argtypes = [vp, C.c_char_p, vp]
     L.b200_params_view.restype = vp
     L.b200_params_view.argtypes = [vp]
     L.b200_params_num_actions.argtypes = [vp]
@@ -204,6 +207,16 @@ FIELDS = {
     'dedx_range': ('<f8', 1), 'rng': ('<u4', 6), 'pos': ('<f8', 3), 'dir': ('<f8', 3),
     'volume_id': ('<u4', 1), 'surface_id': ('<u4', 1), 'geo_level': ('<u4', 1),
     'sort_slots': ('<u4', 1),
+}
+
+
+HIT_FIELDS = {
+    'detector': ('<u4', 1), 'track_id': ('<u4', 1), 'event_id': ('<u4', 1),
+    'parent_id': ('<u4', 1), 'track_step_count': ('<u4', 1), 'particle': ('<u4', 1),
+    'step_length': ('<f8', 1), 'energy_deposition': ('<f8', 1),
+    'pre_time': ('<f8', 1), 'pre_energy': ('<f8', 1), 'pre_pos': ('<f8', 3), 'pre_dir': ('<f8', 3),
+    'post_time': ('<f8', 1), 'post_energy': ('<f8', 1), 'post_pos': ('<f8', 3),
+    'post_dir': ('<f8', 3),
 }
 
 
@@ -398,6 +411,20 @@ class Stepper:
         dt, w = FIELDS[field]
         out = np.zeros((self.n, w) if w > 1 else self.n, dtype=dt)
         _check(L.b200_state_get(L.b200_stepper_state(self.h), field.encode(), out.ctypes.data))
+        return out
+
+    def hits(self):
+        """Step/hit output of the last step iteration (reference: DetectorStepOutput) as a
+        dict of arrays, one entry per hit, in track-slot order."""
+        L = load_library()
+        n = C.c_uint32()
+        _check(L.b200_stepper_hits_count(self.h, C.byref(n)))
+        out = {}
+        for name, (dt, w) in HIT_FIELDS.items():
+            a = np.zeros((n.value, w) if w > 1 else n.value, dtype=dt)
+            if n.value:
+                _check(L.b200_stepper_hits_get(self.h, name.encode(), a.ctypes.data))
+            out[name] = a
         return out
 
     def sort_offsets(self):

@@ -171,6 +171,11 @@ int b200_step_interact(B200ParamsView const*, B200StateView const*, cudaStream_t
 int b200_step_boundary(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_step_tracking_cut(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_step_tally(B200ParamsView const*, B200StateView const*, cudaStream_t);
+/* Step/hit output of the step that just ran (reference: StepCollector + DetectorSteps,
+ * src/celeritas/user/DetectorSteps.cu:150-200): compact records, in slot order, of the tracks
+ * that started the step in a sensitive volume ("hits.volumes" of the image). Called by
+ * b200_step_tally / b200_step_post_tail; read back with b200_stepper_hits_count / _get. */
+int b200_step_gather_hits(B200ParamsView const*, B200StateView const*, cudaStream_t);
 int b200_step_extend_from_secondaries(B200ParamsView const*, B200StateView const*, cudaStream_t);
 /* SortTracksAction::step (src/celeritas/track/SortTracksAction.cc:100-131) for problems whose
  * track order is one of TrackOrder::reindex_* (src/celeritas/Types.hh:151-171): rebuilds the
@@ -305,6 +310,12 @@ int b200_stepper_insert(B200Stepper* stepper, B200Primary const* primaries, uint
 int b200_stepper_begin_iteration(B200Stepper* stepper);
 int b200_stepper_end_iteration(B200Stepper* stepper, B200StepperResult* result);
 cudaStream_t b200_stepper_stream(B200Stepper* stepper);
+/* Hits of the last step iteration (reference: DetectorStepOutput, user/DetectorSteps.hh:38-72).
+ * Fields: detector track_id event_id parent_id track_step_count particle (uint32), step_length
+ * energy_deposition pre_time pre_energy post_time post_energy (double), pre_pos pre_dir post_pos
+ * post_dir (double[3] per hit). `out` holds *count elements of the field. */
+int b200_stepper_hits_count(B200Stepper* stepper, uint32_t* count);
+int b200_stepper_hits_get(B200Stepper* stepper, char const* field, void* out);
 /* Iterations that ran inside the device-resident loop since the stepper was created */
 uint64_t b200_stepper_tail_iterations(B200Stepper const* stepper);
 int b200_stepper_warm_up(B200Stepper* stepper);

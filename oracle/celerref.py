@@ -55,6 +55,9 @@ def lib():
         L.celerref_state_get.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
         L.celerref_calo_get.argtypes = [C.c_void_p, C.c_void_p]
         L.celerref_calo_clear.argtypes = [C.c_void_p]
+        L.celerref_hits_count.argtypes = [C.c_void_p, C.c_uint32]
+        L.celerref_hits_count.restype = C.c_uint32
+        L.celerref_hits_get.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_void_p]
         L.celerref_geo_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                          C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]
@@ -91,6 +94,16 @@ FIELDS = {
 }
 
 
+HIT_FIELDS = {
+    'detector': ('<u4', 1), 'track_id': ('<u4', 1), 'event_id': ('<u4', 1),
+    'parent_id': ('<u4', 1), 'track_step_count': ('<u4', 1), 'particle': ('<u4', 1),
+    'step_length': ('<f8', 1), 'energy_deposition': ('<f8', 1),
+    'pre_time': ('<f8', 1), 'pre_energy': ('<f8', 1), 'pre_pos': ('<f8', 3), 'pre_dir': ('<f8', 3),
+    'post_time': ('<f8', 1), 'post_energy': ('<f8', 1), 'post_pos': ('<f8', 3),
+    'post_dir': ('<f8', 3),
+}
+
+
 class Problem:
     def __init__(self, config):
         config = dict(config)
@@ -113,6 +126,18 @@ class Problem:
 
     def calo_clear(self):
         _check(lib().celerref_calo_clear(self.h))
+
+    def hits(self, stream=0):
+        """Step/hit output of the last step (the reference's DetectorStepOutput) as a dict
+        of arrays; requires 'hit_volumes' in the problem configuration."""
+        n = lib().celerref_hits_count(self.h, stream)
+        out = {}
+        for name, (dt, w) in HIT_FIELDS.items():
+            a = np.zeros((n, w) if w > 1 else n, dtype=dt)
+            if n:
+                _check(lib().celerref_hits_get(self.h, stream, name.encode(), a.ctypes.data))
+            out[name] = a
+        return out
 
     def trace(self, pos, direction, max_segments=64):
         """Ray-trace with the reference's OrangeTrackView (same outputs as Params.trace)."""

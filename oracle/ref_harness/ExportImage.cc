@@ -944,6 +944,15 @@ b200::Image build_image(Problem const& prob)
             names += n + "\n";
         img.put_string("calo.volumes", names);
     }
+    // Sensitive volumes of the step/hit output (HitRecorder): detector id = position
+    if (prob.hits)
+    {
+        std::string names;
+        for (auto const& n : prob.hit_volumes)
+            names += n + "\n";
+        img.put_string("hits.volumes", names);
+        img.put_scalar<uint32_t>("hits.nonzero_edep", prob.hits_nonzero_edep ? 1u : 0u);
+    }
 
     return img;
 }

@@ -561,6 +561,28 @@ std::unique_ptr<Problem> build_problem(json const& config)
     }
     p->core = std::make_shared<CoreParams>(std::move(params));
 
+    if (cfg.contains("hit_volumes"))
+    {
+        // Sensitive detectors with full step output (instead of a calorimeter tally: one
+        // volume cannot feed two step interfaces, user/detail/StepParams.cc:60-70)
+        CELER_VALIDATE(!cfg.contains("simple_calo"),
+                       << "'hit_volumes' and 'simple_calo' are mutually exclusive");
+        std::vector<VolumeId> vols;
+        for (auto const& s : cfg.at("hit_volumes"))
+        {
+            p->hit_volumes.push_back(s.get<std::string>());
+            VolumeId v = p->core->geometry()->volumes().find_unique(s.get<std::string>());
+            CELER_VALIDATE(v, << "no volume '" << s.get<std::string>() << "'");
+            vols.push_back(v);
+        }
+        p->hits_nonzero_edep = cfg.value("hits_nonzero_edep", false);
+        p->hits = std::make_shared<HitRecorder>(std::move(vols), p->hits_nonzero_edep);
+        StepCollector::VecInterface ifaces{p->hits};
+        p->collector = std::make_shared<StepCollector>(p->core->geometry(),
+                                                       std::move(ifaces),
+                                                       p->core->aux_reg().get(),
+                                                       p->core->action_reg().get());
+    }
     if (cfg.contains("simple_calo"))
     {
         std::vector<Label> labels;
@@ -591,5 +613,38 @@ std::unique_ptr<Problem> build_problem(json const& config)
             *p->core, cfg.at("step_diagnostic_bins").get<size_type>());
     }
     return p;
+}
+//---------------------------------------------------------------------------//
+auto HitRecorder::filters() const -> Filters
+{
+    Filters f;
+    for (std::size_t i = 0; i < volumes_.size(); ++i)
+        f.detectors[volumes_[i]] = DetectorId{static_cast<DetectorId::size_type>(i)};
+    f.nonzero_energy_deposition = nonzero_edep_;
+    return f;
+}
+
+StepSelection HitRecorder::selection() const
+{
+    StepSelection sel = StepSelection::all();
+    sel.action_id = false;
+    for (auto& point : sel.points)
+        point.volume_id = false;
+    return sel;
+}
+
+void HitRecorder::process_steps(HostStepState state)
+{
+    copy_steps(&last_.at(state.stream_id.get()), state.steps);
+}
+
+void HitRecorder::process_steps(DeviceStepState state)
+{
+    copy_steps(&last_.at(state.stream_id.get()), state.steps);
+}
+
+DetectorStepOutput const& HitRecorder::last(unsigned stream) const
+{
+    return last_.at(stream);
 }
 }  // namespace celerref

@@ -23,10 +23,35 @@
 #include "celeritas/user/ActionDiagnostic.hh"
 #include "celeritas/user/SimpleCalo.hh"
 #include "celeritas/user/StepDiagnostic.hh"
+#include "celeritas/user/DetectorSteps.hh"
 #include "celeritas/user/StepCollector.hh"
+#include "celeritas/user/StepInterface.hh"
 
 namespace celerref
 {
+//! Step/hit output of the reference, kept per step: a StepInterface whose callback runs the
+//! reference's own compaction (copy_steps, user/DetectorSteps.{cc,cu}) and keeps the result
+//! ("hit_volumes": [...] and "hits_nonzero_edep": bool in the problem configuration)
+class HitRecorder final : public celeritas::StepInterface
+{
+  public:
+    HitRecorder(std::vector<celeritas::VolumeId> volumes, bool nonzero_edep)
+        : volumes_(std::move(volumes)), nonzero_edep_(nonzero_edep)
+    {
+    }
+    Filters filters() const final;
+    celeritas::StepSelection selection() const final;
+    void process_steps(HostStepState) final;
+    void process_steps(DeviceStepState) final;
+    //! Hits of the last step of the given stream
+    celeritas::DetectorStepOutput const& last(unsigned stream = 0) const;
+
+  private:
+    std::vector<celeritas::VolumeId> volumes_;
+    bool nonzero_edep_;
+    std::vector<celeritas::DetectorStepOutput> last_{8};
+};
+
 struct Problem
 {
     nlohmann::json config;
@@ -36,6 +61,9 @@ struct Problem
     std::shared_ptr<celeritas::OrangeParams const> geo;
     std::shared_ptr<celeritas::SimpleCalo> calo;
     std::shared_ptr<celeritas::StepCollector> collector;
+    std::shared_ptr<HitRecorder> hits;
+    std::vector<std::string> hit_volumes;
+    bool hits_nonzero_edep{false};
     std::vector<std::string> calo_volumes;
     //! celer-sim diagnostics ("action_diagnostic": true, "step_diagnostic_bins": N)
     std::shared_ptr<celeritas::ActionDiagnostic> action_diag;

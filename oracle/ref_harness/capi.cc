@@ -32,6 +32,9 @@
 #include "celeritas/phys/PrimaryGeneratorOptionsIO.json.hh"
 #include "celeritas/random/RngEngine.hh"
 
+#include "celeritas/user/DetectorSteps.hh"
+#include "celeritas/user/StepData.hh"
+
 #include "Problem.hh"
 
 using namespace celeritas;
@@ -306,6 +309,72 @@ int celerref_calo_get(void* problem, double* out)
         CELER_VALIDATE(p->calo, << "no simple_calo in this problem");
         auto v = p->calo->calc_total_energy_deposition();
         std::copy(v.begin(), v.end(), out);
+    });
+}
+
+//! Hits of the last step (HitRecorder): count, then one named field at a time.
+//! Fields: detector track_id event_id parent_id track_step_count particle (u32),
+//! step_length energy_deposition pre_time pre_energy post_time post_energy (f64),
+//! pre_pos pre_dir post_pos post_dir (f64 x 3)
+uint32_t celerref_hits_count(void* problem, uint32_t stream)
+{
+    auto* p = static_cast<celerref::Problem*>(problem);
+    return p->hits ? p->hits->last(stream).size() : 0;
+}
+
+int celerref_hits_get(void* problem, uint32_t stream, char const* field, void* out)
+{
+    return guarded([&] {
+        auto* p = static_cast<celerref::Problem*>(problem);
+        CELER_VALIDATE(p->hits, << "no hit_volumes in this problem");
+        DetectorStepOutput const& h = p->hits->last(stream);
+        std::string f = field;
+        auto* o32 = static_cast<uint32_t*>(out);
+        auto* o64 = static_cast<double*>(out);
+        auto ids = [&](auto const& v) {
+            CELER_VALIDATE(v.size() == h.size(), << "field '" << f << "' was not collected");
+            for (size_type i = 0; i < v.size(); ++i)
+                o32[i] = v[i].unchecked_get();
+        };
+        auto point = [&](DetectorStepPointOutput const& pt, std::string const& name) {
+            if (name == "time")
+                std::copy(pt.time.begin(), pt.time.end(), o64);
+            else if (name == "energy")
+                for (size_type i = 0; i < pt.energy.size(); ++i)
+                    o64[i] = pt.energy[i].value();
+            else if (name == "pos" || name == "dir")
+            {
+                auto const& v = name == "pos" ? pt.pos : pt.dir;
+                for (size_type i = 0; i < v.size(); ++i)
+                    for (int k = 0; k < 3; ++k)
+                        o64[3 * i + k] = v[i][k];
+            }
+            else
+                CELER_VALIDATE(false, << "unknown hit field '" << f << "'");
+        };
+        if (f == "detector")
+            ids(h.detector);
+        else if (f == "track_id")
+            ids(h.track_id);
+        else if (f == "event_id")
+            ids(h.event_id);
+        else if (f == "parent_id")
+            ids(h.parent_id);
+        else if (f == "particle")
+            ids(h.particle);
+        else if (f == "track_step_count")
+            std::copy(h.track_step_count.begin(), h.track_step_count.end(), o32);
+        else if (f == "step_length")
+            std::copy(h.step_length.begin(), h.step_length.end(), o64);
+        else if (f == "energy_deposition")
+            for (size_type i = 0; i < h.energy_deposition.size(); ++i)
+                o64[i] = h.energy_deposition[i].value();
+        else if (f.rfind("pre_", 0) == 0)
+            point(h.points[StepPoint::pre], f.substr(4));
+        else if (f.rfind("post_", 0) == 0)
+            point(h.points[StepPoint::post], f.substr(5));
+        else
+            CELER_VALIDATE(false, << "unknown hit field '" << f << "'");
     });
 }
 

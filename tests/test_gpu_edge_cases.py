@@ -116,3 +116,36 @@ def test_event_id_out_of_range_is_rejected():
     with pytest.raises(cb.B200Error) as err:
         gpu.step(prim)
     assert 'max_events' in str(err.value)
+
+
+def test_corrupt_images_fail_at_load(tmp_path):
+    """A truncated or hand-edited problem image is rejected by the loader (index columns are
+    checked against the columns they point into) instead of becoming out-of-bounds device
+    reads inside the kernels."""
+    import celeritas_b200 as cb
+    raw = open(data_path('images', 'testem3-small.b2img'), 'rb').read()
+
+    def patched(name, value, index=0):
+        key = name.encode()
+        at = raw.index(len(key).to_bytes(4, 'little') + key) + 4 + len(key) + 12 + 4 * index
+        return raw[:at] + int(value).to_bytes(4, 'little') + raw[at + 4:]
+
+    cases = {
+        'truncated': raw[:len(raw) // 2],
+        'grid id out of range': patched('phys.pp_grid', 1000),
+        'grid beyond the value pool': patched('phys.grid_value_offset', 1 << 30),
+        'material id out of range': patched('geomat.volume_material', 77, index=3),
+        'surface id range': patched('geo.vol_face_end', 1 << 20, index=5),
+        'element id out of range': patched('mat.elcomp_element', 99),
+    }
+    for what, data in cases.items():
+        path = tmp_path / 'bad.b2img'
+        path.write_bytes(data)
+        with pytest.raises(cb.B200Error) as e:
+            cb.Params(str(path))
+        assert 'image' in str(e.value), (what, str(e.value))
+        with pytest.raises(cb.B200Error):
+            cb.Params(image_bytes=data)
+    # the untouched bytes load from memory as well as from the file
+    assert cb.Params(image_bytes=raw).num_detectors == cb.Params(
+        data_path('images', 'testem3-small.b2img')).num_detectors
