@@ -45,11 +45,11 @@ NUM_STREAMS = 2
 ALG_BYTES_PER_TRACK_STEP = 672  # 2 * S_live, D=1, P=4
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE along-step launch (charged + neutral
 # kernels) at a saturated iteration (all 2^20 slots live), from `ncu --set full`
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 137.8e6 + 131.6e6 + 122.8e6 + 51.0e6
-NCU_TRAFFIC_SOURCE = ('profiles/saturated_kernels_r01e.txt: k_along_step_charged<0> + '
-                      'k_along_step_neutral at one saturated iteration (1.05e6 live tracks = '
-                      '7.0e8 algorithmic bytes at 672 B per track-step for the WHOLE step; the '
-                      'along-step touches about two thirds of the per-slot state)')
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 135.6e6 + 86.0e6 + 90.1e6 + 27.0e6
+NCU_TRAFFIC_SOURCE = ('profiles/layout_variants_r02.txt, section "rng" (the shipped layout): '
+                      'k_along_step_charged<0,0> + k_along_step_neutral<0> at one saturated '
+                      'iteration of this workload (launch 900 of the per-action kernels), '
+                      'dram__bytes_read.sum + dram__bytes_write.sum')
 
 
 # --workload: the headline (BASELINE configs[1]), simple-CMS (configs[2]) and the CMS-scale
