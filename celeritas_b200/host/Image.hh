@@ -89,6 +89,9 @@ class Image
         this->put(name, std::vector<uint8_t>(s.begin(), s.end()));
     }
 
+    //! Insert or replace a whole entry (e.g. a column taken from another image)
+    void put_entry(std::string const& name, ImageEntry const& entry) { entries_[name] = entry; }
+
     bool has(std::string const& name) const { return entries_.count(name) != 0; }
 
     template<class T>

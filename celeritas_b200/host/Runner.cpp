@@ -2,6 +2,9 @@
 // celer-sim front end (see Runner.hh).
 //---------------------------------------------------------------------------//
 #include "Runner.hh"
+#include "OrangeBuilder.hh"
+
+#include <fstream>
 
 #include <chrono>
 #include <cstring>
@@ -286,8 +289,29 @@ std::string celer_sim_run(std::string const& input_json)
         throw std::runtime_error("track_order '" + inp.track_order + "' is not supported");
     }
 
-    std::shared_ptr<CoreParams> params
-        = CoreParams::from_image(resolve(inp.base_dir, inp.image_file));
+    // The problem image carries materials, physics tables and the action table; the GEOMETRY
+    // is built here from `geometry_file` when that is an ORANGE JSON file that exists
+    // (host/OrangeBuilder.cpp: the reference's OrangeParams construction), and must be the
+    // geometry the image's volume -> material map was exported for.
+    b200::Image image = b200::Image::read(resolve(inp.base_dir, inp.image_file));
+    {
+        std::string const geo_path = resolve(inp.base_dir, inp.geometry_file);
+        bool const is_org_json = geo_path.size() > 9
+                                 && geo_path.compare(geo_path.size() - 9, 9, ".org.json") == 0;
+        if (is_org_json && std::ifstream(geo_path).good())
+        {
+            b200::Image const geo = build_orange_image(geo_path);
+            if (geo.get_string("geo.volume_labels") != image.get_string("geo.volume_labels"))
+                throw std::runtime_error(
+                    "geometry_file '" + inp.geometry_file
+                    + "' is not the geometry the problem image was exported for (volume "
+                      "labels differ)");
+            for (auto const& kv : geo.entries())
+                if (kv.first.rfind("geo.", 0) == 0)
+                    image.put_entry(kv.first, kv.second);
+        }
+    }
+    std::shared_ptr<CoreParams> params = CoreParams::from_image(image);
     bool const no_field = inp.field[0] == 0 && inp.field[1] == 0 && inp.field[2] == 0;
     if (!no_field)
         params->uniform_field_tesla(inp.field);

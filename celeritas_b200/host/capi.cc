@@ -13,6 +13,7 @@
 #include "CoreParams.hh"
 #include "CoreState.hh"
 #include "Handles.hh"
+#include "OrangeBuilder.hh"
 #include "Stepper.hh"
 #include "Transporter.hh"
 
@@ -99,6 +100,40 @@ int b200_params_create_from_memory(void const* image, size_t size, B200Params** 
     return guarded([&] {
         auto p = std::make_unique<B200Params>();
         p->params = CoreParams::from_image(b200::Image::parse(image, size));
+        *out = p.release();
+    });
+}
+
+int b200_orange_build_image(char const* org_json_path, void** image, size_t* size)
+{
+    if (!org_json_path || !image || !size)
+        return B200_ERR_INVALID_ARGUMENT;
+    *image = nullptr;
+    *size = 0;
+    return guarded([&] {
+        std::vector<unsigned char> const bytes = build_orange_image(org_json_path).serialize();
+        void* out = std::malloc(bytes.size());
+        if (!out)
+            throw std::runtime_error("out of memory");
+        std::memcpy(out, bytes.data(), bytes.size());
+        *image = out;
+        *size = bytes.size();
+    });
+}
+
+int b200_params_create_from_org_json(char const* org_json_path, B200Params** out)
+{
+    if (!org_json_path || !out)
+        return B200_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (b200_device_count() == 0)
+    {
+        g_error = "no CUDA device available (this library has no CPU path)";
+        return B200_ERR_NO_DEVICE;
+    }
+    return guarded([&] {
+        auto p = std::make_unique<B200Params>();
+        p->params = CoreParams::from_image(build_orange_image(org_json_path));
         *out = p.release();
     });
 }

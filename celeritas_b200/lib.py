@@ -70,6 +70,7 @@ EXPORTS = [
     'b200_params_create_from_memory', 'b200_stepper_insert', 'b200_stepper_begin_iteration',
     'b200_stepper_end_iteration', 'b200_stepper_stream', 'b200_step_sort_tracks',
     'b200_step_gather_hits', 'b200_stepper_hits_count', 'b200_stepper_hits_get',
+    'b200_orange_build_image', 'b200_params_create_from_org_json',
 ]
 
 _lib = None
@@ -97,6 +98,9 @@ def load_library():
     L.b200_params_create_from_image.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.b200_params_create_from_memory.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(vp)]
     L.b200_params_destroy.argtypes = [vp]
+    L.b200_orange_build_image.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.b200_params_create_from_org_json.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.b200_string_free.argtypes = [vp]
     L.b200_stepper_insert.argtypes = [vp, vp, C.c_uint32]
     L.b200_stepper_begin_iteration.argtypes = [vp]
     L.b200_stepper_end_iteration.argtypes = [vp, C.POINTER(StepperResult)]
@@ -220,13 +224,29 @@ HIT_FIELDS = {
 }
 
 
+def orange_build_image(org_json_path):
+    """The geometry image of an .org.json file built by the library's own ORANGE
+    construction (host only): bytes of a .b2img container."""
+    L = load_library()
+    ptr, size = C.c_void_p(), C.c_size_t()
+    _check(L.b200_orange_build_image(os.fspath(org_json_path).encode(), C.byref(ptr),
+                                     C.byref(size)))
+    try:
+        return C.string_at(ptr, size.value)
+    finally:
+        L.b200_string_free(ptr)
+
+
 class Params:
     """Problem parameters in HBM (reference: CoreParams)."""
 
-    def __init__(self, image_path=None, image_bytes=None):
+    def __init__(self, image_path=None, image_bytes=None, org_json=None):
         L = load_library()
         h = C.c_void_p()
-        if image_bytes is not None:
+        if org_json is not None:
+            # geometry built natively from the reference's ORANGE JSON input
+            _check(L.b200_params_create_from_org_json(os.fspath(org_json).encode(), C.byref(h)))
+        elif image_bytes is not None:
             # hand-off in memory (b200_params_create_from_memory)
             buf = bytes(image_bytes)
             _check(L.b200_params_create_from_memory(buf, C.c_size_t(len(buf)), C.byref(h)))

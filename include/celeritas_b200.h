@@ -35,6 +35,7 @@
 #ifndef CELERITAS_B200_H
 #define CELERITAS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -124,6 +125,13 @@ int b200_params_create_from_image(char const* image_path, B200Params** out);
  * CoreParams::host_ref() on the reference side (src/celeritas/global/CoreParams.hh:155-172)
  * without a file in between; the bytes are not referenced after the call returns. */
 int b200_params_create_from_memory(void const* image, size_t size, B200Params** out);
+/* Native ORANGE construction (reference: OrangeParams(OrangeInput&&),
+ * src/orange/OrangeParams.cc:137-209 with UnitInserter / RectArrayInserter / BIHBuilder): the
+ * geometry image of an .org.json file, column for column what the reference builds. The image
+ * bytes are malloc'ed (free with b200_string_free); host-only, needs no GPU. */
+int b200_orange_build_image(char const* org_json_path, void** image, size_t* size);
+/* Geometry-only problem (navigation, b200_geo_trace) straight from an .org.json file. */
+int b200_params_create_from_org_json(char const* org_json_path, B200Params** out);
 void b200_params_destroy(B200Params* params);
 B200ParamsView const* b200_params_view(B200Params const* params);
 /* Problem metadata */

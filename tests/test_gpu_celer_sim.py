@@ -252,3 +252,31 @@ def test_celer_sim_input_errors():
         with pytest.raises(cb.B200Error) as err:
             cb.celer_sim_run(inp)
         assert fragment in str(err.value), (change, str(err.value))
+
+
+def test_celer_sim_builds_the_geometry_from_geometry_file(tmp_path):
+    """`geometry_file` is read: the ORANGE JSON file is built natively and
+    replaces the image's geometry columns; a file that describes another geometry than the
+    one the image's materials were exported for is refused."""
+    import celeritas_b200 as cb
+    cfg = json.load(open(data_path('images', 'testem3-small.json')))
+    run_input = {
+        '_format': 'celer-sim', 'use_device': True,
+        'image_file': 'data/images/testem3-small.b2img', 'base_dir': REPO,
+        'geometry_file': cfg['geometry_file'], 'physics_file': cfg['physics_file'],
+        'primary_options': dict(PRIMARY_OPTIONS, num_events=1, primaries_per_event=2, pdg=[11]),
+        'seed': cfg['seed'], 'num_track_slots': 2048,
+        'initializer_capacity': cfg['initializer_capacity'], 'secondary_stack_factor': 3,
+        'simple_calo': cfg['simple_calo'],
+    }
+    good = cb.celer_sim_run(run_input)
+    assert good['result']['runner']['num_steps'][0] > 100
+    # the same run with the geometry columns of the image (file missing -> image geometry)
+    moved = dict(run_input, geometry_file='data/geometry/does-not-exist.org.json')
+    same = cb.celer_sim_run(moved)
+    assert same['result']['runner']['num_steps'] == good['result']['runner']['num_steps']
+    assert same['result']['runner']['active'] == good['result']['runner']['active']
+    wrong = dict(run_input, geometry_file='data/geometry/simple-cms.org.json')
+    with pytest.raises(cb.B200Error) as e:
+        cb.celer_sim_run(wrong)
+    assert 'geometry_file' in str(e.value)

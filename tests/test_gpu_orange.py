@@ -67,3 +67,22 @@ def test_reference_golden_tracks():
     for geometry, pos, direction, names, dist in GOLDEN:
         gpu = cb.Params(data_path('images', 'geo-%s.b2img' % geometry))
         check_trace(gpu.trace, geometry, pos, direction, names, dist)
+
+
+@pytest.mark.parametrize('name', ['cms-scale', 'many-faces', 'universes', 'nested-rect-arrays',
+                                  'hex-array', 'testem3'])
+def test_trace_with_natively_built_geometry(name):
+    """The geometry built by the library's own ORANGE construction from the .org.json file
+    (celeritas_b200/host/OrangeBuilder.cpp; tests/test_cpu_orange_builder.py shows it equals
+    the reference-built image column for column) traced against the reference."""
+    import celeritas_b200 as cb
+    import celerref
+    ref = celerref.Problem({'problem': 'geometry',
+                            'geometry_file': 'data/geometry/%s.org.json' % name})
+    gpu = cb.Params(org_json=data_path('geometry', name + '.org.json'))
+    pos, d = ray_set(name, 2048, 11)
+    rv, rs, rd, rc, rsafe = ref.trace(pos, d, 256)
+    gv, gs, gd, gc, gsafe = gpu.trace(pos, d, 256)
+    assert np.array_equal(rc, gc) and np.array_equal(rv, gv) and np.array_equal(rs, gs)
+    assert np.array_equal(rd, gd) and np.array_equal(rsafe, gsafe)
+    assert (rc != 0xffffffff).sum() > 500
