@@ -86,6 +86,12 @@ WORKLOADS = {
 }
 
 
+# The CMS-scale problem at 1000 x 10 primaries per GPU: the track slots saturate and the pass is
+# throughput-bound; at 100 x 10 half of the pass is the latency of looping-track chains, whose
+# length differs from one rank's events to another's (profiles/README_r02.md)
+WORKLOADS['cms-scale-10k'] = dict(WORKLOADS['cms-scale'], events=1000, per_event=10)
+
+
 def make_workload_events(workload, params_or_problem, num_events, per_event, first_event, dtype):
     """Primaries of one rank: events [first_event, first_event + num_events)."""
     if workload == 'testem3':
@@ -530,12 +536,14 @@ def main():
     extra = {}
     strong = None
     if not args.no_extra and args.workload == 'testem3':
-        for name in ('cms-scale', 'simple-cms'):
+        for name in ('cms-scale', 'cms-scale-10k', 'simple-cms'):
             if name == 'simple-cms' and world > 1:
                 continue  # configs[4] is the CMS-scale sweep
             w = WORKLOADS[name]
-            extra[name] = run_b200(args, name, 3, 3, rank, local_rank, world, dist,
-                                   w['events'], w['per_event'], with_roofline=(world == 1))
+            big = name == 'cms-scale-10k'
+            extra[name] = run_b200(args, name, 2 if big else 3, 3, rank, local_rank, world, dist,
+                                   w['events'], w['per_event'],
+                                   with_roofline=(world == 1 and not big))
         if world > 1 and args.events % world == 0:
             # strong scaling: the SAME 100 x 100 primaries split over the N GPUs
             strong = run_b200(args, args.workload, 3, 3, rank, local_rank, world, dist,

@@ -65,20 +65,59 @@ struct FieldStepperResult
 #    define B2_FIELD_RHS_FN B2_D
 #endif
 
+//! The magnetic field seen by the equation of motion: a constant vector (UniformField) or
+//! the r-z map (RZMapField::operator(), field/RZMapField.hh:67-106)
+struct FieldSource
+{
+    Real3 uniform;
+    FieldParams const* map;  // null: uniform
+
+    B2_D Real3 operator()(Real3 const& pos) const
+    {
+        if (!map)
+            return uniform;
+        FieldParams const& f = *map;
+        Real3 value = make_real3(0, 0, 0);
+        real const r = sqrt(ipow2(pos[0]) + ipow2(pos[1]));
+        real const z = pos[2];
+        if (!(z >= f.rz_z[0] && z <= f.rz_z[1] && r >= f.rz_r[0] && r <= f.rz_r[1]))
+            return value;
+        // find_interp<UniformGrid> (corecel/grid/FindInterp.hh:43-57)
+        u32 const ir = static_cast<u32>((r - f.rz_r[0]) / f.rz_r[2]);
+        u32 const iz = static_cast<u32>((z - f.rz_z[0]) / f.rz_z[2]);
+        real const r_lo = f.rz_r[0] + f.rz_r[2] * ir, r_hi = f.rz_r[0] + f.rz_r[2] * (ir + 1);
+        real const z_lo = f.rz_z[0] + f.rz_z[2] * iz, z_hi = f.rz_z[0] + f.rz_z[2] * (iz + 1);
+        real const frac_r = (r - r_lo) / (r_hi - r_lo);
+        real const frac_z = (z - z_lo) / (z_hi - z_lo);
+        real const* v = f.rz_values;
+        u32 const nr = f.rz_size_r;
+        real low = v[2 * (iz * nr + ir)];
+        real high = v[2 * ((iz + 1) * nr + ir)];
+        value[2] = low + (high - low) * frac_z;
+        low = v[2 * (iz * nr + ir) + 1];
+        high = v[2 * (iz * nr + ir + 1) + 1];
+        real const tmp = (r != 0) ? (low + (high - low) * frac_r) / r : low;
+        value[0] = tmp * pos[0];
+        value[1] = tmp * pos[1];
+        return value;
+    }
+};
+
 //! Right-hand side of the equation of motion
-B2_FIELD_RHS_FN OdeState field_rhs(real coeffi, Real3 const& field, OdeState const& y)
+B2_FIELD_RHS_FN OdeState field_rhs(real coeffi, FieldSource const& source, OdeState const& y)
 {
     real momentum_inv = 1 / sqrt(dot(y.mom, y.mom));
     OdeState r;
     r.pos = make_real3(momentum_inv * y.mom[0], momentum_inv * y.mom[1], momentum_inv * y.mom[2]);
     real c = coeffi * momentum_inv;
+    Real3 const field = source(y.pos);
     Real3 x = cross_product(y.mom, field);
     r.mom = make_real3(c * x[0], c * x[1], c * x[2]);
     return r;
 }
 
 //! One Dormand-Prince trial step
-B2_FIELD_STEP_FN void field_apply_step(real coeffi, Real3 const& field, real step, OdeState const& beg, FieldStepperResult& result)
+B2_FIELD_STEP_FN void field_apply_step(real coeffi, FieldSource const& field, real step, OdeState const& beg, FieldStepperResult& result)
 {
     using R = real;
     constexpr R a11 = 0.2;
@@ -170,13 +209,14 @@ struct FieldDriver
 {
     FieldParams const& opt;
     real coeffi;     // charge / momentum unit
-    Real3 field;
+    FieldSource field;
     real max_chord;
 
     B2_D FieldDriver(FieldParams const& f, real charge) : opt(f), max_chord(real_inf())
     {
         coeffi = charge * f.coeffi_per_charge;
-        field = make_real3(f.field[0], f.field[1], f.field[2]);
+        field.uniform = make_real3(f.field[0], f.field[1], f.field[2]);
+        field.map = f.rz_values ? &f : nullptr;
     }
 
     //! One Dormand-Prince trial step

@@ -380,6 +380,14 @@ struct FieldParams
     real safety;
     real max_stepping_increase;
     real max_stepping_decrease;
+    // RZ field map (reference: field/RZMapField.hh, RZMapFieldData.hh): rz_values != null
+    // selects it; uniform grids {front, back, delta, size} in z and r, element (iz, ir) =
+    // {value_z, value_r} at 2 * (iz * rz_size_r + ir)
+    real rz_z[3];
+    real rz_r[3];
+    u32 rz_size_z;
+    u32 rz_size_r;
+    real const* rz_values;
 };
 
 struct PhysConstants

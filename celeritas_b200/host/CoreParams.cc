@@ -555,9 +555,27 @@ void CoreParams::load(Image const& img)
             m.fluct.urban = F64("fluct.urban");
         }
         m.field.enabled = 0;
-        if (img.has("field.uniform"))
+        if (img.has("field.uniform") || img.has("field.rz_values"))
         {
-            auto f = img.get<double>("field.uniform");
+            bool const rz = img.has("field.rz_values");
+            auto f = rz ? std::vector<double>{0, 0, 0} : img.get<double>("field.uniform");
+            if (rz)
+            {
+                auto grid = img.get<double>("field.rz_grid");
+                auto sizes = img.get<uint32_t>("field.rz_sizes");
+                auto values = img.get<double>("field.rz_values");
+                if (grid.size() != 6 || sizes.size() != 2 || sizes[0] < 2 || sizes[1] < 2
+                    || values.size() != size_t(2) * sizes[0] * sizes[1])
+                    throw std::runtime_error("inconsistent problem image: field.rz_*");
+                for (int i = 0; i < 3; ++i)
+                {
+                    m.field.rz_z[i] = grid[i];
+                    m.field.rz_r[i] = grid[3 + i];
+                }
+                m.field.rz_size_z = sizes[0];
+                m.field.rz_size_r = sizes[1];
+                m.field.rz_values = arena_.upload(values);
+            }
             auto o = img.get<double>("field.options");
             auto u = img.get<uint32_t>("field.options_u32");
             m.field.enabled = 1;
@@ -716,7 +734,7 @@ void CoreParams::track_order(uint32_t order)
 
 void CoreParams::uniform_field_tesla(double const (&field)[3])
 {
-    if (!this->has_uniform_field())
+    if (!this->has_uniform_field() || view_.model.field.rz_values)
         throw std::runtime_error(
             "the problem image was exported without a uniform-field along-step action");
     // native field unit is gauss (reference: units::FieldTesla -> native, Runner.cc:394-398)

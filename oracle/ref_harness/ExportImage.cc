@@ -40,6 +40,8 @@
 #include "celeritas/track/TrackInitParams.hh"
 
 #include "../../celeritas_b200/host/Image.hh"
+#include "corecel/grid/UniformGridData.hh"
+
 #include "Problem.hh"
 
 using namespace celeritas;
@@ -749,6 +751,40 @@ void export_models(Problem const& prob, b200::Image& img)
         F64 f{prob.field.field[0], prob.field.field[1], prob.field.field[2]};
         auto const& o = prob.field.options;
         img.put("field.uniform", f);
+        img.put("field.options",
+                F64{o.minimum_step,
+                    o.delta_chord,
+                    o.delta_intersection,
+                    o.epsilon_step,
+                    o.epsilon_rel_max,
+                    o.errcon,
+                    o.pgrow,
+                    o.pshrink,
+                    o.safety,
+                    o.max_stepping_increase,
+                    o.max_stepping_decrease,
+                    native_value_from(units::ElementaryCharge{1})
+                        / native_value_from(units::MevMomentum{1})});
+        img.put("field.options_u32", U32{static_cast<uint32_t>(o.max_nsteps), static_cast<uint32_t>(o.max_substeps)});
+    }
+    // RZ field map (field/RZMapFieldParams.cc:30-84): uniform grids in z and r, values in
+    // native units, element (iz, ir) at iz * num_grid_r + ir
+    if (prob.has_rz_field)
+    {
+        auto const& in = prob.rz_field;
+        auto gr = UniformGridData::from_bounds(in.min_r, in.max_r, in.num_grid_r);
+        auto gz = UniformGridData::from_bounds(in.min_z, in.max_z, in.num_grid_z);
+        img.put("field.rz_grid",
+                F64{gz.front, gz.back, gz.delta, gr.front, gr.back, gr.delta});
+        img.put("field.rz_sizes", U32{static_cast<uint32_t>(gz.size), static_cast<uint32_t>(gr.size)});
+        F64 values;
+        for (std::size_t i = 0; i < in.field_z.size(); ++i)
+        {
+            values.push_back(in.field_z[i]);
+            values.push_back(in.field_r[i]);
+        }
+        img.put("field.rz_values", values);
+        auto const& o = in.driver_options;
         img.put("field.options",
                 F64{o.minimum_step,
                     o.delta_chord,

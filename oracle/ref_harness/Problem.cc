@@ -25,6 +25,8 @@
 #include "celeritas/geo/GeoParams.hh"
 #include "celeritas/global/alongstep/AlongStepGeneralLinearAction.hh"
 #include "celeritas/global/alongstep/AlongStepNeutralAction.hh"
+#include "celeritas/field/RZMapFieldInputIO.json.hh"
+#include "celeritas/global/alongstep/AlongStepRZMapFieldMscAction.hh"
 #include "celeritas/global/alongstep/AlongStepUniformMscAction.hh"
 #include "celeritas/io/detail/ImportDataConverter.hh"
 #include "celeritas/mat/MaterialParams.hh"
@@ -486,7 +488,21 @@ void build_imported(Problem& p, CoreParams::Input& params)
         p.fluct = std::make_shared<FluctuationParams>(*params.particle,
                                                       *params.material);
     }
-    if (!p.has_field)
+    if (cfg.contains("field_map"))
+    {
+        // Magnetic field map in r-z (field/RZMapField.hh), e.g. the reference's
+        // test/celeritas/data/cms-tiny.field.json: AlongStepRZMapFieldMscAction
+        CELER_VALIDATE(!p.has_field, << "'field' and 'field_map' are mutually exclusive");
+        std::ifstream in(cfg.at("field_map").get<std::string>());
+        CELER_VALIDATE(in, << "cannot open field map '"
+                           << cfg.at("field_map").get<std::string>() << "'");
+        in >> p.rz_field;
+        p.has_rz_field = true;
+        auto along_step = std::make_shared<AlongStepRZMapFieldMscAction>(
+            params.action_reg->next_id(), p.rz_field, p.fluct, msc);
+        params.action_reg->insert(along_step);
+    }
+    else if (!p.has_field)
     {
         auto along_step = std::make_shared<AlongStepGeneralLinearAction>(
             params.action_reg->next_id(), p.fluct, msc);

@@ -16,6 +16,7 @@
 
 #include "celeritas/em/params/FluctuationParams.hh"
 #include "celeritas/em/params/UrbanMscParams.hh"
+#include "celeritas/field/RZMapFieldInput.hh"
 #include "celeritas/field/UniformFieldData.hh"
 #include "orange/OrangeParams.hh"
 #include "celeritas/global/CoreParams.hh"
@@ -71,6 +72,9 @@ struct Problem
     std::shared_ptr<celeritas::UrbanMscParams const> msc;
     std::shared_ptr<celeritas::FluctuationParams const> fluct;
     celeritas::UniformFieldParams field;
+    //! "field_map": RZ field map file (field/RZMapFieldInput.hh) instead of a uniform field
+    celeritas::RZMapFieldInput rz_field;
+    bool has_rz_field{false};
     bool has_msc{false};
     bool has_fluct{false};
     bool has_field{false};
