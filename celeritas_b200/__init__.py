@@ -7,8 +7,8 @@ and fails loudly otherwise.
 """
 from .lib import (Params, Stepper, Primary, PRIMARY_DTYPE, make_primaries, library_path,
                   load_library, launch_count, device_count, set_device, B200Error,
-                  celer_sim_run, run_events_streams, orange_build_image)
+                  celer_sim_run, run_events_streams, orange_build_image, import_root)
 
 __all__ = ['Params', 'Stepper', 'Primary', 'PRIMARY_DTYPE', 'make_primaries', 'library_path',
            'load_library', 'launch_count', 'device_count', 'set_device', 'B200Error',
-           'celer_sim_run', 'run_events_streams', 'orange_build_image']
+           'celer_sim_run', 'run_events_streams', 'orange_build_image', 'import_root']

@@ -237,6 +237,284 @@ B2_D Interaction interact_klein_nishina(KleinNishinaParams const& shared,
 }
 
 //---------------------------------------------------------------------------//
+// Rayleigh scattering (em/interactor/RayleighInteractor.hh:107-199): coherent scattering off
+// the element chosen by the discrete selection; the angle is drawn from a three-term fit of
+// the squared form factor, the energy is unchanged and nothing is deposited
+//---------------------------------------------------------------------------//
+B2_D Interaction interact_rayleigh(RayleighParams const& shared,
+                                   real inc_energy,
+                                   Real3 const& inc_direction,
+                                   u32 element,
+                                   Rng& rng)
+{
+    real const fit_slice = 0.02;
+    real pa[3], pb[3], pn[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+        pa[i] = shared.params[9 * element + i];
+        pb[i] = shared.params[9 * element + 3 + i];
+        pn[i] = shared.params[9 * element + 6 + i];
+    }
+
+    // evaluate_weight_and_prob
+    real const factor = ipow2(shared.hc_factor * (inc_energy * shared.mev));
+    real weight[3], prob[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+        real const x = fma(factor, pb[i], pb[i]);
+        real const n = pn[i];
+        weight[i] = (x > fit_slice) ? 1 - exp(-n * log(1 + x))
+                                    : n * x * (1 - (n - 1) / 2 * x * (1 - (n - 2) / 3 * x));
+        prob[i] = weight[i] * pa[i] / (pb[i] * n);
+    }
+    real const inv_sum = 1 / (prob[0] + prob[1] + prob[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        prob[i] = fma(inv_sum, prob[i], real(0));
+
+    real cost;
+    do
+    {
+        // Selector over the three terms (total 1; the last is never accumulated)
+        real accum = -rng.canonical();
+        int index = 2;
+        accum += prob[0];
+        if (accum > 0)
+            index = 0;
+        else
+        {
+            accum += prob[1];
+            if (accum > 0)
+                index = 1;
+        }
+        real const w = index == 0 ? weight[0] : index == 1 ? weight[1] : weight[2];
+        real const ninv = 1 / (index == 0 ? pn[0] : index == 1 ? pn[1] : pn[2]);
+        real const b = index == 0 ? pb[0] : index == 1 ? pb[1] : pb[2];
+
+        real x;
+        real const y = w * rng.canonical();
+        if (y < fit_slice)
+            x = y * ninv * (1 + real(0.5) * (ninv + 1) * y * (1 - (ninv + 2) * y / 3));
+        else
+            x = exp(-ninv * log(1 - y)) - 1;
+        cost = 1 - 2 * x / (b * factor);
+    } while (2 * rng.canonical() > 1 + ipow2(cost) || cost < -1);
+
+    Interaction result;
+    result.energy = inc_energy;
+    result.direction = sample_exiting_direction(rng, cost, inc_direction);
+    return result;
+}
+
+//---------------------------------------------------------------------------//
+// Single Coulomb scattering off a nucleus or its electrons, Wentzel model
+// (em/executor/CoulombScatteringExecutor.hh:38-65, em/interactor/
+// CoulombScatteringInteractor.hh:105-176, em/xs/WentzelHelper.hh:139-325,
+// em/distribution/WentzelDistribution.hh:172-313, em/xs/MottRatioCalculator.hh:73-97,
+// em/xs/NuclearFormFactors.hh:184-296, mat/IsotopeSelector.hh:62-76)
+//---------------------------------------------------------------------------//
+//! corecel/math/Algorithms.hh fastpow: exp(b log a)
+B2_D real exp_b_log_a(real a, real b)
+{
+    return exp(b * log(a));
+}
+
+struct WentzelHelper
+{
+    real target_z;
+    real screening_coefficient;
+    real kin_factor;
+    real mott_factor;
+    real cos_thetamax_elec;
+    real cos_thetamax_nuc;
+
+    B2_D WentzelHelper(CoulombParams const& w,
+                       Particle const& particle,
+                       u32 material,
+                       u32 z,
+                       real cutoff)
+        : target_z(z)
+    {
+        real const mom_sq = particle.momentum_sq();
+        real const beta_sq = particle.beta_sq();
+        // Moliere screening coefficient
+        {
+            real correction = 1;
+            real const sq_cbrt_z = exp_b_log_a(target_z, real(2) / 3);
+            if (z > 1)
+            {
+                real const tau = particle.energy / particle.mass;
+                real const factor = sqrt(tau / (tau + sq_cbrt_z));
+                correction = fmin(target_z * real(1.13),
+                                  real(1.13)
+                                      + real(3.76) * ipow2(target_z * w.alpha_fine_structure)
+                                            * factor / beta_sq);
+            }
+            screening_coefficient = correction * w.screen_r_sq_elec * sq_cbrt_z / mom_sq
+                                    * w.screening_factor;
+        }
+        kin_factor = w.twopi_mrsq * target_z * ipow2(particle.charge) / (beta_sq * mom_sq);
+        mott_factor = particle.id == w.electron ? 1 + real(2e-4) * ipow2(target_z) : real(1);
+        // maximum scattering angle off electrons
+        {
+            real const inc_energy = particle.energy;
+            real const max_energy = particle.id == w.electron ? real(0.5) * inc_energy
+                                                              : inc_energy;
+            real const final_energy = inc_energy - fmin(cutoff, max_energy);
+            cos_thetamax_elec = 0;
+            if (final_energy > 0)
+            {
+                real const incident_ratio = 1 + 2 * particle.mass / inc_energy;
+                real const final_ratio = 1 + 2 * particle.mass / final_energy;
+                real const cos_t_max = sqrt(incident_ratio / final_ratio);
+                cos_thetamax_elec = fmin(fmax(cos_t_max, real(0)), real(1));
+            }
+        }
+        // maximum scattering angle off a nucleus
+        cos_thetamax_nuc = w.costheta_limit;
+        if (w.is_combined)
+        {
+            cos_thetamax_nuc = fmax(
+                w.costheta_limit, 1 - w.a_sq_factor * w.inv_mass_cbrt_sq[material] / mom_sq);
+        }
+    }
+
+    B2_D real calc_xs_factor(real cos_thetamin, real cos_thetamax) const
+    {
+        return kin_factor * mott_factor * (cos_thetamin - cos_thetamax)
+               / ((1 - cos_thetamin + 2 * screening_coefficient)
+                  * (1 - cos_thetamax + 2 * screening_coefficient));
+    }
+    B2_D real calc_xs_electron(real cos_thetamin, real cos_thetamax) const
+    {
+        cos_thetamin = fmax(cos_thetamin, cos_thetamax_elec);
+        cos_thetamax = fmax(cos_thetamax, cos_thetamax_elec);
+        if (cos_thetamin <= cos_thetamax)
+            return 0;
+        return calc_xs_factor(cos_thetamin, cos_thetamax);
+    }
+    B2_D real calc_xs_nuclear(real cos_thetamin, real cos_thetamax) const
+    {
+        return target_z * calc_xs_factor(cos_thetamin, cos_thetamax);
+    }
+    //! [Fern] eqn 92 with cos(theta) = 1 - 2 mu
+    B2_D real sample_costheta(real cos_thetamin, real cos_thetamax, Rng& rng) const
+    {
+        real const mu1 = real(0.5) * (1 - cos_thetamin);
+        real const mu2 = real(0.5) * (1 - cos_thetamax);
+        real const w = rng.canonical() * (mu2 - mu1);
+        real const sc = screening_coefficient;
+        return 1 - 2 * mu1 - 2 * (sc + mu1) * w / (sc + mu2 - w);
+    }
+};
+
+//! Nuclear form factor at a squared momentum transfer (NuclearFormFactors.hh)
+B2_D real nuclear_form_factor(CoulombParams const& w, u32 isotope, real mt_sq)
+{
+    switch (w.form_factor_type)
+    {
+        case 1:  // flat: folded uniform-uniform spheres
+        {
+            real const target_mom = sqrt(mt_sq);
+            real const a = real(w.isotope_za[2 * isotope + 1]);
+            real const nucl_radius_fm = real(1.2) * exp_b_log_a(a, real(1) / 3);
+            auto sphere_ff = [&](real r) {
+                real const x = target_mom * (r * w.fm_par_hbar);
+                return (3 / (x * x * x)) * fma(-x, cos(x), sin(x));
+            };
+            return fmin(sphere_ff(nucl_radius_fm) * sphere_ff(real(2)), real(1));
+        }
+        case 2:  // exponential
+            return 1 / ipow2(1 + w.nuclear_form_prefactor[isotope] * mt_sq);
+        case 3:  // gaussian
+            return exp(-2 * w.nuclear_form_prefactor[isotope] * mt_sq);
+        default:
+            return 1;
+    }
+}
+
+B2_D Interaction interact_coulomb(ParamsView const& pv,
+                                  Particle const& particle,
+                                  Real3 const& inc_direction,
+                                  u32 material,
+                                  u32 element,
+                                  Rng& rng)
+{
+    CoulombParams const& w = pv.model.coulomb;
+
+    // IsotopeSelector: the element's isotopes by number fraction
+    u32 isotope;
+    {
+        u32 const begin = w.element_isocomp_range[2 * element];
+        u32 const imax = w.element_isocomp_range[2 * element + 1] - begin - 1;
+        real cumulative = -rng.canonical();
+        u32 i = 0;
+        for (; i < imax; ++i)
+        {
+            cumulative += w.isocomp_fraction[begin + i];
+            if (cumulative > 0)
+                break;
+        }
+        isotope = w.isocomp_isotope[begin + i];
+    }
+    u32 const z = w.isotope_za[2 * isotope];
+
+    WentzelHelper const helper(w, particle, material, z, cutoff_energy(pv, material, w.electron));
+    real const cos_thetamin = helper.cos_thetamax_nuc;
+    real const cos_thetamax = -1;  // CoulombScatteringData::cos_thetamax()
+
+    // WentzelDistribution
+    real cos_theta = 1;
+    if (sample_bernoulli(rng,
+                         helper.calc_xs_electron(cos_thetamin, cos_thetamax),
+                         helper.calc_xs_nuclear(cos_thetamin, cos_thetamax)))
+    {
+        // off electrons
+        real const lo = fmax(cos_thetamin, helper.cos_thetamax_elec);
+        real const hi = fmax(cos_thetamax, helper.cos_thetamax_elec);
+        cos_theta = helper.sample_costheta(lo, hi, rng);
+    }
+    else
+    {
+        // off the nucleus, with rejection for false scattering
+        cos_theta = helper.sample_costheta(cos_thetamin, cos_thetamax, rng);
+        // Mott / Rutherford ratio: polynomial in (beta - 0.7181228) and sqrt(1 - cos)
+        real const beta0 = sqrt(particle.beta_sq()) - real(0.7181228);
+        real const fcos_t = sqrt(1 - cos_theta);
+        u32 const base = (2 * element + (particle.charge < 0 ? 0u : 1u)) * 30;
+        real theta_coeffs[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+        {
+            real c[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                c[j] = w.mott[base + 6 * i + j];
+            theta_coeffs[i] = poly(c, beta0);
+        }
+        real const mott_ratio = poly(theta_coeffs, fcos_t);
+        real const mt_sq = 2 * particle.momentum_sq() * (1 - cos_theta);
+        real const xs = mott_ratio * ipow2(nuclear_form_factor(w, isotope, mt_sq));
+        // RejectionSampler(xs, mott_factor): reject when xs < mott_factor * xi
+        if (xs < helper.mott_factor * rng.canonical())
+            cos_theta = 1;
+    }
+
+    Interaction result;
+    result.direction = sample_exiting_direction(rng, cos_theta, inc_direction);
+    // recoil energy: kinetic energy transferred to the atom
+    real const projectile_mass = particle.mass + particle.energy;
+    real const target_mass = w.isotope_nuclear_mass[isotope];
+    real const recoil_energy = particle.momentum_sq() * (1 - cos_theta)
+                               / (target_mass + projectile_mass * (1 - cos_theta));
+    result.energy = particle.energy - recoil_energy;
+    result.energy_deposition = recoil_energy;
+    return result;
+}
+
+//---------------------------------------------------------------------------//
 // Moller / Bhabha ionisation (em/interactor/MollerBhabhaInteractor.hh,
 // em/distribution/{Moller,Bhabha}EnergyDistribution.hh,
 // em/interactor/detail/IoniFinalStateHelper.hh)
@@ -1046,6 +1324,15 @@ B2_D void run_interaction(ParamsView const& pv, StateView const& s, u32 slot, u3
             result = interact_relativistic_brem(pv, particle, dir, material, element, rng);
         else
             result = interact_seltzer_berger(pv, particle, dir, material, element, rng);
+    }
+    else if (action == m.coulomb.action)
+    {
+        result = interact_coulomb(pv, particle, dir, material, element_of(s.element[slot]), rng);
+    }
+    else if (action == m.rayleigh.action)
+    {
+        result = interact_rayleigh(
+            m.rayleigh, particle.energy, dir, element_of(s.element[slot]), rng);
     }
     else if (action == m.pe.action)
     {

@@ -406,6 +406,42 @@ struct CombinedBremParams
     real sb_upper_limit;  // detail::seltzer_berger_upper_limit() = 1 GeV
 };
 
+//! Rayleigh scattering (em/data/RayleighData.hh): form-factor fit parameters per element
+struct RayleighParams
+{
+    u32 action;
+    u32 gamma;
+    real hc_factor;   // units::centimeter / (c_light * h_planck)
+    real mev;         // native value of 1 MeV
+    RO<real> params;  // [element][a0 a1 a2 b0 b1 b2 n0 n1 n2]
+};
+
+//! Single Coulomb scattering (em/data/CoulombScatteringData.hh, WentzelOKVIData.hh) and the
+//! isotope columns its executor draws the target from (mat/MaterialData.hh:30-60)
+struct CoulombParams
+{
+    u32 action;
+    u32 electron;
+    u32 positron;
+    u32 is_combined;
+    u32 form_factor_type;  // NuclearFormFactorType: none, flat, exponential, gaussian
+    real costheta_limit;
+    real screening_factor;
+    real a_sq_factor;
+    real screen_r_sq_elec;  // (hbar / (2 C_TF a_0))^2 [(MeV/c)^2]
+    real twopi_mrsq;        // 2 pi (m_e r_e)^2
+    real alpha_fine_structure;
+    real fm_par_hbar;       // 1 fm / hbar [1 / (MeV/c)]
+    RO<real> nuclear_form_prefactor;  // per isotope
+    RO<real> mott;                    // [element][electron, positron][theta 5][beta 6]
+    RO<real> inv_mass_cbrt_sq;        // per material (combined with Wentzel VI only)
+    RO<u32> element_isocomp_range;    // 2 per element
+    RO<u32> isocomp_isotope;
+    RO<real> isocomp_fraction;
+    RO<u32> isotope_za;               // 2 per isotope: Z, A
+    RO<real> isotope_nuclear_mass;
+};
+
 struct ModelParams
 {
     KleinNishinaParams kn;
@@ -416,6 +452,8 @@ struct ModelParams
     RelativisticBremParams rb;
     LivermorePEParams pe;
     CombinedBremParams cb;
+    RayleighParams rayleigh;
+    CoulombParams coulomb;
     UrbanMscParams msc;
     FluctuationParams fluct;
     FieldParams field;

@@ -546,6 +546,70 @@ void CoreParams::load(Image const& img)
                 m.msc.grid_energy = arena_.upload(pool.values);
             }
         }
+        m.rayleigh.action = INVALID;
+        if (img.has("model.rayleigh.ids"))
+        {
+            auto ids = img.get<uint32_t>("model.rayleigh.ids");
+            auto consts = img.get<double>("model.rayleigh.consts");
+            auto reals = img.get<double>("model.rayleigh.params");
+            if (reals.size() != size_t(9) * view_.mat.num_elements)
+                throw std::runtime_error(
+                    "inconsistent problem image: model.rayleigh.params is not 9 per element");
+            m.rayleigh.action = ids.at(0);
+            m.rayleigh.gamma = ids.at(1);
+            m.rayleigh.hc_factor = consts.at(0);
+            m.rayleigh.mev = consts.at(1);
+            m.rayleigh.params = arena_.upload(reals);
+        }
+        m.coulomb.action = INVALID;
+        if (img.has("model.coulomb.ids"))
+        {
+            auto ids = img.get<uint32_t>("model.coulomb.ids");
+            auto reals = img.get<double>("model.coulomb.reals");
+            auto mott = img.get<double>("model.coulomb.mott");
+            auto prefactor = img.get<double>("model.coulomb.nuclear_form_prefactor");
+            auto inv_mass = img.get<double>("model.coulomb.inv_mass_cbrt_sq");
+            auto el_range = img.get<uint32_t>("mat.element_isocomp_range");
+            auto ic_iso = img.get<uint32_t>("mat.isocomp_isotope");
+            auto ic_frac = img.get<double>("mat.isocomp_fraction");
+            auto iso_za = img.get<uint32_t>("mat.isotope_za");
+            auto iso_mass = img.get<double>("mat.isotope_nuclear_mass");
+            size_t const ne = view_.mat.num_elements;
+            size_t const ni = iso_mass.size();
+            bool ok = ids.size() == 5 && reals.size() == 7 && mott.size() == 60 * ne
+                      && el_range.size() == 2 * ne && ic_frac.size() == ic_iso.size()
+                      && iso_za.size() == 2 * ni && prefactor.size() == ni
+                      && (ids[3] == 0 || inv_mass.size() == view_.mat.num_materials)
+                      && ids[4] <= 3;
+            for (size_t e = 0; ok && e < ne; ++e)
+                ok = el_range[2 * e] < el_range[2 * e + 1]
+                     && el_range[2 * e + 1] <= ic_iso.size();
+            for (size_t i = 0; ok && i < ic_iso.size(); ++i)
+                ok = ic_iso[i] < ni;
+            if (!ok)
+                throw std::runtime_error(
+                    "inconsistent problem image: model.coulomb.* / isotope columns");
+            m.coulomb.action = ids[0];
+            m.coulomb.electron = ids[1];
+            m.coulomb.positron = ids[2];
+            m.coulomb.is_combined = ids[3];
+            m.coulomb.form_factor_type = ids[4];
+            m.coulomb.costheta_limit = reals[0];
+            m.coulomb.screening_factor = reals[1];
+            m.coulomb.a_sq_factor = reals[2];
+            m.coulomb.screen_r_sq_elec = reals[3];
+            m.coulomb.twopi_mrsq = reals[4];
+            m.coulomb.alpha_fine_structure = reals[5];
+            m.coulomb.fm_par_hbar = reals[6];
+            m.coulomb.nuclear_form_prefactor = arena_.upload(prefactor);
+            m.coulomb.mott = arena_.upload(mott);
+            m.coulomb.inv_mass_cbrt_sq = arena_.upload(inv_mass);
+            m.coulomb.element_isocomp_range = arena_.upload(el_range);
+            m.coulomb.isocomp_isotope = arena_.upload(ic_iso);
+            m.coulomb.isocomp_fraction = arena_.upload(ic_frac);
+            m.coulomb.isotope_za = arena_.upload(iso_za);
+            m.coulomb.isotope_nuclear_mass = arena_.upload(iso_mass);
+        }
         m.fluct.enabled = 0;
         if (img.has("fluct.urban"))
         {
@@ -604,7 +668,8 @@ void CoreParams::load(Image const& img)
         {
             bool const claimed = a == m.kn.action || a == m.mb.action || a == m.epgg.action
                                  || a == m.bh.action || a == m.sb.action || a == m.rb.action
-                                 || a == m.pe.action || a == m.cb.action;
+                                 || a == m.pe.action || a == m.cb.action
+                                 || a == m.rayleigh.action || a == m.coulomb.action;
             if (!claimed)
                 throw std::runtime_error(
                     "no B200 interactor for model action '"

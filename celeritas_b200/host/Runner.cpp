@@ -3,10 +3,12 @@
 //---------------------------------------------------------------------------//
 #include "Runner.hh"
 #include "OrangeBuilder.hh"
+#include "RootImport.hh"
 
 #include <fstream>
 
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -311,6 +313,61 @@ std::string celer_sim_run(std::string const& input_json)
                     image.put_entry(kv.first, kv.second);
         }
     }
+    // `physics_file`: a reference physics export (ROOT, decoded by host/RootImport.cpp) or
+    // its JSON form is read when it exists and must describe the particles and elements the
+    // image's tables were built for (the tables themselves come from the image)
+    std::string physics_check;
+    {
+        std::string const phys_path = resolve(inp.base_dir, inp.physics_file);
+        auto ends_with = [&](char const* ext) {
+            size_t const n = std::strlen(ext);
+            return phys_path.size() > n && phys_path.compare(phys_path.size() - n, n, ext) == 0;
+        };
+        if ((ends_with(".root") || ends_with(".json")) && !inp.physics_file.empty()
+            && std::ifstream(phys_path).good())
+        {
+            json data;
+            if (ends_with(".root"))
+                data = json::parse(b200::import_root_to_json(phys_path));
+            else
+                data = json::parse(std::ifstream(phys_path));
+            if (!data.contains("particles") || !data.contains("elements"))
+                throw std::runtime_error("physics_file '" + inp.physics_file
+                                         + "' is not a celeritas::ImportData export");
+            auto const pdg = image.get<uint32_t>("particle.pdg");
+            auto const mass = image.get<double>("particle.mass");
+            for (size_t i = 0; i < pdg.size(); ++i)
+            {
+                bool found = false;
+                for (auto const& p : data.at("particles"))
+                {
+                    double const m = p.at("mass").get<double>();
+                    found = found
+                            || (p.at("pdg").get<int>() == static_cast<int32_t>(pdg[i])
+                                && std::fabs(m - mass[i]) <= 1e-9 * std::fabs(m));
+                }
+                if (!found)
+                    throw std::runtime_error(
+                        "physics_file '" + inp.physics_file
+                        + "' is not the physics the problem image was exported for (particle "
+                        + std::to_string(static_cast<int32_t>(pdg[i])) + ")");
+            }
+            for (uint32_t z : image.get<uint32_t>("mat.element_z"))
+            {
+                bool found = false;
+                for (auto const& e : data.at("elements"))
+                    found = found || e.at("atomic_number").get<uint32_t>() == z;
+                if (!found)
+                    throw std::runtime_error(
+                        "physics_file '" + inp.physics_file
+                        + "' is not the physics the problem image was exported for (element Z="
+                        + std::to_string(z) + ")");
+            }
+            physics_check = std::to_string(data.at("particles").size()) + " particles, "
+                            + std::to_string(data.at("elements").size()) + " elements, "
+                            + std::to_string(data.at("processes").size()) + " processes";
+        }
+    }
     std::shared_ptr<CoreParams> params = CoreParams::from_image(image);
     bool const no_field = inp.field[0] == 0 && inp.field[1] == 0 && inp.field[2] == 0;
     if (!no_field)
@@ -465,6 +522,8 @@ std::string celer_sim_run(std::string const& input_json)
                           {"device_bytes", {{"params", params->device_bytes()},
                                             {"state", state.device_bytes()}}}};
     output["system"] = {{"device", "B200 (sm_100a)"}, {"library", "celeritas_b200"}};
+    if (!physics_check.empty())
+        output["internal"]["physics_file"] = physics_check;
     return output.dump(1);
 }
 }  // namespace celeritas_b200

@@ -14,6 +14,7 @@
 #include "CoreState.hh"
 #include "Handles.hh"
 #include "OrangeBuilder.hh"
+#include "RootImport.hh"
 #include "Stepper.hh"
 #include "Transporter.hh"
 
@@ -118,6 +119,21 @@ int b200_orange_build_image(char const* org_json_path, void** image, size_t* siz
         std::memcpy(out, bytes.data(), bytes.size());
         *image = out;
         *size = bytes.size();
+    });
+}
+
+int b200_import_root(char const* root_path, char** import_data_json)
+{
+    if (!root_path || !import_data_json)
+        return B200_ERR_INVALID_ARGUMENT;
+    *import_data_json = nullptr;
+    return guarded([&] {
+        std::string const text = b200::import_root_to_json(root_path);
+        char* out = static_cast<char*>(std::malloc(text.size() + 1));
+        if (!out)
+            throw std::runtime_error("out of memory");
+        std::memcpy(out, text.c_str(), text.size() + 1);
+        *import_data_json = out;
     });
 }
 

@@ -70,7 +70,7 @@ EXPORTS = [
     'b200_params_create_from_memory', 'b200_stepper_insert', 'b200_stepper_begin_iteration',
     'b200_stepper_end_iteration', 'b200_stepper_stream', 'b200_step_sort_tracks',
     'b200_step_gather_hits', 'b200_stepper_hits_count', 'b200_stepper_hits_get',
-    'b200_orange_build_image', 'b200_params_create_from_org_json',
+    'b200_orange_build_image', 'b200_params_create_from_org_json', 'b200_import_root',
 ]
 
 _lib = None
@@ -99,6 +99,7 @@ def load_library():
     L.b200_params_create_from_memory.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(vp)]
     L.b200_params_destroy.argtypes = [vp]
     L.b200_orange_build_image.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.b200_import_root.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.b200_params_create_from_org_json.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.b200_string_free.argtypes = [vp]
     L.b200_stepper_insert.argtypes = [vp, vp, C.c_uint32]
@@ -233,6 +234,19 @@ def orange_build_image(org_json_path):
                                      C.byref(size)))
     try:
         return C.string_at(ptr, size.value)
+    finally:
+        L.b200_string_free(ptr)
+
+
+def import_root(root_path):
+    """`celeritas::ImportData` of a reference physics export (.root) as a dict with the
+    reference's member names, decoded by the library's own reader (host only)."""
+    import json
+    L = load_library()
+    ptr = C.c_void_p()
+    _check(L.b200_import_root(os.fspath(root_path).encode(), C.byref(ptr)))
+    try:
+        return json.loads(C.string_at(ptr))
     finally:
         L.b200_string_free(ptr)
 

@@ -130,6 +130,13 @@ int b200_params_create_from_memory(void const* image, size_t size, B200Params** 
  * geometry image of an .org.json file, column for column what the reference builds. The image
  * bytes are malloc'ed (free with b200_string_free); host-only, needs no GPU. */
 int b200_orange_build_image(char const* org_json_path, void** image, size_t* size);
+/* Physics-data reader (reference: RootImporter::operator(), src/celeritas/ext/RootImporter.cc,
+ * reading what RootExporter.cc:47-76 wrote): the `celeritas::ImportData` entry
+ * (src/celeritas/io/ImportData.hh:55-112) of a reference physics export (.root), decoded
+ * without the ROOT library and returned as a JSON document with the reference's member
+ * names (optical_* members are skipped). The string is malloc'ed (free with
+ * b200_string_free); host-only, needs no GPU. */
+int b200_import_root(char const* root_path, char** import_data_json);
 /* Geometry-only problem (navigation, b200_geo_trace) straight from an .org.json file. */
 int b200_params_create_from_org_json(char const* org_json_path, B200Params** out);
 void b200_params_destroy(B200Params* params);

@@ -22,7 +22,11 @@
 #include "celeritas/em/model/KleinNishinaModel.hh"
 #include "celeritas/em/model/LivermorePEModel.hh"
 #include "celeritas/em/model/MollerBhabhaModel.hh"
+#include "celeritas/em/model/RayleighModel.hh"
 #include "celeritas/em/model/CombinedBremModel.hh"
+#include "celeritas/em/model/CoulombScatteringModel.hh"
+#include "celeritas/em/params/WentzelOKVIParams.hh"
+#include "celeritas/em/xs/NuclearFormFactors.hh"
 #include "celeritas/em/model/RelativisticBremModel.hh"
 #include "celeritas/em/model/SeltzerBergerModel.hh"
 #include "celeritas/em/params/FluctuationParams.hh"
@@ -296,6 +300,31 @@ void export_materials(HostCRef<MaterialParamsData> const& m, b200::Image& img)
     }
     img.put("mat.elcomp_element", ce);
     img.put("mat.elcomp_fraction", cf);
+    // Isotopes (mat/MaterialData.hh:30-60): per element a range of (isotope, fraction)
+    // components; per isotope Z, A and the nuclear mass
+    U32 el_iso, ic_iso, iso_za;
+    F64 ic_frac, iso_mass;
+    for (auto const& e : all(m.elements))
+    {
+        el_iso.push_back(e.isotopes.begin()->unchecked_get());
+        el_iso.push_back(e.isotopes.end()->unchecked_get());
+    }
+    for (auto const& c : all(m.isocomponents))
+    {
+        ic_iso.push_back(raw(c.isotope));
+        ic_frac.push_back(c.fraction);
+    }
+    for (auto const& i : all(m.isotopes))
+    {
+        iso_za.push_back(i.atomic_number.unchecked_get());
+        iso_za.push_back(i.atomic_mass_number.unchecked_get());
+        iso_mass.push_back(i.nuclear_mass.value());
+    }
+    img.put("mat.element_isocomp_range", el_iso);
+    img.put("mat.isocomp_isotope", ic_iso);
+    img.put("mat.isocomp_fraction", ic_frac);
+    img.put("mat.isotope_za", iso_za);
+    img.put("mat.isotope_nuclear_mass", iso_mass);
     U32 mb, me, ms;
     F64 mr;  // 8 per material
     for (auto const& r : all(m.materials))
@@ -668,6 +697,79 @@ void export_models(Problem const& prob, b200::Image& img)
             img.put("model.pe.shell_reals", sh_reals);
             F64 reals(all(d.xs.reals).begin(), all(d.xs.reals).end());
             img.put("model.pe.reals", reals);
+        }
+        else if (auto* cs = dynamic_cast<CoulombScatteringModel const*>(&model))
+        {
+            // em/data/CoulombScatteringData.hh + em/data/WentzelOKVIData.hh (the shared
+            // Wentzel OK&VI data CoreParams carries for this model)
+            CELER_VALIDATE(prob.core->wentzel(),
+                           << "Coulomb scattering without Wentzel OK&VI data");
+            auto const& d = cs->host_ref();
+            auto const& w = prob.core->wentzel()->host_ref();
+            img.put("model.coulomb.ids",
+                    U32{cs->action_id().unchecked_get(),
+                        raw(d.ids.electron),
+                        raw(d.ids.positron),
+                        static_cast<uint32_t>(w.params.is_combined),
+                        static_cast<uint32_t>(w.params.form_factor_type)});
+            // constants as WentzelHelper / NuclearFormFactors compute them
+            // (em/xs/WentzelHelper.hh:253-283, em/xs/NuclearFormFactors.hh)
+            constexpr real_type ctf = 0.8853413770001135;
+            img.put("model.coulomb.reals",
+                    F64{w.params.costheta_limit,
+                        w.params.screening_factor,
+                        w.params.a_sq_factor,
+                        native_value_to<units::MevMomentumSq>(
+                            ipow<2>(constants::hbar_planck
+                                    / (2 * ctf * constants::a0_bohr)))
+                            .value(),
+                        2 * constants::pi
+                            * ipow<2>(native_value_to<units::MevMass>(
+                                          constants::electron_mass)
+                                          .value()
+                                      * constants::r_electron),
+                        constants::alpha_fine_structure,
+                        value_as<NuclearFormFactorTraits::InvMomentum>(
+                            NuclearFormFactorTraits::fm_par_hbar())});
+            F64 prefactor(all(w.nuclear_form_prefactor).begin(),
+                          all(w.nuclear_form_prefactor).end());
+            img.put("model.coulomb.nuclear_form_prefactor", prefactor);
+            F64 mott;  // [element][electron, positron][theta 5][beta 6]
+            for (auto const& el : all(w.mott_coeffs))
+            {
+                for (auto const* mat : {&el.electron, &el.positron})
+                    for (auto const& row : *mat)
+                        for (real_type v : row)
+                            mott.push_back(v);
+            }
+            img.put("model.coulomb.mott", mott);
+            F64 inv_mass(all(w.inv_mass_cbrt_sq).begin(),
+                         all(w.inv_mass_cbrt_sq).end());
+            img.put("model.coulomb.inv_mass_cbrt_sq", inv_mass);
+        }
+        else if (auto* ray = dynamic_cast<RayleighModel const*>(&model))
+        {
+            // em/data/RayleighData.hh: the gamma id and nine form-factor fit parameters
+            // (a[3], b[3], n[3]) per element
+            auto const& d = ray->host_ref();
+            img.put("model.rayleigh.ids",
+                    U32{ray->action_id().unchecked_get(), raw(d.gamma)});
+            F64 reals;
+            for (auto const& el : all(d.params))
+            {
+                for (int i = 0; i < 3; ++i)
+                    reals.push_back(el.a[i]);
+                for (int i = 0; i < 3; ++i)
+                    reals.push_back(el.b[i]);
+                for (int i = 0; i < 3; ++i)
+                    reals.push_back(el.n[i]);
+            }
+            img.put("model.rayleigh.params", reals);
+            // RayleighInteractor.hh:180-182: factor = (cm / (c h) * E_native)^2
+            img.put("model.rayleigh.consts",
+                    F64{units::centimeter
+                            / (constants::c_light * constants::h_planck),
+                        native_value_from(units::MevEnergy{1})});
         }
         else
         {

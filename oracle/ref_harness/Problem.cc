@@ -605,7 +605,8 @@ std::unique_ptr<Problem> build_problem(json const& config)
         for (auto const& s : cfg.at("simple_calo"))
         {
             p->calo_volumes.push_back(s.get<std::string>());
-            labels.emplace_back(s.get<std::string>());
+            // "name@ext" names a volume by its full label (Label::default_sep)
+            labels.push_back(Label::from_separator(s.get<std::string>()));
         }
         p->calo = std::make_shared<SimpleCalo>(
             labels, *p->core->geometry(), p->core->max_streams());

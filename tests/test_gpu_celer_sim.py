@@ -280,3 +280,35 @@ def test_celer_sim_builds_the_geometry_from_geometry_file(tmp_path):
     with pytest.raises(cb.B200Error) as e:
         cb.celer_sim_run(wrong)
     assert 'geometry_file' in str(e.value)
+
+
+def test_celer_sim_reads_physics_file():
+    """`physics_file` is read: a reference ROOT export is decoded by the
+    library's own reader and must hold the particles and elements the image's tables were
+    built for. simple-cms.b2img was exported from data/physics/simple-cms.json, the decoded
+    form of the reference's test/celeritas/data/simple-cms.root."""
+    import celeritas_b200 as cb
+    cfg = json.load(open(data_path('images', 'simple-cms.json')))
+    run_input = {
+        '_format': 'celer-sim', 'use_device': True,
+        'image_file': 'data/images/simple-cms.b2img', 'base_dir': REPO,
+        'geometry_file': cfg['geometry_file'],
+        'physics_file': 'tests/golden/root/simple-cms.root',
+        'primary_options': {
+            '_format': 'primary-generator', 'seed': 1, 'pdg': [11, 22], 'num_events': 1,
+            'primaries_per_event': 8,
+            'energy': {'distribution': 'delta', 'params': [100.0]},
+            'position': {'distribution': 'delta', 'params': [0, 0, 0]},
+            'direction': {'distribution': 'isotropic'}},
+        'seed': cfg['seed'], 'num_track_slots': 2048,
+        'initializer_capacity': cfg['initializer_capacity'], 'secondary_stack_factor': 3,
+    }
+    out = cb.celer_sim_run(run_input)
+    assert out['result']['runner']['num_steps'][0] > 50
+    assert 'particles' in out['internal']['physics_file']
+    as_json = cb.celer_sim_run(dict(run_input, physics_file=cfg['physics_file']))
+    assert as_json['result']['runner']['num_steps'] == out['result']['runner']['num_steps']
+    # liquid argon only: not the physics of an image with silicon / lead / iron tables
+    with pytest.raises(cb.B200Error) as e:
+        cb.celer_sim_run(dict(run_input, physics_file='tests/golden/root/lar-sphere.root'))
+    assert 'physics_file' in str(e.value)

@@ -102,6 +102,19 @@ PROBLEMS['many-faces'] = {'geometry_file': 'data/geometry/many-faces.org.json',
                           'seed': 20220904, 'initializer_capacity': 1 << 18, 'max_events': 64,
                           'simple_calo': ['mother', 'polyhedron', 'cheese']}
 
+# Rayleigh scattering on top of the full-EM list: the reference's
+# four-steel-slabs export with its LivermoreRayleigh cross sections kept
+PROBLEMS['four-steel-slabs-rayleigh'] = {
+    'geometry_file': 'data/geometry/four-steel-slabs.org.json',
+    'physics_file': 'data/physics/four-steel-slabs-em-rayleigh.json',
+    'seed': 20220904, 'initializer_capacity': 1 << 18, 'max_events': 64,
+    'simple_calo': ['box@1', 'box@2', 'box@3', 'box@4']}
+
+# ... plus single Coulomb scattering (Wentzel model) for e-/e+ above 100 MeV
+PROBLEMS['four-steel-slabs-coulomb'] = dict(
+    PROBLEMS['four-steel-slabs-rayleigh'],
+    physics_file='data/physics/four-steel-slabs-em-coulomb.json')
+
 # Geometry-only images for the navigation (ray-trace) parity tests: the ORANGE test
 # geometries of the reference (test/orange/data, test/geocel/data)
 for _g in ('two-boxes', 'testem3-flat', 'testem3', 'simple-cms', 'five-volumes', 'universes',

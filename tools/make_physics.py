@@ -16,8 +16,9 @@ parity is unaffected; absolute physics is *not* that of a Pb/lAr calorimeter):
   2. Every element uses the Z=29 Seltzer-Berger differential cross-section table and the
      Z=19 Livermore photoelectric subshell data (the only ones bundled).
   3. Processes kept: e-/e+ ionisation, bremsstrahlung, e+ annihilation, Compton,
-     photoelectric, gamma conversion, plus Urban MSC. Rayleigh, Coulomb and muon
-     processes are dropped (outside the hot-path scope).
+     photoelectric, gamma conversion, plus Urban MSC. Coulomb and muon processes are
+     dropped (outside the hot-path scope); Rayleigh is kept only
+     in four-steel-slabs-em-rayleigh.json.
 
 Outputs: data/physics/testem3-steel-lar.json (and lar/steel single-material variants used by
 the unit tests).
@@ -83,11 +84,43 @@ def extend_urban_msc(data):
     data['msc_models'] = [m for m in data['msc_models'] if m['model_class'] == 3]
 
 
-def filter_physics(data):
+def extend_coulomb_down(data, emin=1e-4):
+    """Give the Coulomb-scattering process a defined cross section below its 100 MeV limit.
+
+    Geant4 exports eCoulombScattering from 100 MeV up (it is meant to go with Wentzel VI
+    multiple scattering above that energy). The reference extrapolates a cross-section grid
+    flat below its first node (grid/XsCalculator.hh:119-122) and then finds no applicable
+    model for the selected process (CoulombScatteringModel.cc:44-66 notes the limitation), so
+    the export as-is cannot be run with electrons below 100 MeV. Here the grids are continued
+    down to `emin` on the same logarithmic spacing with ZERO macroscopic cross section (what
+    Geant4 itself does below a model's limit); the per-element grids repeat their first
+    value so that element selection stays defined on the sliver below 100 MeV where the
+    linear interpolation towards the first exported node is nonzero.
+    """
+    import math
+    for p in data['processes']:
+        if p['process_class'] != 6:
+            continue
+        for t in p['tables']:
+            for v in t['physics_vectors']:
+                per_decade = round((len(v['x']) - 1) / math.log10(v['x'][-1] / v['x'][0]))
+                n = round(math.log10(v['x'][0] / emin) * per_decade)
+                low = [v['x'][0] * 10 ** (-(n - k) / per_decade) for k in range(n)]
+                v['x'] = low + v['x']
+                v['y'] = [0.0] * n + v['y']
+        for m in p['models']:
+            for mm in m['materials']:
+                n = round(math.log10(mm['energy'][0] / emin))
+                low = [mm['energy'][0] * 10 ** (-(n - k)) for k in range(n)]
+                mm['energy'] = low + mm['energy']
+                mm['micro_xs'] = [[xs[0]] * n + xs for xs in mm['micro_xs']]
+
+
+def filter_physics(data, keep_process=KEEP_PROCESS):
     extend_urban_msc(data)
     data['particles'] = [p for p in data['particles'] if p['pdg'] in KEEP_PDG]
     data['processes'] = [p for p in data['processes']
-                         if p['particle_pdg'] in KEEP_PDG and p['process_class'] in KEEP_PROCESS]
+                         if p['particle_pdg'] in KEEP_PDG and p['process_class'] in keep_process]
     data['msc_models'] = [m for m in data['msc_models'] if m['particle_pdg'] in KEEP_PDG]
     for pm in data['phys_materials']:
         pm['pdg_cutoffs'] = [c for c in pm['pdg_cutoffs'] if c['first'] in KEEP_PDG]
@@ -225,6 +258,30 @@ def main():
     filter_physics(steel_full)
     add_element_data(steel_full)
     json.dump(steel_full, open(os.path.join(PHYS, 'four-steel-slabs-em.json'), 'w'),
+              separators=(',', ':'))
+
+    # the same with Rayleigh scattering kept (ImportProcessClass::rayleigh = 12,
+    # LivermoreRayleigh cross sections as exported): SURVEY 8(f)4
+    steel_ray = load('four-steel-slabs')
+    filter_physics(steel_ray, KEEP_PROCESS + (12,))
+    # volumes named as in data/geometry/four-steel-slabs.org.json ('box@1'..'box@4' match
+    # the extension-free 'box', geo/GeoMaterialParams.cc:108-140)
+    steel_ray = merge([(steel_ray, 'G4_Galactic'), (steel_ray, 'G4_STAINLESS-STEEL')],
+                      [('box', 1), ('World', 0)])
+    add_element_data(steel_ray)
+    json.dump(steel_ray, open(os.path.join(PHYS, 'four-steel-slabs-em-rayleigh.json'), 'w'),
+              separators=(',', ':'))
+
+    # ... and with single Coulomb scattering kept (ImportProcessClass::coulomb_scat = 6,
+    # eCoulombScattering tables above 100 MeV as exported; without the Wentzel VI
+    # multiple-scattering model the reference samples every angle, WentzelOKVIParams.cc:40-56)
+    steel_cs = load('four-steel-slabs')
+    filter_physics(steel_cs, KEEP_PROCESS + (6, 12))
+    extend_coulomb_down(steel_cs)
+    steel_cs = merge([(steel_cs, 'G4_Galactic'), (steel_cs, 'G4_STAINLESS-STEEL')],
+                     [('box', 1), ('World', 0)])
+    add_element_data(steel_cs)
+    json.dump(steel_cs, open(os.path.join(PHYS, 'four-steel-slabs-em-coulomb.json'), 'w'),
               separators=(',', ':'))
 
 
