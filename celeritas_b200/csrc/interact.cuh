@@ -869,6 +869,193 @@ B2_D Interaction interact_bethe_heitler(ParamsView const& pv,
 }
 
 //---------------------------------------------------------------------------//
+// Muon / hadron ionisation (em/interactor/MuHadIonizationInteractor.hh:103-146 with the
+// delta-ray energy distributions em/distribution/{BraggICRU73QO,BetheBloch,MuBB}
+// EnergyDistribution.hh and the maximum energy transfer of em/distribution/detail/Utils.hh)
+//---------------------------------------------------------------------------//
+enum MuHadSampler { MUHAD_BRAGG_ICRU73QO, MUHAD_BETHE_BLOCH, MUHAD_MU_BETHE_BLOCH };
+
+B2_D Interaction interact_muhad_ionization(MuHadIonizationParams const& shared,
+                                           int sampler,
+                                           Particle const& particle,
+                                           real electron_cutoff,
+                                           Real3 const& inc_direction,
+                                           Rng& rng)
+{
+    real const inc_mass = particle.mass;
+    real const me = shared.electron_mass;
+    real const beta_sq = particle.beta_sq();
+    // calc_max_secondary_energy
+    real max_energy;
+    {
+        real const mass_ratio = me / inc_mass;
+        real const tau = particle.energy / inc_mass;
+        max_energy = 2 * me * tau * (tau + 2) / (1 + 2 * (tau + 1) * mass_ratio + ipow2(mass_ratio));
+    }
+    real min_energy = electron_cutoff;
+    if (sampler == MUHAD_BRAGG_ICRU73QO)
+    {
+        // lowest kinetic energy scaled from the proton: ICRU73QO 5 keV, Bragg 0.25 keV
+        real const lowest = particle.charge < 0 ? real(5e-3) : real(2.5e-4);
+        min_energy = fmin(electron_cutoff, lowest * inc_mass / shared.proton_mass);
+    }
+    if (min_energy >= max_energy)
+        return Interaction::from_unchanged();
+
+    real const total_energy = particle.energy + inc_mass;
+    bool const use_rad_correction = sampler == MUHAD_MU_BETHE_BLOCH && particle.energy > 250
+                                    && max_energy > real(0.1);
+    real envelope = 1;
+    if (use_rad_correction)
+        envelope = 1 + shared.alpha_over_twopi * ipow2(log(2 * total_energy / inc_mass));
+
+    // InverseSquareDistribution(min, max) with the model's rejection function
+    real const product = min_energy * max_energy;
+    real energy;
+    bool rejected;
+    do
+    {
+        energy = product / sample_uniform(rng, min_energy, max_energy);
+        real target = 1 - (beta_sq / max_energy) * energy;
+        if (sampler == MUHAD_MU_BETHE_BLOCH)
+        {
+            target = target + real(0.5) * ipow2(energy / total_energy);
+            if (use_rad_correction && energy > real(0.1))
+            {
+                real const a1 = log(1 + 2 * energy / me);
+                real const a3 = log(4 * total_energy * (total_energy - energy) / ipow2(inc_mass));
+                target *= (1 + shared.alpha_over_twopi * a1 * (a3 - a1));
+            }
+            rejected = target < envelope * rng.canonical();
+        }
+        else
+        {
+            rejected = target < rng.canonical();  // RejectionSampler(f): fmax = 1
+        }
+    } while (rejected);
+
+    // IoniFinalStateHelper
+    real const inc_momentum = particle.momentum();
+    real const momentum = sqrt(energy * (energy + 2 * me));
+    real const costheta = energy * (particle.energy + inc_mass + me) / (momentum * inc_momentum);
+    Interaction result;
+    result.num_secondaries = 1;
+    result.sec[0].energy = energy;
+    result.sec[0].direction = sample_exiting_direction(rng, costheta, inc_direction);
+    result.sec[0].particle = shared.electron;
+    result.energy = particle.energy - energy;
+    result.direction
+        = calc_exiting_direction(inc_momentum, inc_direction, momentum, result.sec[0].direction);
+    return result;
+}
+
+B2_D Interaction brem_final_state(real inc_energy,
+                                  Real3 const& inc_direction,
+                                  real inc_momentum,
+                                  u32 gamma_id,
+                                  real gamma_energy,
+                                  real costheta,
+                                  Rng& rng);
+
+//---------------------------------------------------------------------------//
+// Muon bremsstrahlung (em/interactor/MuBremsstrahlungInteractor.hh:104-181,
+// em/xs/MuBremsDiffXsCalculator.hh:108-200)
+//---------------------------------------------------------------------------//
+struct MuBremsDiffXs
+{
+    real atomic_number, atomic_mass, inv_cbrt_z, inc_energy, inc_mass, inc_mass_sq;
+    real total_energy, electron_mass, d_n, b, b_prime, sqrt_euler, dcs_factor;
+
+    B2_D MuBremsDiffXs(ParamsView const& pv, u32 element, Particle const& particle)
+    {
+        MuBremsstrahlungParams const& shared = pv.model.mubrems;
+        u32 const z = pv.mat.element_z[element];
+        atomic_number = real(z);
+        atomic_mass = pv.mat.element_reals[EL_NUM_REALS * element + EL_MASS];
+        inv_cbrt_z = 1 / pv.mat.element_reals[EL_NUM_REALS * element + EL_CBRT_Z];
+        inc_energy = particle.energy;
+        inc_mass = particle.mass;
+        inc_mass_sq = ipow2(inc_mass);
+        total_energy = inc_energy + inc_mass;
+        electron_mass = shared.electron_mass;
+        sqrt_euler = shared.sqrt_euler;
+        dcs_factor = shared.dcs_factor;
+        d_n = real(1.54) * pow(atomic_mass, real(0.27));
+        if (z == 1)
+        {
+            b = real(202.4);
+            b_prime = 446;
+        }
+        else
+        {
+            b = 183;
+            b_prime = 1429;
+            d_n = pow(d_n, 1 - real(1) / atomic_number);
+        }
+    }
+
+    B2_D real operator()(real energy) const
+    {
+        if (energy >= inc_energy)
+            return 0;
+        real const v = energy / total_energy;
+        real const delta = real(0.5) * inc_mass_sq * v / (total_energy - energy);
+        real const phi_n = fmax(
+            log(b * inv_cbrt_z * (inc_mass + delta * (d_n * sqrt_euler - 2))
+                / (d_n * (electron_mass + delta * sqrt_euler * b * inv_cbrt_z))),
+            real(0));
+        real const energy_max_prime
+            = total_energy / (1 + real(0.5) * inc_mass_sq / (electron_mass * total_energy));
+        real phi_e = 0;
+        if (energy < energy_max_prime)
+        {
+            real const inv_cbrt_z_sq = ipow2(inv_cbrt_z);
+            phi_e = fmax(
+                log(b_prime * inv_cbrt_z_sq * inc_mass
+                    / ((1 + delta * inc_mass / (ipow2(electron_mass) * sqrt_euler))
+                       * (electron_mass + delta * sqrt_euler * b_prime * inv_cbrt_z_sq))),
+                real(0));
+        }
+        return dcs_factor * atomic_number * (atomic_number * phi_n + phi_e)
+               * (1 - v * (1 - real(0.75) * v)) / (3 * inc_mass_sq * energy * atomic_mass);
+    }
+};
+
+B2_D Interaction interact_mu_bremsstrahlung(ParamsView const& pv,
+                                            Particle const& particle,
+                                            Real3 const& inc_direction,
+                                            u32 material,
+                                            u32 element,
+                                            Rng& rng)
+{
+    MuBremsstrahlungParams const& shared = pv.model.mubrems;
+    MuBremsDiffXs const calc_dcs(pv, element, particle);
+    real const gamma_cutoff = cutoff_energy(pv, material, shared.gamma);
+    ReciprocalDist const sample_energy(gamma_cutoff, particle.energy);
+    real const envelope = gamma_cutoff * calc_dcs(gamma_cutoff);
+
+    real gamma_energy;
+    do
+    {
+        gamma_energy = sample_energy(rng);
+    } while (gamma_energy * calc_dcs(gamma_energy) < envelope * rng.canonical());
+
+    // sample_cos_theta
+    real const gamma = particle.lorentz_factor();
+    real const r_max_sq = ipow2(gamma * constants::pi * real(0.5)
+                                * fmin(real(1), gamma * particle.mass / gamma_energy - 1));
+    real const a = rng.canonical() * r_max_sq / (1 + r_max_sq);
+    real const costheta = cos(sqrt(a / (1 - a)) / gamma);
+    return brem_final_state(particle.energy,
+                            inc_direction,
+                            particle.momentum(),
+                            shared.gamma,
+                            gamma_energy,
+                            costheta,
+                            rng);
+}
+
+//---------------------------------------------------------------------------//
 // Bremsstrahlung final state (em/interactor/detail/BremFinalStateHelper.hh)
 //---------------------------------------------------------------------------//
 B2_D Interaction brem_final_state(real inc_energy,
@@ -1324,6 +1511,20 @@ B2_D void run_interaction(ParamsView const& pv, StateView const& s, u32 slot, u3
             result = interact_relativistic_brem(pv, particle, dir, material, element, rng);
         else
             result = interact_seltzer_berger(pv, particle, dir, material, element, rng);
+    }
+    else if (action == m.muioni.bragg_action || action == m.muioni.icru73qo_action
+             || action == m.muioni.bethe_bloch_action || action == m.muioni.mu_bethe_bloch_action)
+    {
+        int const sampler = action == m.muioni.mu_bethe_bloch_action ? MUHAD_MU_BETHE_BLOCH
+                            : action == m.muioni.bethe_bloch_action  ? MUHAD_BETHE_BLOCH
+                                                                      : MUHAD_BRAGG_ICRU73QO;
+        result = interact_muhad_ionization(
+            m.muioni, sampler, particle, cutoff_energy(pv, material, m.muioni.electron), dir, rng);
+    }
+    else if (action == m.mubrems.action)
+    {
+        result = interact_mu_bremsstrahlung(
+            pv, particle, dir, material, element_of(s.element[slot]), rng);
     }
     else if (action == m.coulomb.action)
     {

@@ -442,6 +442,34 @@ struct CoulombParams
     RO<real> isotope_nuclear_mass;
 };
 
+//! Muon / hadron ionisation (em/data/MuHadIonizationData.hh): four models share one
+//! interactor and differ by the delta-ray energy distribution
+struct MuHadIonizationParams
+{
+    // action ids by energy sampler: Bragg (positive) / ICRU73QO (negative), Bethe-Bloch,
+    // muon Bethe-Bloch; INVALID when absent
+    u32 bragg_action;
+    u32 icru73qo_action;
+    u32 bethe_bloch_action;
+    u32 mu_bethe_bloch_action;
+    u32 electron;
+    real electron_mass;
+    real proton_mass;           // [MeV]
+    real alpha_over_twopi;
+};
+
+//! Muon bremsstrahlung (em/data/MuBremsstrahlungData.hh)
+struct MuBremsstrahlungParams
+{
+    u32 action;
+    u32 gamma;
+    u32 mu_minus;
+    u32 mu_plus;
+    real electron_mass;
+    real sqrt_euler;
+    real dcs_factor;  // 16 alpha N_A (m_e r_e)^2
+};
+
 struct ModelParams
 {
     KleinNishinaParams kn;
@@ -454,6 +482,8 @@ struct ModelParams
     CombinedBremParams cb;
     RayleighParams rayleigh;
     CoulombParams coulomb;
+    MuHadIonizationParams muioni;
+    MuBremsstrahlungParams mubrems;
     UrbanMscParams msc;
     FluctuationParams fluct;
     FieldParams field;

@@ -561,6 +561,38 @@ void CoreParams::load(Image const& img)
             m.rayleigh.mev = consts.at(1);
             m.rayleigh.params = arena_.upload(reals);
         }
+        m.muioni.bragg_action = m.muioni.icru73qo_action = INVALID;
+        m.muioni.bethe_bloch_action = m.muioni.mu_bethe_bloch_action = INVALID;
+        if (img.has("model.muioni.actions"))
+        {
+            auto actions = img.get<uint32_t>("model.muioni.actions");
+            auto reals = img.get<double>("model.muioni.reals");
+            if (actions.size() != 4 || reals.size() != 3)
+                throw std::runtime_error("inconsistent problem image: model.muioni.*");
+            m.muioni.bragg_action = actions[0];
+            m.muioni.icru73qo_action = actions[1];
+            m.muioni.bethe_bloch_action = actions[2];
+            m.muioni.mu_bethe_bloch_action = actions[3];
+            m.muioni.electron = img.get<uint32_t>("model.muioni.electron").at(0);
+            m.muioni.electron_mass = reals[0];
+            m.muioni.proton_mass = reals[1];
+            m.muioni.alpha_over_twopi = reals[2];
+        }
+        m.mubrems.action = INVALID;
+        if (img.has("model.mubrems.ids"))
+        {
+            auto ids = img.get<uint32_t>("model.mubrems.ids");
+            auto reals = img.get<double>("model.mubrems.reals");
+            if (ids.size() != 4 || reals.size() != 3)
+                throw std::runtime_error("inconsistent problem image: model.mubrems.*");
+            m.mubrems.action = ids[0];
+            m.mubrems.gamma = ids[1];
+            m.mubrems.mu_minus = ids[2];
+            m.mubrems.mu_plus = ids[3];
+            m.mubrems.electron_mass = reals[0];
+            m.mubrems.sqrt_euler = reals[1];
+            m.mubrems.dcs_factor = reals[2];
+        }
         m.coulomb.action = INVALID;
         if (img.has("model.coulomb.ids"))
         {
@@ -669,7 +701,11 @@ void CoreParams::load(Image const& img)
             bool const claimed = a == m.kn.action || a == m.mb.action || a == m.epgg.action
                                  || a == m.bh.action || a == m.sb.action || a == m.rb.action
                                  || a == m.pe.action || a == m.cb.action
-                                 || a == m.rayleigh.action || a == m.coulomb.action;
+                                 || a == m.rayleigh.action || a == m.coulomb.action
+                                 || a == m.muioni.bragg_action || a == m.muioni.icru73qo_action
+                                 || a == m.muioni.bethe_bloch_action
+                                 || a == m.muioni.mu_bethe_bloch_action
+                                 || a == m.mubrems.action;
             if (!claimed)
                 throw std::runtime_error(
                     "no B200 interactor for model action '"

@@ -254,10 +254,26 @@ int logic_depth(std::vector<uint32_t> const& logic)
     return cur == 1 ? max_depth : -1;
 }
 
+//! The name part of "name@ext" (corecel/io/Label.cc:40-51)
 std::string label_name(std::string const& text)
 {
     auto pos = text.rfind('@');
     return pos == std::string::npos ? text : text.substr(0, pos);
+}
+
+//! Label written to the image: the name; volumes of one unit that share a name keep their
+//! explicit extension ("box@1" .. "box@4") so that detectors can be attached to one of them
+std::string image_label(std::vector<std::string> const& labels, size_t i)
+{
+    if (labels.empty())
+        return {};
+    std::string const name = label_name(labels[i]);
+    if (name.size() + 1 >= labels[i].size())
+        return name;  // no extension
+    size_t same = 0;
+    for (std::string const& other : labels)
+        same += label_name(other) == name;
+    return same > 1 ? labels[i] : name;
 }
 
 //! A daughter placement: universe + transform data (0, 3 or 12 reals)
@@ -794,7 +810,7 @@ class Builder
                       && ((flags & F_IMPLICIT)
                           || ((flags & F_SIMPLE_SAFETY) && !(flags & F_INTERNAL)));
             last_is_background = background;
-            c_.volume_labels += label_name(labels.empty() ? std::string() : labels[i]) + "\n";
+            c_.volume_labels += image_label(labels, i) + "\n";
         }
         auto const tree = bih_(std::move(boxes));
         uint32_t const conn_begin = c_.conn_begin.size();

@@ -23,7 +23,12 @@
 #include "celeritas/em/model/LivermorePEModel.hh"
 #include "celeritas/em/model/MollerBhabhaModel.hh"
 #include "celeritas/em/model/RayleighModel.hh"
+#include "celeritas/em/model/BetheBlochModel.hh"
+#include "celeritas/em/model/BraggModel.hh"
 #include "celeritas/em/model/CombinedBremModel.hh"
+#include "celeritas/em/model/ICRU73QOModel.hh"
+#include "celeritas/em/model/MuBetheBlochModel.hh"
+#include "celeritas/em/model/MuBremsstrahlungModel.hh"
 #include "celeritas/em/model/CoulombScatteringModel.hh"
 #include "celeritas/em/params/WentzelOKVIParams.hh"
 #include "celeritas/em/xs/NuclearFormFactors.hh"
@@ -528,10 +533,38 @@ void export_physics(HostCRef<PhysicsParamsData> const& p,
 }
 
 //---------------------------------------------------------------------------//
+//! Volume labels of the image: the name; volumes of one universe that share a name keep
+//! their extension ("box@1" .. "box@4", corecel/io/Label.cc:59-71) so that a detector can
+//! be attached to one of them
+template<class GeoParamsT>
+std::string image_volume_labels(GeoParamsT const& geo)
+{
+    auto const& offsets = geo.host_ref().universe_indexer_data.volumes;
+    std::string labels;
+    for (size_t u = 0; u + 1 < offsets.size(); ++u)
+    {
+        size_t const begin = offsets[AllItems<size_type>{}][u];
+        size_t const end = offsets[AllItems<size_type>{}][u + 1];
+        for (size_t v = begin; v < end; ++v)
+        {
+            Label const& lab = geo.volumes().at(VolumeId(v));
+            size_t same = 0;
+            for (size_t w = begin; w < end; ++w)
+                same += geo.volumes().at(VolumeId(w)).name == lab.name;
+            labels += (same > 1 && !lab.ext.empty())
+                          ? lab.name + Label::default_sep + lab.ext
+                          : lab.name;
+            labels += "\n";
+        }
+    }
+    return labels;
+}
+
 void export_models(Problem const& prob, b200::Image& img)
 {
     PhysicsParams const& phys = *prob.core->physics();
     U32 model_kind(phys.num_models(), 0);
+    U32 muioni_actions(4, 0xffffffffu);  // Bragg, ICRU73QO, Bethe-Bloch, mu Bethe-Bloch
     std::string labels;
     auto put_sb = [&img](uint32_t action,
                          uint32_t electron,
@@ -697,6 +730,60 @@ void export_models(Problem const& prob, b200::Image& img)
             img.put("model.pe.shell_reals", sh_reals);
             F64 reals(all(d.xs.reals).begin(), all(d.xs.reals).end());
             img.put("model.pe.reals", reals);
+        }
+        else if (dynamic_cast<BraggModel const*>(&model)
+                 || dynamic_cast<ICRU73QOModel const*>(&model)
+                 || dynamic_cast<BetheBlochModel const*>(&model)
+                 || dynamic_cast<MuBetheBlochModel const*>(&model))
+        {
+            // em/data/MuHadIonizationData.hh: one interactor, four energy samplers
+            MuHadIonizationData const* d = nullptr;
+            uint32_t which = 0;
+            if (auto* m = dynamic_cast<BraggModel const*>(&model))
+            {
+                d = &m->host_ref();
+                which = 0;
+            }
+            else if (auto* m = dynamic_cast<ICRU73QOModel const*>(&model))
+            {
+                d = &m->host_ref();
+                which = 1;
+            }
+            else if (auto* m = dynamic_cast<BetheBlochModel const*>(&model))
+            {
+                d = &m->host_ref();
+                which = 2;
+            }
+            else if (auto* m = dynamic_cast<MuBetheBlochModel const*>(&model))
+            {
+                d = &m->host_ref();
+                which = 3;
+            }
+            muioni_actions[which] = model.action_id().unchecked_get();
+            img.put("model.muioni.electron", U32{raw(d->electron)});
+            img.put("model.muioni.reals",
+                    F64{d->electron_mass.value(),
+                        native_value_to<units::MevMass>(constants::proton_mass)
+                            .value(),
+                        constants::alpha_fine_structure / (2 * constants::pi)});
+            img.put("model.muioni.actions", muioni_actions);
+        }
+        else if (auto* mub = dynamic_cast<MuBremsstrahlungModel const*>(&model))
+        {
+            auto const& d = mub->host_ref();
+            img.put("model.mubrems.ids",
+                    U32{mub->action_id().unchecked_get(),
+                        raw(d.gamma),
+                        raw(d.mu_minus),
+                        raw(d.mu_plus)});
+            real_type const me = d.electron_mass.value();
+            // em/xs/MuBremsDiffXsCalculator.hh:147,195-197
+            img.put("model.mubrems.reals",
+                    F64{me,
+                        std::sqrt(constants::euler),
+                        16 * constants::alpha_fine_structure
+                            * constants::na_avogadro
+                            * ipow<2>(me * constants::r_electron)});
         }
         else if (auto* cs = dynamic_cast<CoulombScatteringModel const*>(&model))
         {
@@ -941,10 +1028,7 @@ b200::Image build_image(Problem const& prob)
         // Geometry-only image
         CELER_VALIDATE(prob.geo, << "empty problem");
         export_geometry(prob.geo->host_ref(), img);
-        std::string labels;
-        for (auto v : range(VolumeId{prob.geo->volumes().size()}))
-            labels += prob.geo->volumes().at(v).name + "\n";
-        img.put_string("geo.volume_labels", labels);
+        img.put_string("geo.volume_labels", image_volume_labels(*prob.geo));
         return img;
     }
     CoreParams const& core = *prob.core;
@@ -983,11 +1067,7 @@ b200::Image build_image(Problem const& prob)
             vm.push_back(raw(m));
         img.put("geomat.volume_material", vm);
         // volume labels (for detector maps / diagnostics)
-        std::string labels;
-        auto const& geo = *core.geometry();
-        for (auto v : range(VolumeId{geo.volumes().size()}))
-            labels += geo.volumes().at(v).name + "\n";
-        img.put_string("geo.volume_labels", labels);
+        img.put_string("geo.volume_labels", image_volume_labels(*core.geometry()));
     }
     export_materials(ref.materials, img);
 

@@ -285,15 +285,15 @@ def test_celer_sim_builds_the_geometry_from_geometry_file(tmp_path):
 def test_celer_sim_reads_physics_file():
     """`physics_file` is read: a reference ROOT export is decoded by the
     library's own reader and must hold the particles and elements the image's tables were
-    built for. simple-cms.b2img was exported from data/physics/simple-cms.json, the decoded
-    form of the reference's test/celeritas/data/simple-cms.root."""
+    built for. lar-sphere-combined.b2img was exported from data/physics/lar-sphere-em.json,
+    derived from the decoded form of the reference's test/celeritas/data/lar-sphere.root."""
     import celeritas_b200 as cb
-    cfg = json.load(open(data_path('images', 'simple-cms.json')))
+    cfg = json.load(open(data_path('images', 'lar-sphere-combined.json')))
     run_input = {
         '_format': 'celer-sim', 'use_device': True,
-        'image_file': 'data/images/simple-cms.b2img', 'base_dir': REPO,
+        'image_file': 'data/images/lar-sphere-combined.b2img', 'base_dir': REPO,
         'geometry_file': cfg['geometry_file'],
-        'physics_file': 'tests/golden/root/simple-cms.root',
+        'physics_file': 'tests/golden/root/lar-sphere.root',
         'primary_options': {
             '_format': 'primary-generator', 'seed': 1, 'pdg': [11, 22], 'num_events': 1,
             'primaries_per_event': 8,
@@ -302,13 +302,15 @@ def test_celer_sim_reads_physics_file():
             'direction': {'distribution': 'isotropic'}},
         'seed': cfg['seed'], 'num_track_slots': 2048,
         'initializer_capacity': cfg['initializer_capacity'], 'secondary_stack_factor': 3,
+        'simple_calo': cfg['simple_calo'], 'brem_combined': True, 'max_steps': 100000,
     }
     out = cb.celer_sim_run(run_input)
     assert out['result']['runner']['num_steps'][0] > 50
+    assert out['result']['runner']['num_aborted'] == [0]
     assert 'particles' in out['internal']['physics_file']
     as_json = cb.celer_sim_run(dict(run_input, physics_file=cfg['physics_file']))
     assert as_json['result']['runner']['num_steps'] == out['result']['runner']['num_steps']
-    # liquid argon only: not the physics of an image with silicon / lead / iron tables
+    # silicon / lead / iron ...: not the physics of an image with liquid-argon tables
     with pytest.raises(cb.B200Error) as e:
-        cb.celer_sim_run(dict(run_input, physics_file='tests/golden/root/lar-sphere.root'))
+        cb.celer_sim_run(dict(run_input, physics_file='tests/golden/root/simple-cms.root'))
     assert 'physics_file' in str(e.value)

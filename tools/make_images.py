@@ -115,6 +115,11 @@ PROBLEMS['four-steel-slabs-coulomb'] = dict(
     PROBLEMS['four-steel-slabs-rayleigh'],
     physics_file='data/physics/four-steel-slabs-em-coulomb.json')
 
+# ... and the export's muons: mu-/mu+ ionisation (four models) and muon bremsstrahlung
+PROBLEMS['four-steel-slabs-muon'] = dict(
+    PROBLEMS['four-steel-slabs-rayleigh'],
+    physics_file='data/physics/four-steel-slabs-em-muon.json')
+
 # Geometry-only images for the navigation (ray-trace) parity tests: the ORANGE test
 # geometries of the reference (test/orange/data, test/geocel/data)
 for _g in ('two-boxes', 'testem3-flat', 'testem3', 'simple-cms', 'five-volumes', 'universes',

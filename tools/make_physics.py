@@ -116,16 +116,16 @@ def extend_coulomb_down(data, emin=1e-4):
                 mm['micro_xs'] = [[xs[0]] * n + xs for xs in mm['micro_xs']]
 
 
-def filter_physics(data, keep_process=KEEP_PROCESS):
+def filter_physics(data, keep_process=KEEP_PROCESS, keep_pdg=KEEP_PDG):
     extend_urban_msc(data)
-    data['particles'] = [p for p in data['particles'] if p['pdg'] in KEEP_PDG]
+    data['particles'] = [p for p in data['particles'] if p['pdg'] in keep_pdg]
     data['processes'] = [p for p in data['processes']
-                         if p['particle_pdg'] in KEEP_PDG and p['process_class'] in keep_process]
-    data['msc_models'] = [m for m in data['msc_models'] if m['particle_pdg'] in KEEP_PDG]
+                         if p['particle_pdg'] in keep_pdg and p['process_class'] in keep_process]
+    data['msc_models'] = [m for m in data['msc_models'] if m['particle_pdg'] in keep_pdg]
     for pm in data['phys_materials']:
-        pm['pdg_cutoffs'] = [c for c in pm['pdg_cutoffs'] if c['first'] in KEEP_PDG]
+        pm['pdg_cutoffs'] = [c for c in pm['pdg_cutoffs'] if c['first'] in keep_pdg]
     tp = data['trans_params']
-    tp['looping'] = {k: v for k, v in tp['looping'].items() if int(k) in KEEP_PDG}
+    tp['looping'] = {k: v for k, v in tp['looping'].items() if int(k) in keep_pdg}
     data['mu_pair_production_data'] = {'atomic_number': [], 'physics_vectors': []}
 
 
@@ -282,6 +282,18 @@ def main():
                      [('box', 1), ('World', 0)])
     add_element_data(steel_cs)
     json.dump(steel_cs, open(os.path.join(PHYS, 'four-steel-slabs-em-coulomb.json'), 'w'),
+              separators=(',', ':'))
+
+    # ... and with the muons of the export: mu-/mu+ ionisation (ICRU73QO / Bragg below
+    # 200 keV, Bethe-Bloch to 1 GeV, muon Bethe-Bloch above; ImportProcessClass::mu_ioni = 14)
+    # and muon bremsstrahlung above 1 GeV (mu_brems = 15). The export has no multiple
+    # scattering or pair production for muons.
+    steel_mu = load('four-steel-slabs')
+    filter_physics(steel_mu, KEEP_PROCESS + (12, 14, 15), KEEP_PDG + (-13, 13))
+    steel_mu = merge([(steel_mu, 'G4_Galactic'), (steel_mu, 'G4_STAINLESS-STEEL')],
+                     [('box', 1), ('World', 0)])
+    add_element_data(steel_mu)
+    json.dump(steel_mu, open(os.path.join(PHYS, 'four-steel-slabs-em-muon.json'), 'w'),
               separators=(',', ':'))
 
 
