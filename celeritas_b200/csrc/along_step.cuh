@@ -1033,8 +1033,9 @@ B2_D void along_phase_msc_limit(ParamsView const& p, StateView const& s, u32 slo
 }
 
 //! Phase 2: propagation through the geometry. FIELD is a property of the problem (the
-//! along-step action it was built with), so it selects the kernel at launch.
-template<bool FIELD>
+//! along-step action it was built with), so it selects the kernel at launch: 0 = none,
+//! 1 = uniform field, 2 = r-z map field.
+template<int FIELD>
 B2_D void along_phase_propagate(ParamsView const& p, StateView const& s, u32 slot)
 {
     if (s.step_length[slot] == 0)
@@ -1042,11 +1043,11 @@ B2_D void along_phase_propagate(ParamsView const& p, StateView const& s, u32 slo
     Particle particle = load_particle(p, s, slot);
     GeoTrack geo(p, s, slot);
     Propagation pr;
-    if constexpr (FIELD)
-        pr = propagate_field(p, particle, geo, s.step_length[slot]);
+    if constexpr (FIELD != 0)
+        pr = propagate_field_impl<FIELD == 2>(p, particle, geo, s.step_length[slot]);
     else
         pr = propagate_linear(geo, s.step_length[slot]);
-    apply_propagation(p, s, slot, pr, FIELD, particle);
+    apply_propagation(p, s, slot, pr, FIELD != 0, particle);
 }
 
 //! Phase 3: MSC scattering and displacement
@@ -1073,14 +1074,14 @@ B2_D void along_phase_finish(ParamsView const& p, StateView const& s, u32 slot)
 //! Whole along-step for one alive track. CHARGED is a compile-time property of the
 //! launch (dense per-charge slot lists), so the neutral kernel carries no msc/eloss code.
 //! COOP: the warp's 32 lanes all run this track (see GeoTrackT in orange.cuh).
-template<bool CHARGED, bool FIELD, bool COOP = false>
+template<bool CHARGED, int FIELD, bool COOP = false>
 B2_D void along_step(ParamsView const& p, StateView const& s, u32 slot)
 {
     Particle particle = load_particle(p, s, slot);
     GeoTrackT<COOP> geo(p, s, slot);
     PhysTrack phys(p, particle.id, s.material_id[slot]);
     constexpr bool charged = CHARGED;
-    constexpr bool use_field = CHARGED && FIELD;
+    constexpr bool use_field = CHARGED && FIELD != 0;
 
     // msc step limit
     bool use_msc = false;
@@ -1101,7 +1102,7 @@ B2_D void along_step(ParamsView const& p, StateView const& s, u32 slot)
     {
         Propagation pr;
         if constexpr (use_field)
-            pr = propagate_field(p, particle, geo, s.step_length[slot]);
+            pr = propagate_field_impl<FIELD == 2>(p, particle, geo, s.step_length[slot]);
         else
             pr = propagate_linear(geo, s.step_length[slot]);
         apply_propagation(p, s, slot, pr, use_field, particle);

@@ -66,45 +66,55 @@ struct FieldStepperResult
 #endif
 
 //! The magnetic field seen by the equation of motion: a constant vector (UniformField) or
-//! the r-z map (RZMapField::operator(), field/RZMapField.hh:67-106)
+//! the r-z map (RZMapField::operator(), field/RZMapField.hh:67-106). The kind is a
+//! compile-time parameter: as a run-time branch inside the right-hand side (seven
+//! evaluations per Dormand-Prince trial) the map code cost the UNIFORM-field problems 35 % of
+//! their along-step (CMS-scale pass 351 -> 433 ms, profiles/README_r02.md).
+template<bool RZ>
 struct FieldSource
 {
     Real3 uniform;
-    FieldParams const* map;  // null: uniform
+    FieldParams const* map;
 
     B2_D Real3 operator()(Real3 const& pos) const
     {
-        if (!map)
+        if constexpr (!RZ)
+        {
             return uniform;
-        FieldParams const& f = *map;
-        Real3 value = make_real3(0, 0, 0);
-        real const r = sqrt(ipow2(pos[0]) + ipow2(pos[1]));
-        real const z = pos[2];
-        if (!(z >= f.rz_z[0] && z <= f.rz_z[1] && r >= f.rz_r[0] && r <= f.rz_r[1]))
+        }
+        else
+        {
+            FieldParams const& f = *map;
+            Real3 value = make_real3(0, 0, 0);
+            real const r = sqrt(ipow2(pos[0]) + ipow2(pos[1]));
+            real const z = pos[2];
+            if (!(z >= f.rz_z[0] && z <= f.rz_z[1] && r >= f.rz_r[0] && r <= f.rz_r[1]))
+                return value;
+            // find_interp<UniformGrid> (corecel/grid/FindInterp.hh:43-57)
+            u32 const ir = static_cast<u32>((r - f.rz_r[0]) / f.rz_r[2]);
+            u32 const iz = static_cast<u32>((z - f.rz_z[0]) / f.rz_z[2]);
+            real const r_lo = f.rz_r[0] + f.rz_r[2] * ir, r_hi = f.rz_r[0] + f.rz_r[2] * (ir + 1);
+            real const z_lo = f.rz_z[0] + f.rz_z[2] * iz, z_hi = f.rz_z[0] + f.rz_z[2] * (iz + 1);
+            real const frac_r = (r - r_lo) / (r_hi - r_lo);
+            real const frac_z = (z - z_lo) / (z_hi - z_lo);
+            real const* v = f.rz_values;
+            u32 const nr = f.rz_size_r;
+            real low = v[2 * (iz * nr + ir)];
+            real high = v[2 * ((iz + 1) * nr + ir)];
+            value[2] = low + (high - low) * frac_z;
+            low = v[2 * (iz * nr + ir) + 1];
+            high = v[2 * (iz * nr + ir + 1) + 1];
+            real const tmp = (r != 0) ? (low + (high - low) * frac_r) / r : low;
+            value[0] = tmp * pos[0];
+            value[1] = tmp * pos[1];
             return value;
-        // find_interp<UniformGrid> (corecel/grid/FindInterp.hh:43-57)
-        u32 const ir = static_cast<u32>((r - f.rz_r[0]) / f.rz_r[2]);
-        u32 const iz = static_cast<u32>((z - f.rz_z[0]) / f.rz_z[2]);
-        real const r_lo = f.rz_r[0] + f.rz_r[2] * ir, r_hi = f.rz_r[0] + f.rz_r[2] * (ir + 1);
-        real const z_lo = f.rz_z[0] + f.rz_z[2] * iz, z_hi = f.rz_z[0] + f.rz_z[2] * (iz + 1);
-        real const frac_r = (r - r_lo) / (r_hi - r_lo);
-        real const frac_z = (z - z_lo) / (z_hi - z_lo);
-        real const* v = f.rz_values;
-        u32 const nr = f.rz_size_r;
-        real low = v[2 * (iz * nr + ir)];
-        real high = v[2 * ((iz + 1) * nr + ir)];
-        value[2] = low + (high - low) * frac_z;
-        low = v[2 * (iz * nr + ir) + 1];
-        high = v[2 * (iz * nr + ir + 1) + 1];
-        real const tmp = (r != 0) ? (low + (high - low) * frac_r) / r : low;
-        value[0] = tmp * pos[0];
-        value[1] = tmp * pos[1];
-        return value;
+        }
     }
 };
 
 //! Right-hand side of the equation of motion
-B2_FIELD_RHS_FN OdeState field_rhs(real coeffi, FieldSource const& source, OdeState const& y)
+template<bool RZ>
+B2_FIELD_RHS_FN OdeState field_rhs(real coeffi, FieldSource<RZ> const& source, OdeState const& y)
 {
     real momentum_inv = 1 / sqrt(dot(y.mom, y.mom));
     OdeState r;
@@ -117,7 +127,8 @@ B2_FIELD_RHS_FN OdeState field_rhs(real coeffi, FieldSource const& source, OdeSt
 }
 
 //! One Dormand-Prince trial step
-B2_FIELD_STEP_FN void field_apply_step(real coeffi, FieldSource const& field, real step, OdeState const& beg, FieldStepperResult& result)
+template<bool RZ>
+B2_FIELD_STEP_FN void field_apply_step(real coeffi, FieldSource<RZ> const& field, real step, OdeState const& beg, FieldStepperResult& result)
 {
     using R = real;
     constexpr R a11 = 0.2;
@@ -205,18 +216,19 @@ B2_FIELD_STEP_FN void field_apply_step(real coeffi, FieldSource const& field, re
 }
 
 
+template<bool RZ>
 struct FieldDriver
 {
     FieldParams const& opt;
     real coeffi;     // charge / momentum unit
-    FieldSource field;
+    FieldSource<RZ> field;
     real max_chord;
 
     B2_D FieldDriver(FieldParams const& f, real charge) : opt(f), max_chord(real_inf())
     {
         coeffi = charge * f.coeffi_per_charge;
         field.uniform = make_real3(f.field[0], f.field[1], f.field[2]);
-        field.map = f.rz_values ? &f : nullptr;
+        field.map = &f;
     }
 
     //! One Dormand-Prince trial step
@@ -391,11 +403,11 @@ struct FieldDriver
 };
 
 //! Propagate a charged track in the field up to `step` or the next boundary
-template<class Geo>
-B2_D Propagation propagate_field(ParamsView const& p, Particle const& particle, Geo& geo, real step)
+template<bool RZ, class Geo>
+B2_D Propagation propagate_field_impl(ParamsView const& p, Particle const& particle, Geo& geo, real step)
 {
     FieldParams const& opt = p.model.field;
-    FieldDriver driver(opt, particle.charge);
+    FieldDriver<RZ> driver(opt, particle.charge);
     OdeState state;
     state.pos = geo.pos();
     {
@@ -415,7 +427,7 @@ B2_D Propagation propagate_field(ParamsView const& p, Particle const& particle, 
     int remaining_substeps = static_cast<int>(opt.max_substeps);
     do
     {
-        FieldDriver::DriverResult substep = driver.advance(remaining, state);
+        typename FieldDriver<RZ>::DriverResult substep = driver.advance(remaining, state);
         // make_chord
         Real3 cdir = make_real3(substep.state.pos[0] - state.pos[0],
                                 substep.state.pos[1] - state.pos[1],

@@ -237,11 +237,16 @@ B2_D Interaction interact_klein_nishina(KleinNishinaParams const& shared,
 }
 
 //---------------------------------------------------------------------------//
+// The interactors beyond the north star's list (Rayleigh, Coulomb, muons) are out-of-line
+// calls: the fused step and the device-resident loop carry every interactor, and these are
+// never run by the benchmark problems; out of line they stay out of those kernels' register
+// allocation.
+//
 // Rayleigh scattering (em/interactor/RayleighInteractor.hh:107-199): coherent scattering off
 // the element chosen by the discrete selection; the angle is drawn from a three-term fit of
 // the squared form factor, the energy is unchanged and nothing is deposited
 //---------------------------------------------------------------------------//
-B2_D Interaction interact_rayleigh(RayleighParams const& shared,
+B2_NOINLINE inline Interaction interact_rayleigh(RayleighParams const& shared,
                                    real inc_energy,
                                    Real3 const& inc_direction,
                                    u32 element,
@@ -435,7 +440,7 @@ B2_D real nuclear_form_factor(CoulombParams const& w, u32 isotope, real mt_sq)
     }
 }
 
-B2_D Interaction interact_coulomb(ParamsView const& pv,
+B2_NOINLINE inline Interaction interact_coulomb(ParamsView const& pv,
                                   Particle const& particle,
                                   Real3 const& inc_direction,
                                   u32 material,
@@ -875,7 +880,7 @@ B2_D Interaction interact_bethe_heitler(ParamsView const& pv,
 //---------------------------------------------------------------------------//
 enum MuHadSampler { MUHAD_BRAGG_ICRU73QO, MUHAD_BETHE_BLOCH, MUHAD_MU_BETHE_BLOCH };
 
-B2_D Interaction interact_muhad_ionization(MuHadIonizationParams const& shared,
+B2_NOINLINE inline Interaction interact_muhad_ionization(MuHadIonizationParams const& shared,
                                            int sampler,
                                            Particle const& particle,
                                            real electron_cutoff,
@@ -1021,7 +1026,7 @@ struct MuBremsDiffXs
     }
 };
 
-B2_D Interaction interact_mu_bremsstrahlung(ParamsView const& pv,
+B2_NOINLINE inline Interaction interact_mu_bremsstrahlung(ParamsView const& pv,
                                             Particle const& particle,
                                             Real3 const& inc_direction,
                                             u32 material,

@@ -8,7 +8,7 @@
 
 namespace b200
 {
-template<bool FIELD, bool SELECT>
+template<int FIELD, bool SELECT>
 __global__ void __launch_bounds__(B2_ALONG_BLOCK, (FIELD ? B2_ALONG_FIELD_MIN_BLOCKS : ALONG_MIN_BLOCKS) * BLOCK / B2_ALONG_BLOCK) k_along_step_charged(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 tid = thread_id();
@@ -38,8 +38,9 @@ __global__ void __launch_bounds__(B2_ALONG_BLOCK, (FIELD ? B2_ALONG_FIELD_MIN_BL
         PHASE(p, s, slot);                                                               \
     }
 B2_ALONG_PHASE_KERNEL(k_along_msc_limit, along_phase_msc_limit, B2_PHASE_MIN_BLOCKS)
-B2_ALONG_PHASE_KERNEL(k_along_propagate_linear, along_phase_propagate<false>, B2_PHASE_MIN_BLOCKS)
-B2_ALONG_PHASE_KERNEL(k_along_propagate_field, along_phase_propagate<true>, B2_PROPAGATE_FIELD_MIN_BLOCKS)
+B2_ALONG_PHASE_KERNEL(k_along_propagate_linear, along_phase_propagate<0>, B2_PHASE_MIN_BLOCKS)
+B2_ALONG_PHASE_KERNEL(k_along_propagate_field, along_phase_propagate<1>, B2_PROPAGATE_FIELD_MIN_BLOCKS)
+B2_ALONG_PHASE_KERNEL(k_along_propagate_rzfield, along_phase_propagate<2>, B2_PROPAGATE_FIELD_MIN_BLOCKS)
 B2_ALONG_PHASE_KERNEL(k_along_msc_apply, along_phase_msc_apply, B2_PHASE_MIN_BLOCKS)
 B2_ALONG_PHASE_KERNEL(k_along_finish, along_phase_finish, B2_PHASE_MIN_BLOCKS)
 #undef B2_ALONG_PHASE_KERNEL
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(B2_ALONG_BLOCK, B2_NEUTRAL_MIN_BLOCKS * BLOCK 
     {
         prefetch_along_step_state<false>(s, slot);
         if (s.status[slot] == ST_ALIVE)
-            along_step<false, false>(p, s, slot);
+            along_step<false, 0>(p, s, slot);
     }
     if (SELECT)
         select_and_append(p, s, slot);
@@ -81,7 +82,9 @@ int b200_step_along_step(B200ParamsView const* params, B200StateView const* stat
         unsigned const grid = grid_for(nc);
         if (p.model.msc.enabled)
             k_along_msc_limit<<<grid, BLOCK, 0, stream>>>(p, s);
-        if (p.model.field.enabled)
+        if (p.model.field.enabled && p.model.field.rz_values)
+            k_along_propagate_rzfield<<<grid, BLOCK, 0, stream>>>(p, s);
+        else if (p.model.field.enabled)
             k_along_propagate_field<<<grid, BLOCK, 0, stream>>>(p, s);
         else
             k_along_propagate_linear<<<grid, BLOCK, 0, stream>>>(p, s);
@@ -92,10 +95,12 @@ int b200_step_along_step(B200ParamsView const* params, B200StateView const* stat
     }
     else if (nc > 0)
     {
-        if (PV(params).model.field.enabled)
-            k_along_step_charged<true, false><<<(nc + B2_ALONG_BLOCK - 1) / B2_ALONG_BLOCK, B2_ALONG_BLOCK, 0, stream>>>(PV(params), s);
+        if (PV(params).model.field.enabled && PV(params).model.field.rz_values)
+            k_along_step_charged<2, false><<<(nc + B2_ALONG_BLOCK - 1) / B2_ALONG_BLOCK, B2_ALONG_BLOCK, 0, stream>>>(PV(params), s);
+        else if (PV(params).model.field.enabled)
+            k_along_step_charged<1, false><<<(nc + B2_ALONG_BLOCK - 1) / B2_ALONG_BLOCK, B2_ALONG_BLOCK, 0, stream>>>(PV(params), s);
         else
-            k_along_step_charged<false, false><<<(nc + B2_ALONG_BLOCK - 1) / B2_ALONG_BLOCK, B2_ALONG_BLOCK, 0, stream>>>(PV(params), s);
+            k_along_step_charged<0, false><<<(nc + B2_ALONG_BLOCK - 1) / B2_ALONG_BLOCK, B2_ALONG_BLOCK, 0, stream>>>(PV(params), s);
         B2_COUNT(1);
     }
     if (nn > 0)
@@ -115,10 +120,12 @@ int b200_step_along_select(B200ParamsView const* params, B200StateView const* st
     u32 nn = s.hint_neutral < s.num_slots ? s.hint_neutral : s.num_slots;
     if (nc > 0)
     {
-        if (PV(params).model.field.enabled)
-            k_along_step_charged<true, true><<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
+        if (PV(params).model.field.enabled && PV(params).model.field.rz_values)
+            k_along_step_charged<2, true><<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
+        else if (PV(params).model.field.enabled)
+            k_along_step_charged<1, true><<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
         else
-            k_along_step_charged<false, true><<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
+            k_along_step_charged<0, true><<<grid_for(nc), BLOCK, 0, stream>>>(PV(params), s);
         B2_COUNT(1);
     }
     if (nn > 0)

@@ -19,7 +19,7 @@ namespace b200
 // device-resident loop, profiles/README_r02.md: 16..128 tracks 85 -> 46 us per iteration
 // on TestEm3, 366 -> 257 us on the CMS-scale stand-in); with many, num_warps = tracks / 32 and
 // the mapping is the dense one.
-template<bool FIELD>
+template<int FIELD>
 __global__ void __launch_bounds__(BLOCK, B2_FUSED_MIN_BLOCKS)
     k_step_fused(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s, u32 num_warps)
 {
@@ -58,10 +58,12 @@ int b200_step_fused(B200ParamsView const* params, B200StateView const* state, cu
     u32 const num_warps = std::max<u32>(
         n <= spread_max_tracks ? std::max<u32>(dense, std::min<u32>(n, spread_warps)) : dense, 1u);
     unsigned const grid = grid_for(num_warps * 32u);
-    if (PV(params).model.field.enabled)
-        k_step_fused<true><<<grid, BLOCK, 0, stream>>>(PV(params), s, num_warps);
+    if (PV(params).model.field.enabled && PV(params).model.field.rz_values)
+        k_step_fused<2><<<grid, BLOCK, 0, stream>>>(PV(params), s, num_warps);
+    else if (PV(params).model.field.enabled)
+        k_step_fused<1><<<grid, BLOCK, 0, stream>>>(PV(params), s, num_warps);
     else
-        k_step_fused<false><<<grid, BLOCK, 0, stream>>>(PV(params), s, num_warps);
+        k_step_fused<0><<<grid, BLOCK, 0, stream>>>(PV(params), s, num_warps);
     B2_COUNT(1);
     return check_launch();
 }

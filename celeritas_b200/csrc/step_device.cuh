@@ -582,7 +582,7 @@ constexpr u32 DIAG_SMEM_BINS = 1024;
 //---------------------------------------------------------------------------//
 //! COOP: called by all 32 lanes of a warp with the same `tid` (warp-cooperative navigation,
 //! orange.cuh); everything but the face searches runs redundantly, tallies by lane 0 only.
-template<bool FIELD, bool COOP = false>
+template<int FIELD, bool COOP = false>
 B2_D void step_fused_slot(ParamsView const& p, StateView const& s, u32 slot, bool charged)
 {
     bool const tally_lane = !COOP || (threadIdx.x & 31u) == 0;
@@ -627,7 +627,7 @@ B2_D void step_fused_slot(ParamsView const& p, StateView const& s, u32 slot, boo
     }
 }
 
-template<bool FIELD>
+template<int FIELD>
 B2_D void step_fused_track(ParamsView const& p, StateView const& s, u32 tid)
 {
     u32 const slot = active_slot(s, tid);
@@ -763,7 +763,7 @@ B2_D void shadow_store(StateView const& s, u32 slot, ShadowSlot const& buf)
 //! Whole step of the tid-th active track by ONE thread on a private copy of its state
 //! (experiment: is it the private copy or the shared searches that makes the cooperative
 //! step faster? see profiles/README_r02.md)
-template<bool FIELD>
+template<int FIELD>
 B2_D void step_fused_track_shadow(ParamsView const& p, StateView const& s, u32 tid)
 {
     u32 const slot = active_slot(s, tid);
@@ -778,7 +778,7 @@ B2_D void step_fused_track_shadow(ParamsView const& p, StateView const& s, u32 t
 }
 
 //! Whole step of the tid-th active track by the calling WARP (all 32 lanes)
-template<bool FIELD>
+template<int FIELD>
 B2_D void step_fused_track_coop(ParamsView const& p, StateView const& s, u32 tid)
 {
     u32 const slot = active_slot(s, tid);

@@ -19,8 +19,10 @@ int b200_tail_max_blocks(B200ParamsView const* params, int* out)
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess)
     {
-        e = PV(params).model.field.enabled ? tail_blocks_per_sm_field(&per_sm)
-                                           : tail_blocks_per_sm_nofield(&per_sm);
+        FieldParams const& f = PV(params).model.field;
+        e = !f.enabled ? tail_blocks_per_sm_nofield(&per_sm)
+            : f.rz_values ? tail_blocks_per_sm_rzfield(&per_sm)
+                          : tail_blocks_per_sm_field(&per_sm);
     }
     if (e != cudaSuccess)
         return static_cast<int>(e);
@@ -53,8 +55,10 @@ int b200_step_tail_loop(B200ParamsView const* params,
     u32 const coop_max = std::min<u32>(coop_max_env, num_blocks * (BLOCK / 32));
     TailArgs args{max_iterations, exit_active, ring, done, coop, coop_max};
     ParamsView const& p = PV(params);
-    cudaError_t const e = p.model.field.enabled ? tail_launch_field(p, s, args, num_blocks, stream)
-                                                : tail_launch_nofield(p, s, args, num_blocks, stream);
+    FieldParams const& f = p.model.field;
+    cudaError_t const e = !f.enabled    ? tail_launch_nofield(p, s, args, num_blocks, stream)
+                          : f.rz_values ? tail_launch_rzfield(p, s, args, num_blocks, stream)
+                                        : tail_launch_field(p, s, args, num_blocks, stream);
     B2_COUNT(1);
     return e == cudaSuccess ? check_launch() : static_cast<int>(e);
 }

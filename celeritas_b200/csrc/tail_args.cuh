@@ -19,9 +19,12 @@ struct TailArgs
 };
 
 cudaError_t tail_blocks_per_sm_field(int* per_sm);
+cudaError_t tail_blocks_per_sm_rzfield(int* per_sm);
 cudaError_t tail_blocks_per_sm_nofield(int* per_sm);
 cudaError_t tail_launch_field(ParamsView const&, StateView const&, TailArgs const&, u32 num_blocks,
                               cudaStream_t);
+cudaError_t tail_launch_rzfield(ParamsView const&, StateView const&, TailArgs const&,
+                                u32 num_blocks, cudaStream_t);
 cudaError_t tail_launch_nofield(ParamsView const&, StateView const&, TailArgs const&,
                                 u32 num_blocks, cudaStream_t);
 }  // namespace b200

@@ -120,7 +120,7 @@ enum TailExit : u32
     TAIL_EXIT_ERROR            // device error flag set (CTR_ERROR)
 };
 
-template<bool FIELD>
+template<int FIELD>
 __global__ void B2_LOOP_BOUNDS
     k_tail_loop(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s, TailArgs const a)
 {
@@ -479,13 +479,13 @@ __global__ void B2_LOOP_BOUNDS
 }
 
 //! Resident blocks per SM and cooperative launch of one instantiation
-template<bool FIELD>
+template<int FIELD>
 inline cudaError_t tail_blocks_per_sm(int* per_sm)
 {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_tail_loop<FIELD>, BLOCK, 0);
 }
 
-template<bool FIELD>
+template<int FIELD>
 inline cudaError_t tail_launch(ParamsView const& p,
                                StateView const& s,
                                TailArgs const& a,

@@ -1,15 +1,15 @@
-// k_tail_loop<false>: see tail_loop.cuh
+// k_tail_loop<0>: see tail_loop.cuh
 #include "tail_loop.cuh"
 
 namespace b200
 {
 cudaError_t tail_blocks_per_sm_nofield(int* per_sm)
 {
-    return tail_blocks_per_sm<false>(per_sm);
+    return tail_blocks_per_sm<0>(per_sm);
 }
 cudaError_t tail_launch_nofield(ParamsView const& p, StateView const& s, TailArgs const& a,
                            u32 num_blocks, cudaStream_t stream)
 {
-    return tail_launch<false>(p, s, a, num_blocks, stream);
+    return tail_launch<0>(p, s, a, num_blocks, stream);
 }
 }  // namespace b200

@@ -1,0 +1,15 @@
+// k_tail_loop<2> (r-z map field): see tail_loop.cuh
+#include "tail_loop.cuh"
+
+namespace b200
+{
+cudaError_t tail_blocks_per_sm_rzfield(int* per_sm)
+{
+    return tail_blocks_per_sm<2>(per_sm);
+}
+cudaError_t tail_launch_rzfield(ParamsView const& p, StateView const& s, TailArgs const& a,
+                                u32 num_blocks, cudaStream_t stream)
+{
+    return tail_launch<2>(p, s, a, num_blocks, stream);
+}
+}  // namespace b200

@@ -651,6 +651,7 @@ void CoreParams::load(Image const& img)
             m.fluct.urban = F64("fluct.urban");
         }
         m.field.enabled = 0;
+        m.field.rz_values = nullptr;
         if (img.has("field.uniform") || img.has("field.rz_values"))
         {
             bool const rz = img.has("field.rz_values");
