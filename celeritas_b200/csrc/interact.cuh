@@ -1462,6 +1462,10 @@ B2_D real calc_hardwired_xs(ParamsView const& pv, u32 model, u32 material, real 
 }
 
 //! Dispatch the interaction for a model action (the reference's *Executor.hh)
+//! EXTRA: with the interactors beyond the north star's list (Rayleigh, Coulomb, muons). The
+//! fused step and the device-resident loop are built without them: carried along (even as
+//! out-of-line calls) they cost the TestEm3 pass 1.1 % (k_step_fused +4 %, measured).
+template<bool EXTRA>
 B2_D void run_interaction(ParamsView const& pv, StateView const& s, u32 slot, u32 action, Rng& rng)
 {
     ModelParams const& m = pv.model;
@@ -1517,8 +1521,10 @@ B2_D void run_interaction(ParamsView const& pv, StateView const& s, u32 slot, u3
         else
             result = interact_seltzer_berger(pv, particle, dir, material, element, rng);
     }
-    else if (action == m.muioni.bragg_action || action == m.muioni.icru73qo_action
-             || action == m.muioni.bethe_bloch_action || action == m.muioni.mu_bethe_bloch_action)
+    else if (EXTRA
+             && (action == m.muioni.bragg_action || action == m.muioni.icru73qo_action
+                 || action == m.muioni.bethe_bloch_action
+                 || action == m.muioni.mu_bethe_bloch_action))
     {
         int const sampler = action == m.muioni.mu_bethe_bloch_action ? MUHAD_MU_BETHE_BLOCH
                             : action == m.muioni.bethe_bloch_action  ? MUHAD_BETHE_BLOCH
@@ -1526,16 +1532,16 @@ B2_D void run_interaction(ParamsView const& pv, StateView const& s, u32 slot, u3
         result = interact_muhad_ionization(
             m.muioni, sampler, particle, cutoff_energy(pv, material, m.muioni.electron), dir, rng);
     }
-    else if (action == m.mubrems.action)
+    else if (EXTRA && action == m.mubrems.action)
     {
         result = interact_mu_bremsstrahlung(
             pv, particle, dir, material, element_of(s.element[slot]), rng);
     }
-    else if (action == m.coulomb.action)
+    else if (EXTRA && action == m.coulomb.action)
     {
         result = interact_coulomb(pv, particle, dir, material, element_of(s.element[slot]), rng);
     }
-    else if (action == m.rayleigh.action)
+    else if (EXTRA && action == m.rayleigh.action)
     {
         result = interact_rayleigh(
             m.rayleigh, particle.energy, dir, element_of(s.element[slot]), rng);

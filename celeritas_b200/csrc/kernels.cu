@@ -182,13 +182,15 @@ __global__ void __launch_bounds__(BLOCK) k_discrete_select(B2_GRID_CONSTANT Para
     select_and_append(p, s, active_slot(s, thread_id()));
 }
 
+template<bool EXTRA>
 __global__ void __launch_bounds__(BLOCK) k_interact(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 slot = active_slot(s, thread_id());
     if (slot != INVALID)
-        do_interact(p, s, slot);
+        do_interact<EXTRA>(p, s, slot);
 }
 
+template<bool EXTRA>
 __global__ void __launch_bounds__(BLOCK, B2_INTERACT_MIN_BLOCKS) k_interact_lists(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
 {
     u32 tid = thread_id();
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(BLOCK, B2_INTERACT_MIN_BLOCKS) k_interact_list
     }
     if (model == num_models || tid >= count)
         return;
-    do_interact(p, s, s.interact_list[size_t(model) * s.num_slots + tid]);
+    do_interact<EXTRA>(p, s, s.interact_list[size_t(model) * s.num_slots + tid]);
 }
 
 __global__ void __launch_bounds__(BLOCK) k_boundary(B2_GRID_CONSTANT ParamsView const p, B2_GRID_CONSTANT StateView const s)
@@ -603,11 +605,18 @@ int b200_step_interact(B200ParamsView const* params, B200StateView const* state,
         // lists built by this step's b200_step_discrete_select; segments are padded to
         // whole warps
         u32 const bound = active_hint(s) + 32 * PV(params).phys.num_models;
-        k_interact_lists<<<grid_for(bound), BLOCK, 0, stream>>>(PV(params), s);
+        if (PV(params).model.has_extra_models)
+            k_interact_lists<true><<<grid_for(bound), BLOCK, 0, stream>>>(PV(params), s);
+        else
+            k_interact_lists<false><<<grid_for(bound), BLOCK, 0, stream>>>(PV(params), s);
+    }
+    else if (PV(params).model.has_extra_models)
+    {
+        k_interact<true><<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s);
     }
     else
     {
-        k_interact<<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s);
+        k_interact<false><<<grid_for(active_hint(s)), BLOCK, 0, stream>>>(PV(params), s);
     }
     B2_COUNT(1);
     return check_launch();

@@ -37,6 +37,9 @@ extern "C" {
 int b200_step_fused(B200ParamsView const* params, B200StateView const* state, cudaStream_t stream)
 {
     StateView const& s = SV(state);
+    // built without the interactors beyond the core list (run_interaction<false>)
+    if (PV(params).model.has_extra_models)
+        return B200_ERR_INVALID_ARGUMENT;
     // Warps to spread the tracks over: one track per warp up to B200_SPREAD_WARPS warps
     // (default 8 per SM), never fewer than tracks / 32
     static u32 const spread_warps = [] {

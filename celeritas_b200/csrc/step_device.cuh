@@ -487,6 +487,7 @@ B2_D void select_and_append(ParamsView const& p, StateView const& s, u32 slot)
 //---------------------------------------------------------------------------//
 // post: every EM model (dispatch on the selected action id)
 //---------------------------------------------------------------------------//
+template<bool EXTRA>
 B2_D void do_interact(ParamsView const& p, StateView const& s, u32 slot)
 {
     if (s.status[slot] != ST_ALIVE)
@@ -496,7 +497,7 @@ B2_D void do_interact(ParamsView const& p, StateView const& s, u32 slot)
         return;
     Rng rng;
     rng.load(s, slot);
-    run_interaction(p, s, slot, action, rng);
+    run_interaction<EXTRA>(p, s, slot, action, rng);
     rng.store(s, slot);
 }
 
@@ -598,7 +599,7 @@ B2_D void step_fused_slot(ParamsView const& p, StateView const& s, u32 slot, boo
     }
     // pre_post, post
     do_discrete_select(p, s, slot);
-    do_interact(p, s, slot);
+    do_interact<false>(p, s, slot);
     do_boundary(p, s, slot);
     do_tracking_cut(p, s, slot);
     u8 const status = s.status[slot];

@@ -41,7 +41,8 @@ int b200_step_tail_loop(B200ParamsView const* params,
 {
     StateView const& s = SV(state);
     if (!s.run_vac_prefix || !s.run_vac_mask || !s.run_scan || !s.tail_reset_list || !s.tail_ctrl || !ring || !done
-        || num_blocks == 0 || max_iterations == 0 || s.num_slots % 32u != 0)
+        || num_blocks == 0 || max_iterations == 0 || s.num_slots % 32u != 0
+        || PV(params).model.has_extra_models)
         return B200_ERR_INVALID_ARGUMENT;
     static u32 const coop = [] {
         char const* env = std::getenv("B200_TAIL_COOP");

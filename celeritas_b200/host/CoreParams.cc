@@ -693,6 +693,12 @@ void CoreParams::load(Image const& img)
             m.field.max_nsteps = u.at(0);
             m.field.max_substeps = u.at(1);
         }
+        m.has_extra_models = m.rayleigh.action != INVALID || m.coulomb.action != INVALID
+                             || m.mubrems.action != INVALID
+                             || m.muioni.bragg_action != INVALID
+                             || m.muioni.icru73qo_action != INVALID
+                             || m.muioni.bethe_bloch_action != INVALID
+                             || m.muioni.mu_bethe_bloch_action != INVALID;
         // Every discrete model action must have an interactor here: an unclaimed one would
         // limit steps through its cross section and then do nothing at the interaction
         for (uint32_t a = view_.phys.model_to_action;

@@ -253,6 +253,9 @@ ActionSequence::ActionSequence(CoreParams const& params, Options options)
     // step/hit output is gathered after every iteration by the tally launch
     if (have_sort || params.hit_detector_of_volume())
         fusable_ = false;
+    // The fused step and the device-resident loop are built with the core interactors only
+    if (params.view().model.has_extra_models)
+        fusable_ = false;
     fuse_threshold_ = options.fuse_threshold ? options.fuse_threshold : default_fuse_threshold;
     if (char const* env = std::getenv("B200_FUSE_THRESHOLD"))
         fuse_threshold_ = static_cast<uint32_t>(std::strtoul(env, nullptr, 10));

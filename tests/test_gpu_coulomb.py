@@ -26,12 +26,13 @@ NAME = 'four-steel-slabs-coulomb'
 
 
 @pytest.mark.parametrize('slots,fuse', [(65536, 0), (1 << 18, NEVER_FUSE)],
-                         ids=['fused', 'per-action'])
+                         ids=['65536-slots', '262144-slots'])
 def test_lockstep_coulomb(slots, fuse):
     """The exported mean free path is ~1.7 m in steel, about 0.4 interactions per 10 GeV
-    shower: 128 showers (3.5 million track-steps) give a few dozen. With 65 536 slots every
-    iteration is one fused launch and primaries queue up; with 2^18 slots and fusing off
-    the interactions run over the per-model lists."""
+    shower: 128 showers (3.5 million track-steps) give a few dozen. Problems with this model
+    run one launch per action (the fused step carries the core interactors only): with
+    65 536 slots primaries queue up, with 2^18 slots all start at once; the interactions run
+    over the per-model lists."""
     import celeritas_b200 as cb
     import celerref
     from parity import compare_states

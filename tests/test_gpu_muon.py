@@ -25,7 +25,7 @@ NEVER_FUSE = 0xffffffff
 NAME = 'four-steel-slabs-muon'
 
 
-@pytest.mark.parametrize('fuse', [0, NEVER_FUSE], ids=['fused', 'per-action'])
+@pytest.mark.parametrize('fuse', [0, NEVER_FUSE], ids=['default', 'per-action'])
 def test_lockstep_muons(fuse):
     import celeritas_b200 as cb
     import celerref

@@ -3,7 +3,9 @@
 bundled four-steel-slabs export with its LivermoreRayleigh cross sections kept
 (tools/make_physics.py), in lock-step with the reference's host Stepper: integers and the
 six RNG words of every slot identical (the rejection loop draws 3 + 2 numbers per trial, so
-the words pin the accepted trial count), reals at 1e-7.
+the words pin the accepted trial count), reals at 1e-7. Problems with this model run one
+launch per action: the fused step and the device-resident loop are built with the core
+interactors only (csrc/interact.cuh: run_interaction<EXTRA>).
 """
 import json
 
@@ -35,7 +37,7 @@ def gammas(params, energies):
     return p
 
 
-@pytest.mark.parametrize('fuse', [0, NEVER_FUSE], ids=['fused', 'per-action'])
+@pytest.mark.parametrize('fuse', [0, NEVER_FUSE], ids=['default', 'per-action'])
 def test_lockstep_rayleigh(fuse):
     """Low-energy photons (20 keV .. 1 MeV; Rayleigh is ~10 % of the attenuation in steel at
     50 keV) through the four slabs; every Rayleigh interaction is counted from the
