@@ -225,7 +225,12 @@ void CoreParams::load(Image const& img)
         init_capacity_ = init.at(0);
         max_events_ = init.at(1);
         view_.scalars.track_order = init.at(2);
-        if (init.at(2) >= ORDER_SIZE_ || init.at(2) == ORDER_REINDEX_SHUFFLE)
+        // reindex_shuffle (CoreTrackData.cc:52-56, detail/TrackSlotUtils.cc:21-32) permutes
+        // the reference's thread -> slot map once at construction: which thread works on a
+        // slot changes, the slot's results do not. Here threads walk dense lists, so the
+        // order is accepted and every per-slot result equals the reference's
+        // (tests/test_gpu_track_order.py::test_reindex_shuffle_is_slot_identical).
+        if (init.at(2) >= ORDER_SIZE_)
             throw std::runtime_error("unsupported track_order in image");
     }
 
@@ -824,7 +829,7 @@ void CoreParams::max_events(uint32_t num_events)
 
 void CoreParams::track_order(uint32_t order)
 {
-    if (order >= ORDER_SIZE_ || order == ORDER_REINDEX_SHUFFLE)
+    if (order >= ORDER_SIZE_)
         throw std::runtime_error("unsupported track_order");
     // The reindex orders come with SortTracksAction entries in the action table
     // (CoreParams.cc:253-284 of the reference): they are a property of the exported image

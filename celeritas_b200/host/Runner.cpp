@@ -285,11 +285,10 @@ std::string celer_sim_run(std::string const& input_json)
         track_order = b200::ORDER_REINDEX_STEP_LIMIT_ACTION;
     else if (inp.track_order == "reindex_both_action")
         track_order = b200::ORDER_REINDEX_BOTH_ACTION;
+    else if (inp.track_order == "reindex_shuffle")
+        track_order = b200::ORDER_REINDEX_SHUFFLE;  // same per-slot results as "none"
     else
-    {
-        // reindex_shuffle is a std::shuffle of the slot map at construction: not reproduced
         throw std::runtime_error("track_order '" + inp.track_order + "' is not supported");
-    }
 
     // The problem image carries materials, physics tables and the action table; the GEOMETRY
     // is built here from `geometry_file` when that is an ORANGE JSON file that exists

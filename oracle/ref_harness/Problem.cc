@@ -565,6 +565,7 @@ std::unique_ptr<Problem> build_problem(json const& config)
         static std::map<std::string, TrackOrder> const orders{
             {"none", TrackOrder::none},
             {"init_charge", TrackOrder::init_charge},
+            {"reindex_shuffle", TrackOrder::reindex_shuffle},
             {"reindex_status", TrackOrder::reindex_status},
             {"reindex_particle_type", TrackOrder::reindex_particle_type},
             {"reindex_along_step_action", TrackOrder::reindex_along_step_action},

@@ -139,7 +139,7 @@ def test_celer_sim_input_validation_without_gpu():
              ({'geometry_file': None}, 'geometry_file'),
              ({'use_device': False}, 'no host track loop'),
              ({'max_steps': 0}, 'nonpositive max_steps'),
-             ({'track_order': 'reindex_shuffle'}, 'track_order'),
+             ({'track_order': 'reindex_everything'}, 'track_order'),
              ({'mctruth_file': 'out.root'}, 'outside the scope'),
              ({'_format': 'other'}, 'invalid format')]
     for change, fragment in cases:

@@ -75,3 +75,23 @@ def test_rayleigh_with_showers():
     hist = lockstep(ref, gpu, prim, compare_every=1)
     assert sum(h['active'] for h in hist) > 3000
     assert np.allclose(refp.calo(4), gpu.calo(), rtol=1e-9, atol=1e-9)
+
+
+def test_fused_step_refuses_problems_with_extra_models():
+    """The fused step (and the device-resident loop) are built with the core interactors
+    only: the launcher refuses a problem that has Rayleigh / Coulomb / muon models instead of
+    stepping it with an interactor missing, and the Stepper runs such problems one launch
+    per action whatever the fuse threshold (both configurations above reproduce the
+    reference)."""
+    import ctypes as C
+    import celeritas_b200 as cb
+    L = cb.load_library()
+    params = cb.Params(data_path('images', NAME + '.b2img'))
+    state = C.c_void_p()
+    assert L.b200_state_create(params.h, 0, 256, C.byref(state)) == 0
+    try:
+        L.b200_step_fused.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = L.b200_step_fused(L.b200_params_view(params.h), L.b200_state_view(state), None)
+        assert rc == 10001  # B200_ERR_INVALID_ARGUMENT
+    finally:
+        L.b200_state_destroy(state)

@@ -129,6 +129,48 @@ def test_celer_sim_accepts_reindex_orders(tmp_path):
     with pytest.raises(cb.B200Error) as e:
         cb.celer_sim_run(inp)
     assert 'sort' in str(e.value)
-    inp['track_order'] = 'reindex_shuffle'
+    inp['track_order'] = 'reindex_everything'
     with pytest.raises(cb.B200Error):
         cb.celer_sim_run(inp)
+
+
+def test_reindex_shuffle_is_slot_identical():
+    """TrackOrder::reindex_shuffle: the reference shuffles its thread -> slot map once at
+    construction (global/CoreTrackData.cc:52-56, detail/TrackSlotUtils.cc:21-32: std::shuffle
+    with mt19937 seeded by the slot count). Which thread works on a slot changes; what happens
+    in the slot does not. The reference built with that order is compared slot by slot with
+    this library running the stock image (threads walk dense lists here, there is no
+    thread -> slot map to shuffle), and celer-sim accepts the value."""
+    import celeritas_b200 as cb
+    import celerref
+    from parity import lockstep
+    cfg = json.load(open(data_path('images', 'testem3-small.json')))
+    ref_problem = celerref.Problem(dict(cfg, track_order='reindex_shuffle'))
+    slots = 4096
+    ref = ref_problem.stepper(slots)
+    shuffled = ref.get('track_slots')
+    assert np.array_equal(np.sort(shuffled), np.arange(slots))
+    assert not np.array_equal(shuffled, np.arange(slots))
+    params = cb.Params(data_path('images', 'testem3-small.b2img'))
+    gpu = cb.Stepper(params, slots)
+    prim = cb.make_primaries(3, particle_id=params.find_particle(11), energy=1000.0,
+                             pos=(-22, 0, 0), direction=(1, 0, 0))
+    hist = lockstep(ref, gpu, prim, compare_every=3)
+    assert sum(h['active'] for h in hist) > 20000
+    assert np.allclose(ref_problem.calo(100), gpu.calo(), rtol=1e-9, atol=1e-9)
+
+    from conftest import REPO
+    inp = {'_format': 'celer-sim', 'use_device': True, 'base_dir': REPO,
+           'image_file': 'data/images/testem3-small.b2img',
+           'geometry_file': cfg['geometry_file'], 'physics_file': cfg['physics_file'],
+           'seed': cfg['seed'], 'num_track_slots': 1024,
+           'initializer_capacity': cfg['initializer_capacity'], 'secondary_stack_factor': 3,
+           'simple_calo': cfg['simple_calo'], 'track_order': 'reindex_shuffle',
+           'primary_options': {'seed': 0, 'pdg': [11], 'num_events': 1, 'primaries_per_event': 2,
+                               'energy': {'distribution': 'delta', 'params': [100.0]},
+                               'position': {'distribution': 'delta', 'params': [-22, 0, 0]},
+                               'direction': {'distribution': 'delta', 'params': [1, 0, 0]}}}
+    report = cb.celer_sim_run(inp)
+    assert report['input']['track_order'] == 'reindex_shuffle'
+    none = cb.celer_sim_run(dict(inp, track_order='none'))
+    assert report['result']['runner']['num_steps'] == none['result']['runner']['num_steps']
