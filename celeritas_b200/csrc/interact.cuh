@@ -1462,7 +1462,8 @@ B2_D real calc_hardwired_xs(ParamsView const& pv, u32 model, u32 material, real 
 }
 
 //! Dispatch the interaction for a model action (the reference's *Executor.hh)
-//! EXTRA: with the interactors beyond the north star's list (Rayleigh, Coulomb, muons). The
+//! EXTRA: with the interactors beyond the north star's list (Rayleigh, Coulomb, muons) and
+//! the combined bremsstrahlung model, which no benchmark problem has. The
 //! fused step and the device-resident loop are built without them: carried along (even as
 //! out-of-line calls) they cost the TestEm3 pass 1.1 % (k_step_fused +4 %, measured).
 template<bool EXTRA>
@@ -1509,8 +1510,10 @@ B2_D void run_interaction(ParamsView const& pv, StateView const& s, u32 slot, u3
         result = interact_relativistic_brem(
             pv, particle, dir, material, element_of(s.element[slot]), rng);
     }
-    else if (action == m.cb.action)
+    else if (EXTRA && action == m.cb.action)
     {
+        // (EXTRA: a second inlined copy of both bremsstrahlung samplers, used only by
+        // problems built with celer-sim's `brem_combined`)
         // em/interactor/CombinedBremInteractor.hh:132-170: relativistic sampler at and above
         // 1 GeV, Seltzer-Berger below; same angular distribution and final state either way
         // The combined model has no element selector: its executor always interacts with the

@@ -70,7 +70,7 @@ B2_D SurfaceRef get_surface(GeoParams const& g, SimpleUnit const& u, u32 local_s
     return s;
 }
 
-B2_D int surface_sense(SurfaceRef const& s, Real3 const& pos)
+B2_D int surface_sense_all(SurfaceRef const& s, Real3 const& pos)
 {
     real const* d = s.d;
     switch (s.type)
@@ -223,7 +223,7 @@ B2_D int surface_num_isect(u8 type)
 }
 
 //! Distances to a surface along (pos, dir); roots are +inf when absent
-B2_D Roots surface_intersect(SurfaceRef const& s, Real3 const& pos, Real3 const& dir, bool on_surface)
+B2_D Roots surface_intersect_all(SurfaceRef const& s, Real3 const& pos, Real3 const& dir, bool on_surface)
 {
     real const* d = s.d;
     Roots none;
@@ -390,14 +390,14 @@ B2_D bool surface_simple_safety(u8 type)
 }
 
 //! Safety distance to one surface (CalcSafetyDistance, SurfaceFunctors.hh)
-B2_D real surface_safety(SurfaceRef const& s, Real3 const& pos)
+B2_D real surface_safety_all(SurfaceRef const& s, Real3 const& pos)
 {
     if (!surface_simple_safety(s.type))
         return 0;
     Real3 dir = surface_normal(s, pos);
     if (isnan(dir[0]))
         return real_inf();
-    int sense = surface_sense(s, pos);
+    int sense = surface_sense_all(s, pos);
     if (sense > 0)
     {
         dir[0] *= -1;
@@ -408,10 +408,204 @@ B2_D real surface_safety(SurfaceRef const& s, Real3 const& pos)
     {
         return 0;
     }
-    Roots r = surface_intersect(s, pos, dir, false);
+    Roots r = surface_intersect_all(s, pos, dir, false);
     if (surface_num_isect(s.type) == 1)
         return r.r[0];
     return r.r[1] < r.r[0] ? r.r[1] : r.r[0];
+}
+
+// Surface dispatch by frequency. Every call site of the three functions below inlines what
+// it calls: with all 17 quadric types inline, surface code was 53 % of the fused step's
+// 61 k SASS instructions (quad_solve_off alone 10 %), and a kernel waiting on instruction
+// fetch pays for code it never runs (profiles/README_r02.md). B2_SURF_OUTLINE:
+//   0  everything inline (the round-1 layout)
+//   1  axis-aligned planes, centred axis-aligned cylinders and general planes inline (what
+//      TestEm3, simple-CMS and the CMS-scale geometry are made of); spheres, off-axis
+//      cylinders, cones, simple and general quadrics are ONE out-of-line copy per kernel
+//   2  only the axis-aligned planes inline
+// Same arithmetic either way (the out-of-line functions call the full implementations).
+#ifndef B2_SURF_OUTLINE
+#    define B2_SURF_OUTLINE 1
+#endif
+
+B2_D bool surface_is_inline_type(u8 type)
+{
+#if B2_SURF_OUTLINE == 0
+    return true;
+#elif B2_SURF_OUTLINE == 1
+    return type <= SURF_CZC || type == SURF_P;
+#else
+    return type <= SURF_PZ;
+#endif
+}
+
+B2_NOINLINE inline int surface_sense_general(u32 type, real const* d, real x, real y, real z)
+{
+    SurfaceRef s;
+    s.type = static_cast<u8>(type);
+    s.d = d;
+    return surface_sense_all(s, make_real3(x, y, z));
+}
+
+B2_NOINLINE inline Roots surface_intersect_general(
+    u32 type, real const* d, real x, real y, real z, real dx, real dy, real dz, bool on_surface)
+{
+    SurfaceRef s;
+    s.type = static_cast<u8>(type);
+    s.d = d;
+    return surface_intersect_all(s, make_real3(x, y, z), make_real3(dx, dy, dz), on_surface);
+}
+
+B2_NOINLINE inline real surface_safety_general(u32 type, real const* d, real x, real y, real z)
+{
+    SurfaceRef s;
+    s.type = static_cast<u8>(type);
+    s.d = d;
+    return surface_safety_all(s, make_real3(x, y, z));
+}
+
+B2_D real select_axis(Real3 const& v, int axis)
+{
+    return axis == 0 ? v[0] : axis == 1 ? v[1] : v[2];
+}
+
+B2_D int surface_sense(SurfaceRef const& s, Real3 const& pos)
+{
+#if B2_SURF_OUTLINE == 0
+    return surface_sense_all(s, pos);
+#else
+    real const* d = s.d;
+    if (s.type <= SURF_PZ)
+        return real_to_sense(select_axis(pos, s.type) - d[0]);
+#    if B2_SURF_OUTLINE == 1
+    if (s.type <= SURF_CZC)
+    {
+        int const T = s.type - SURF_CXC;
+        real const u = T == 0 ? pos[1] : pos[0];
+        real const v = T == 2 ? pos[1] : pos[2];
+        return real_to_sense(ipow2(u) + ipow2(v) - d[0]);
+    }
+    if (s.type == SURF_P)
+    {
+        Real3 n = make_real3(d[0], d[1], d[2]);
+        return real_to_sense(dot(n, pos) - d[3]);
+    }
+#    endif
+    return surface_sense_general(s.type, d, pos[0], pos[1], pos[2]);
+#endif
+}
+
+B2_D Roots surface_intersect(SurfaceRef const& s, Real3 const& pos, Real3 const& dir, bool on_surface)
+{
+#if B2_SURF_OUTLINE == 0
+    return surface_intersect_all(s, pos, dir, on_surface);
+#else
+    real const* d = s.d;
+    if (s.type <= SURF_PZ)
+    {
+        Roots none;
+        none.r[0] = real_inf();
+        none.r[1] = real_inf();
+        real const n_dir = select_axis(dir, s.type);
+        if (!on_surface && n_dir != 0)
+        {
+            real dist = (d[0] - select_axis(pos, s.type)) / n_dir;
+            if (dist > 0)
+                none.r[0] = dist;
+        }
+        return none;
+    }
+#    if B2_SURF_OUTLINE == 1
+    if (s.type <= SURF_CZC)
+    {
+        Roots none;
+        none.r[0] = real_inf();
+        none.r[1] = real_inf();
+        int const T = s.type - SURF_CXC;
+        int const U = (T == 0) ? 1 : 0;
+        int const V = (T == 2) ? 1 : 2;
+        real const a = 1 - ipow2(select_axis(dir, T));
+        if (a < MIN_A)
+            return none;
+        real const u = select_axis(pos, U), v = select_axis(pos, V);
+        real const half_b = select_axis(dir, U) * u + select_axis(dir, V) * v;
+        return quad_solve(a, half_b, ipow2(u) + ipow2(v) - d[0], on_surface);
+    }
+    if (s.type == SURF_P)
+    {
+        Roots none;
+        none.r[0] = real_inf();
+        none.r[1] = real_inf();
+        Real3 n = make_real3(d[0], d[1], d[2]);
+        real n_dir = dot(n, dir);
+        if (!on_surface && n_dir != 0)
+        {
+            real n_pos = dot(n, pos);
+            real dist = (d[3] - n_pos) / n_dir;
+            if (dist > 0)
+                none.r[0] = dist;
+        }
+        return none;
+    }
+#    endif
+    return surface_intersect_general(
+        s.type, d, pos[0], pos[1], pos[2], dir[0], dir[1], dir[2], on_surface);
+#endif
+}
+
+B2_D real surface_safety(SurfaceRef const& s, Real3 const& pos)
+{
+#if B2_SURF_OUTLINE == 0
+    return surface_safety_all(s, pos);
+#else
+    if (s.type <= SURF_PZ)
+    {
+        // CalcSafetyDistance for an axis-aligned plane: the distance along the normal
+        real const p = select_axis(pos, s.type);
+        int const sense = real_to_sense(p - s.d[0]);
+        if (sense == 0)
+            return 0;
+        real const n_dir = sense > 0 ? real(-1) : real(1);
+        real const dist = (s.d[0] - p) / n_dir;
+        return dist > 0 ? dist : real_inf();
+    }
+#    if B2_SURF_OUTLINE == 1
+    if (s.type <= SURF_CZC || s.type == SURF_P)
+    {
+        // surface_safety_all for these types, with the inline sense / intersection
+        Real3 dir;
+        if (s.type == SURF_P)
+        {
+            dir = make_real3(s.d[0], s.d[1], s.d[2]);
+        }
+        else
+        {
+            int const T = s.type - SURF_CXC;
+            dir = make_unit_vector(make_real3(T == 0 ? real(0) : pos[0],
+                                              T == 1 ? real(0) : pos[1],
+                                              T == 2 ? real(0) : pos[2]));
+        }
+        if (isnan(dir[0]))
+            return real_inf();
+        int const sense = surface_sense(s, pos);
+        if (sense > 0)
+        {
+            dir[0] *= -1;
+            dir[1] *= -1;
+            dir[2] *= -1;
+        }
+        else if (sense == 0)
+        {
+            return 0;
+        }
+        Roots const r = surface_intersect(s, pos, dir, false);
+        if (s.type == SURF_P)
+            return r.r[0];
+        return r.r[1] < r.r[0] ? r.r[1] : r.r[0];
+    }
+#    endif
+    return surface_safety_general(s.type, s.d, pos[0], pos[1], pos[2]);
+#endif
 }
 
 //---------------------------------------------------------------------------//

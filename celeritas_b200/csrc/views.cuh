@@ -484,7 +484,7 @@ struct ModelParams
     CoulombParams coulomb;
     MuHadIonizationParams muioni;
     MuBremsstrahlungParams mubrems;
-    // any of rayleigh / coulomb / muioni / mubrems present: their interactors are compiled
+    // any of cb / rayleigh / coulomb / muioni / mubrems present: their interactors are compiled
     // only into the per-action interaction kernels (run_interaction<true>), and such problems
     // do not use the fused step or the device-resident loop
     u32 has_extra_models;

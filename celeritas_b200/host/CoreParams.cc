@@ -698,7 +698,8 @@ void CoreParams::load(Image const& img)
             m.field.max_nsteps = u.at(0);
             m.field.max_substeps = u.at(1);
         }
-        m.has_extra_models = m.rayleigh.action != INVALID || m.coulomb.action != INVALID
+        m.has_extra_models = m.cb.action != INVALID || m.rayleigh.action != INVALID
+                             || m.coulomb.action != INVALID
                              || m.mubrems.action != INVALID
                              || m.muioni.bragg_action != INVALID
                              || m.muioni.icru73qo_action != INVALID
