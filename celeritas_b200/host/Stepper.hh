@@ -102,7 +102,10 @@ class ActionSequence
     //! costs what the host round trip does)
     static constexpr uint32_t default_tail_threshold = 256;
     //! Default of Options::fuse_threshold (measured: profiles/README_r01.md)
-    static constexpr uint32_t default_fuse_threshold = 65536;
+    // Swept on the final code (profiles/fuse_sweep_r02*.log): a plateau from 16 384 to
+    // 32 768 tracks (TestEm3 89.4 ms, CMS-scale 337 ms per pass) against 90.7 / 342.8 ms at
+    // the 65 536 that was best before the per-action kernels lost a quarter of their code
+    static constexpr uint32_t default_fuse_threshold = 24576;
     //! Build the B200 adapters for every step action in the problem's table
     explicit ActionSequence(CoreParams const& params) : ActionSequence(params, Options{}) {}
     ActionSequence(CoreParams const& params, Options options);
