@@ -195,3 +195,28 @@ def test_compiled_dropin_uses_only_the_declared_cabi():
     out = subprocess.run(['nm', '-DC', lib], capture_output=True, text=True, check=True).stdout
     assert 'celeritas::ActionSequence::step' in out
     assert 'celeritas_b200_adapter::B200StepAction' in out
+
+
+def test_coulomb_fixture_is_defined_below_the_model_limit():
+    """tools/make_physics.py::extend_coulomb_down: the exported eCoulombScattering tables
+    start at 100 MeV; the fixture continues them to 1e-4 MeV on the same logarithmic spacing
+    with zero macroscopic cross section (the reference extrapolates a grid flat below its
+    first node and would then select a process with no applicable model)."""
+    import math
+    d = json.load(open(data_path('physics', 'four-steel-slabs-em-coulomb.json')))
+    procs = [p for p in d['processes'] if p['process_class'] == 6]
+    assert {p['particle_pdg'] for p in procs} == {11, -11}
+    for p in procs:
+        for t in p['tables']:
+            for v in t['physics_vectors']:
+                x, y = v['x'], v['y']
+                assert x[0] == pytest.approx(1e-4) and x[-1] == pytest.approx(1e8)
+                steps = [math.log(b / a) for a, b in zip(x, x[1:])]
+                assert max(steps) - min(steps) < 1e-9
+                below = [yy for xx, yy in zip(x, y) if xx < 99.9]
+                assert below and all(yy == 0 for yy in below)
+                assert all(yy > 0 for xx, yy in zip(x, y) if xx > 99.9)
+        for m in p['models']:
+            for mm in m['materials']:
+                assert mm['energy'][0] == pytest.approx(1e-4)
+                assert all(len(xs) == len(mm['energy']) for xs in mm['micro_xs'])
